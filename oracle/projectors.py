@@ -1,0 +1,134 @@
+"""Oracle restatement of the projectors / proximal maps on the hot path (TEST INFRASTRUCTURE ONLY).
+
+Follows /root/reference/src/projectors/project_bounds!.jl:3-25, project_l1_Duchi!.jl:21-52,
+project_l2!.jl:3-16, project_annulus!.jl:3-21, project_cardinality!.jl:3-21, prox_l2s!.jl:3-6,
+prox_l1!.jl:8-10.  All functions mutate their first argument in place and return it, like the
+Julia `!` functions.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .sip_types import norm1, norm2
+
+
+def project_bounds(x: np.ndarray, LB, UB) -> np.ndarray:
+    """Scalar bounds: x[j] = max(LB, min(x[j], UB)) (project_bounds!.jl:3-12);
+    vector bounds: min then max (project_bounds!.jl:14-25)."""
+    TF = x.dtype.type
+    if np.ndim(LB) == 0:
+        np.minimum(x, TF(UB), out=x)
+        np.maximum(x, TF(LB), out=x)
+    else:
+        np.minimum(x, np.asarray(UB, dtype=TF), out=x)
+        np.maximum(np.asarray(LB, dtype=TF), x, out=x)
+    return x
+
+
+def _accumulate_pairwise(c: np.ndarray, v: np.ndarray, s, i1: int, n: int):
+    """Julia Base._accumulate_pairwise!(+, c, v, s, i1, n) (base/accumulate.jl; Julia >= 1.0):
+    pairwise cumulative sum with leaves of fewer than 128 elements.  `cumsum!` on a Float vector
+    dispatches here (project_l1_Duchi!.jl:38).  Third-party (Julia Base) arithmetic restated."""
+    TF = c.dtype.type
+    if n < 128:
+        loc = np.cumsum(v[i1:i1 + n], dtype=TF)     # s_ = op(s_, v[i]) sequentially in TF
+        c[i1:i1 + n] = s + loc                      # c[i] = op(s, s_)
+        return loc[-1]
+    n2 = n >> 1
+    s_ = _accumulate_pairwise(c, v, s, i1, n2)
+    s_ = s_ + _accumulate_pairwise(c, v, s + s_, i1 + n2, n - n2)
+    return s_
+
+
+def julia_cumsum(v: np.ndarray) -> np.ndarray:
+    """cumsum!(sv, u) for a Float vector: c[1]=v[1], then pairwise accumulate of the rest."""
+    TF = v.dtype.type
+    c = np.empty_like(v)
+    n = v.size
+    if n == 0:
+        return c
+    # Base._accumulate1!: c[1] = v[1]; _accumulate_pairwise!(op, c, v, v1, 2, n-1)
+    c[0] = v[0]
+    if n > 1:
+        with np.errstate(over="ignore"):
+            _accumulate_pairwise(c, v, TF(v[0]), 1, n - 1)
+    return c
+
+
+def project_l1_Duchi(v: np.ndarray, b) -> np.ndarray:
+    """project_l1_Duchi!.jl:21-52 (real vectors)."""
+    TF = v.dtype.type
+    b = TF(b)
+    if b <= TF(0):
+        raise ValueError("Radius of L1 ball is negative")          # :22
+    if norm1(v) <= b:                                               # :23
+        return v
+    lv = v.size
+    u = np.sort(np.abs(v))[::-1].copy()                             # :30-37 (sort order is alg-independent)
+    sv = julia_cumsum(u)                                            # :38
+    # :41-44  while u[rho+1] > ((sv[rho+1]-b)/(rho+1)) && (rho+1) < lv; rho += 1
+    j = np.arange(1, lv + 1).astype(TF)
+    cond = u > (sv - b) / j
+    rho = int(np.argmin(cond)) if not cond.all() else lv            # number of leading trues
+    rho = min(rho, lv - 1)
+    rho = max(1, rho)                                               # :45
+    theta = max(TF(0), (sv[rho - 1] - b) / TF(rho))                 # :46
+    theta = TF(theta)
+    v[:] = np.sign(v) * np.maximum(np.abs(v) - theta, TF(0))        # :49
+    return v
+
+
+def project_l2(x: np.ndarray, sigma) -> np.ndarray:
+    """project_l2!.jl:3-16."""
+    TF = x.dtype.type
+    sigma = TF(sigma)
+    nl2 = norm2(x)
+    if nl2 <= sigma:
+        return x
+    x *= TF(sigma / nl2)
+    return x
+
+
+def project_annulus(x: np.ndarray, sigma_min, sigma_max) -> np.ndarray:
+    """project_annulus!.jl:3-21."""
+    TF = x.dtype.type
+    sigma_min, sigma_max = TF(sigma_min), TF(sigma_max)
+    nl2 = norm2(x)
+    if sigma_min <= nl2 <= sigma_max:
+        return x
+    if nl2 > sigma_max:
+        x *= TF(sigma_max / nl2)
+    elif nl2 < sigma_min and nl2 > 0:
+        x *= TF(sigma_min / nl2)
+    elif nl2 < sigma_min and nl2 == 0:
+        # ones(TF,n) .* (sigma_min ./ sqrt(length(x))): sqrt(Int) is Float64, rounded to TF by copy!
+        x[:] = TF(np.float64(sigma_min) / np.sqrt(np.float64(x.size)))
+    return x
+
+
+def project_cardinality(x: np.ndarray, k: int) -> np.ndarray:
+    """project_cardinality!.jl:3-21: sort_ind = sortperm(x, by=abs, rev=true) (stable => among equal
+    magnitudes the lower index ranks first and is kept); x[sort_ind[k+1:end]] .= 0."""
+    TF = x.dtype.type
+    k = int(k)
+    sort_ind = np.argsort(-np.abs(x), kind="stable")
+    x[sort_ind[k:]] = TF(0.0)
+    return x
+
+
+def prox_l2s(x: np.ndarray, rho, m: np.ndarray) -> np.ndarray:
+    """prox_l2s!.jl:3-6:  x .= (x .* rho .+ m) ./ (rho .+ 1.0)  — the literal 1.0 is Float64, so the
+    division runs in Float64 and the result is rounded to TF on assignment."""
+    TF = x.dtype.type
+    num = x * TF(rho) + m                                       # TF
+    den = np.float64(TF(rho)) + np.float64(1.0)                 # Float64
+    x[:] = (num.astype(np.float64) / den).astype(TF)
+    return x
+
+
+def prox_l1(x: np.ndarray, rho) -> np.ndarray:
+    """prox_l1!.jl:8-10: x .= sign.(x) .* max.(0, abs.(x) .- (1 ./ rho))."""
+    TF = x.dtype.type
+    thr = TF(TF(1) / TF(rho))          # 1 ./ rho : Int / TF -> TF
+    x[:] = np.sign(x) * np.maximum(TF(0.0), np.abs(x) - thr)
+    return x
