@@ -1,0 +1,199 @@
+/*
+ * sipb200.h — C ABI of the B200-native PARSDMM projection iteration.
+ *
+ * Drop-in boundary for the hot path of slimgroup/SetIntersectionProjection.jl (pure Julia): the
+ * Julia (or Python) host keeps the reference API and `ccall`s / `ctypes`-calls these entry points.
+ * Every entry point cites the reference routine it replaces (paths relative to the reference's
+ * src/).  Plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *
+ * Conventions
+ *   - every function returns SIPB_OK (0) or a negative error code and never throws;
+ *     sipb_last_error() returns a thread-local message for the last failure;
+ *   - `dtype`: SIPB_F32 (Float32) or SIPB_F64 (Float64) — the reference's TF;
+ *   - vectors are column-major vec(model): linear index i + n1*(j + n2*k) (get_discrete_Grad.jl:63);
+ *   - host arrays stay owned by the caller; device memory is owned by the ctx / problem;
+ *   - one host thread drives one GPU (one process per GPU; multi-GPU slabs use sipb_comm_*).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     SIPB_E_CUDA.
+ */
+#ifndef SIPB200_H
+#define SIPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SIPB_ABI_VERSION 1
+
+/* error codes */
+#define SIPB_OK             0
+#define SIPB_E_INVALID     -1   /* bad argument / inconsistent sizes                           */
+#define SIPB_E_UNSUPPORTED -2   /* set / operator / option outside the device hot path          */
+#define SIPB_E_CUDA        -3   /* CUDA runtime failure (incl. "no device")                      */
+#define SIPB_E_NCCL        -4
+#define SIPB_E_STATE       -5   /* call order violated (e.g. solve before finalize)              */
+#define SIPB_E_MISSING_DIAG -6  /* CDS_scaled_add!.jl:18-20: diagonal of AtA_i missing in Q      */
+
+#define SIPB_F32 0
+#define SIPB_F64 1
+
+/* projector / prox kinds (get_projector.jl:3-103, prox_l2s!.jl, prox_l1!.jl) */
+#define SIPB_SET_BOUNDS_SCALAR 0   /* project_bounds!.jl:3-12   */
+#define SIPB_SET_BOUNDS_VECTOR 1   /* project_bounds!.jl:14-25  */
+#define SIPB_SET_L1            2   /* project_l1_Duchi!.jl:21-52 */
+#define SIPB_SET_L2            3   /* project_l2!.jl:3-16       */
+#define SIPB_SET_ANNULUS       4   /* project_annulus!.jl:3-21  */
+#define SIPB_SET_CARDINALITY   5   /* project_cardinality!.jl:3-21 (vector mode) */
+#define SIPB_SET_PROX_L1       6   /* prox_l1!.jl:8-10 (set_type "prox_l1", get_projector.jl:21-27) */
+#define SIPB_SET_DISTANCE      7   /* prox_l2s!.jl:3-6: the 1/2||x-m||^2 term (PARSDMM_initialize.jl:64-71) */
+
+/* transform-domain operator kinds (get_TD_operator.jl:12-95, get_discrete_Grad.jl) */
+#define SIPB_OP_IDENTITY 0
+#define SIPB_OP_DX       1   /* first (fastest) axis  : offset 1        */
+#define SIPB_OP_DY       2   /* second axis (3-D only): offset n1       */
+#define SIPB_OP_DZ       3   /* last axis             : offset n1 (2-D) or n1*n2 (3-D) */
+#define SIPB_OP_TV       4   /* vcat(D_z[,D_y],D_x)   (get_discrete_Grad.jl:33,69-72)  */
+#define SIPB_OP_DXZ      5   /* D_z*D_x, 2-D only     (get_TD_operator.jl:69-73)       */
+
+/* Minkowski block placement of an operator (PARSDMM_precompute_distribute_Minkowski.jl:78-88) */
+#define SIPB_BLOCK_PLAIN 0   /* A       (N columns)  */
+#define SIPB_BLOCK_LEFT  1   /* [A 0]   (2N columns) */
+#define SIPB_BLOCK_RIGHT 2   /* [0 A]                */
+#define SIPB_BLOCK_BOTH  3   /* [A A]                */
+
+typedef struct sipb_ctx sipb_ctx;
+typedef struct sipb_problem sipb_problem;
+
+/* One term of the intersection: projector + operator.  Replaces one entry of the reference's
+ * (P_sub[i], TD_OP[i], set_Prop.*[i]) triple (setup_constraints.jl:17-102). */
+typedef struct sipb_set_desc {
+  int32_t set_kind;        /* SIPB_SET_*                                                       */
+  int32_t op_kind;         /* SIPB_OP_*                                                        */
+  int32_t block_mode;      /* SIPB_BLOCK_*                                                     */
+  int32_t ncvx;            /* set_Prop.ncvx[i] (setup_constraints.jl:89-97)                    */
+  double  min;             /* scalar lower bound / annulus sigma_min                           */
+  double  max;             /* scalar upper bound / l1 tau / l2 sigma / prox_l1 rho             */
+  int64_t k;               /* cardinality                                                      */
+  const void* min_vec;     /* host TF[M] for SIPB_SET_BOUNDS_VECTOR, else NULL                 */
+  const void* max_vec;
+} sipb_set_desc;
+
+/* Mirror of PARSDMM_options (SetIntersectionProjection.jl:110-128) after convert_options!. */
+typedef struct sipb_options {
+  int32_t maxit;
+  int32_t rho_update_frequency;
+  int32_t adjust_rho;
+  int32_t adjust_gamma;
+  int32_t adjust_feasibility_rho;
+  int32_t zero_ini_guess;
+  int32_t n_rho_ini;            /* 1 or p                                                       */
+  int32_t profile_kernels;      /* 1: bracket every launch with CUDA events (kernel table below) */
+  double  evol_rel_tol;         /* already rounded to TF by the host                            */
+  double  feas_tol;
+  double  obj_tol;
+  double  gamma_ini;
+  const double* rho_ini;        /* n_rho_ini values, already rounded to TF                      */
+  int32_t fixed_iterations;     /* >0: ignore the stop rules and run exactly this many iterations (benchmarks) */
+  int32_t return_ly;            /* 1: copy l and y back to the host arrays                      */
+} sipb_options;
+
+#define SIPB_N_PHASES 7         /* TimerOutputs sections of PARSDMM.jl:40,100,105,113,152,163,229 */
+#define SIPB_N_KERNEL_CLASSES 24
+
+/* Mirror of log_type_PARSDMM (SetIntersectionProjection.jl:95-108).  The caller allocates every
+ * array with `maxit` rows (row-major [maxit][p] / [maxit][pp]); the solver fills rows 0..iters-1
+ * (set_feasibility rows 0..feas_rows-1), exactly the rows output_check_PARSDMM keeps
+ * (PARSDMM.jl:261-278). */
+typedef struct sipb_log {
+  int32_t iters;                /* number of PARSDMM iterations performed (0 if input was feasible) */
+  int32_t feas_rows;            /* rows of set_feasibility that are meaningful (= `counter`)        */
+  int32_t stopped_feasible;     /* 1: PARSDMM_initialize found the input feasible (PARSDMM.jl:63-82) */
+  int32_t p, pp;
+  double* set_feasibility;      /* [maxit][pp] */
+  double* r_dual;               /* [maxit][p]  */
+  double* r_pri;                /* [maxit][p]  */
+  double* r_dual_total;         /* [maxit]     */
+  double* r_pri_total;
+  double* obj;
+  double* evol_x;
+  double* rho;                  /* [maxit][p]  */
+  double* gamma;                /* [maxit][p]  */
+  int32_t* cg_it;               /* [maxit]     */
+  double* cg_relres;
+  double  phase_seconds[SIPB_N_PHASES];   /* host wall time per TimerOutputs section, same order   */
+  double  solve_seconds;                  /* whole sipb_solve call incl. H2D/D2H                    */
+  double  device_seconds;                 /* CUDA-event time of the iteration loop on the stream    */
+  /* kernel table (profile_kernels=1): launches and summed CUDA-event milliseconds per class */
+  int64_t kernel_launches[SIPB_N_KERNEL_CLASSES];
+  double  kernel_ms[SIPB_N_KERNEL_CLASSES];
+  int64_t total_launches;                 /* all kernel launches inside sipb_solve (always counted) */
+  int64_t h2d_bytes, d2h_bytes;
+} sipb_log;
+
+/* ---- library / context ------------------------------------------------------------------- */
+int         sipb_abi_version(void);
+const char* sipb_last_error(void);
+const char* sipb_kernel_class_name(int cls);          /* name of kernel class 0..SIPB_N_KERNEL_CLASSES-1 */
+int sipb_ctx_create(int device, sipb_ctx** out);      /* binds the calling process to `device`   */
+int sipb_ctx_destroy(sipb_ctx* ctx);
+int sipb_ctx_num_sms(sipb_ctx* ctx, int* out);
+
+/* ---- multi-GPU slabs (one process per GPU).  Replaces the reference's Distributed/DArray
+ *      set-parallelism (update_y_l_parallel.jl, adapt_rho_gamma_parallel.jl) by z-slab domain
+ *      decomposition; the 128-byte NCCL unique id travels over the host's own transport
+ *      (torch.distributed / MPI / Julia Distributed). ------------------------------------------ */
+int sipb_comm_unique_id(void* out128);
+int sipb_comm_init(sipb_ctx* ctx, int rank, int world, const void* uid128);
+
+/* ---- problem set-up: replaces the device-relevant part of PARSDMM_precompute_distribute.jl:6-77
+ *      and the allocation / Q assembly of PARSDMM_initialize.jl:117-230 ---------------------- */
+int sipb_problem_create(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const double* h,
+                        int minkowski, int feasibility_only, sipb_problem** out);
+/* sets must be added in TD_OP order; the distance term (SIPB_SET_DISTANCE) last. */
+int sipb_problem_add_set(sipb_problem* pb, const sipb_set_desc* desc);
+/* AtA[i] in CDS form exactly as mat2CDS (mat2CDS.jl:7-32) returns it: R is column-major
+ * [rows x nd] host TF, offsets int64[nd] ascending. */
+int sipb_problem_set_ata(sipb_problem* pb, int set_index, const void* R, int64_t rows,
+                         const int64_t* offsets, int nd);
+/* uploads, builds Q_offsets in the reference's order (PARSDMM_initialize.jl:217-221). */
+int sipb_problem_finalize(sipb_problem* pb);
+int sipb_problem_num_q_offsets(sipb_problem* pb, int* nd);
+int sipb_problem_q_offsets(sipb_problem* pb, int64_t* out);     /* Q_offsets, reference order */
+int sipb_problem_destroy(sipb_problem* pb);
+
+/* ---- the solve: replaces PARSDMM(m,AtA,TD_OP,set_Prop,P_sub,comp_grid,options[,x,l,y])
+ *      (PARSDMM.jl:25-258).  m: host TF[N_model]; x: host TF[N] in/out (start guess when
+ *      zero_ini_guess==0); l,y: arrays of p host pointers (may be NULL when zero_ini_guess==1 and
+ *      return_ly==0). ------------------------------------------------------------------------- */
+int sipb_solve(sipb_problem* pb, const void* m, void* x, void* const* l, void* const* y,
+               const sipb_options* opt, sipb_log* log);
+
+/* ---- unit entry points (host pointers; used by the parity tests and micro-benchmarks) ------ */
+/* y = A*x for A in CDS form: replaces Ax_CDS_MT / CDS_MVp_MT (argmin_x.jl:72-78, CDS_MVp_MT.jl:9-25) */
+int sipb_cds_spmv(sipb_ctx* ctx, int dtype, int64_t N, int nd, const void* R, const int64_t* offsets,
+                  const void* x, void* y);
+/* cg(A,b;tol,maxIter,x) with A in CDS form (cg.jl:44-128).  x in/out. */
+int sipb_cds_cg(sipb_ctx* ctx, int dtype, int64_t N, int nd, const void* R, const int64_t* offsets,
+                const void* b, void* x, double tol, int max_iter, int* flag, double* relres, int* iters);
+/* in-place projector / prox on a host vector (P_sub[i](v), get_projector.jl). `m_vec` only for
+ * SIPB_SET_DISTANCE (prox_l2s!(v,rho,m)), with rho passed in desc->max. */
+int sipb_project(sipb_ctx* ctx, int dtype, const sipb_set_desc* desc, int64_t M, void* v, const void* m_vec);
+/* s = TD_OP*x (forward) or t = TD_OP'*v (adjoint) for a matrix-free operator descriptor
+ * (update_y_l.jl:43, rhs_compose.jl:28). */
+int sipb_op_apply(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const double* h, int op_kind,
+                  int block_mode, int adjoint, const void* in, void* out);
+int sipb_op_rows(int ndim, const int64_t* n, int op_kind, int64_t* rows);
+/* Q += alpha*B on matching diagonals (CDS_scaled_add!.jl:8-26). */
+int sipb_cds_scaled_add(sipb_ctx* ctx, int dtype, int64_t N, int nd_a, void* A, const int64_t* a_offsets,
+                        int nd_b, const void* B, const int64_t* b_offsets, double alpha);
+/* micro-benchmark: device-resident CDS SpMV(+dot) on synthetic data, CUDA-event timed;
+ * returns average milliseconds per launch over `reps` launches after `warmup`. */
+int sipb_bench_spmv(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, int warmup, int reps,
+                    int flush_l2, double* avg_ms, int64_t* algorithmic_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIPB200_H */

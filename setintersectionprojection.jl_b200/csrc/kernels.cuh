@@ -1,0 +1,847 @@
+// kernels.cuh — hand-written sm_100a kernels of the PARSDMM iteration.
+//
+// One kernel per reference routine (all HBM-bandwidth bound, one pass over their operands):
+//   k_spmv            CDS_MVp_MT.jl:9-25 + Ax_CDS_MT (argmin_x.jl:72-78) [+ dot(p,Ap), cg.jl:88]
+//   k_cg_init         argmin_x.jl:33-37 + cg.jl:47-76   (one SpMV instead of the reference's two)
+//   k_cg_xr / k_cg_p  cg.jl:86-114
+//   k_rhs             rhs_compose.jl:24-36
+//   k_yl              update_y_l.jl:39-94 with the projector / prox fused in
+//   k_rdual           update_y_l.jl:82-84
+//   k_adapt           adapt_rho_gamma.jl:41-53 + snapshots PARSDMM.jl:164-207 (+ a_is_b_min_c_MT!.jl)
+//   k_stop            PARSDMM.jl:140-145
+//   k_cds_axpy        CDS_scaled_add!.jl:16-22 / Q assembly PARSDMM_initialize.jl:223-229
+//   k_l1_pass         project_l1_Duchi!.jl:33-46 replaced by a sort-free Newton (Michelot) threshold search
+//   k_radix_hist/...  project_cardinality!.jl:18-19 replaced by a radix select with index-ordered ties
+#pragma once
+#include "common.cuh"
+#include "ops.cuh"
+
+namespace sipb {
+
+constexpr int kMaxDiag = 32;   // max diagonals of Q handled by the SpMV kernels
+constexpr int kMaxSets = 16;   // max terms (incl. the distance term) per problem
+
+// =============================================================================================
+// CDS SpMV
+// =============================================================================================
+template <typename T>
+struct SpmvArgs {
+  const T* R;        // [nd][ld] diagonals, row aligned (R[j*ld + r] = A[r, r+off_j]), zero padded
+  i64 ld;            // leading dimension (multiple of 16 elements)
+  int nd;
+  i64 off[kMaxDiag]; // offsets in accumulation order (Q_offsets order of the reference)
+  i64 N;             // local rows
+  i64 row0;          // global index of local row 0 (slabs); 0 on a single GPU
+  i64 Nglob;         // global rows
+  const T* x;        // x[r + off] addresses local row r (+halo), same indexing as y
+  T* y;
+};
+
+// acc[e] for VW consecutive rows starting at r (vector path; r % VW == 0, r + VW <= N)
+template <typename T>
+__device__ __forceinline__ void spmv_rows_vec(const SpmvArgs<T>& a, i64 r, T (&acc)[Vec<T>::W]) {
+  constexpr int VW = Vec<T>::W;
+#pragma unroll
+  for (int e = 0; e < VW; ++e) acc[e] = (T)0;
+  const i64 g = a.row0 + r;
+#pragma unroll 4
+  for (int j = 0; j < a.nd; ++j) {
+    T rv[VW], xv[VW];
+    vload_stream<T>(a.R + (i64)j * a.ld + r, rv);
+    const i64 o = a.off[j];
+    const i64 gc = g + o;
+    if (gc >= 0 && gc + VW <= a.Nglob) {
+      const T* xp = a.x + r + o;
+      if ((o & (VW - 1)) == 0) {
+        vload<T>(xp, xv);
+      } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) xv[e] = xp[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        const i64 ge = gc + e;
+        xv[e] = (ge >= 0 && ge < a.Nglob) ? a.x[r + o + e] : (T)0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VW; ++e) acc[e] = acc[e] + rv[e] * xv[e];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T spmv_row_scalar(const SpmvArgs<T>& a, i64 r) {
+  T acc = (T)0;
+  const i64 g = a.row0 + r;
+  for (int j = 0; j < a.nd; ++j) {
+    const i64 gc = g + a.off[j];
+    if (gc >= 0 && gc < a.Nglob) acc = acc + a.R[(i64)j * a.ld + r] * a.x[r + a.off[j]];
+  }
+  return acc;
+}
+
+// y = A x  and (DOT) partial sum of x.*y  -> out_dot[0]
+template <typename T, bool DOT>
+__global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs, double* out_dot,
+                                                   const int* __restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  constexpr int VW = Vec<T>::W;
+  double d[1] = {0.0};
+  const i64 nvec = a.N / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+    const i64 r = iv * VW;
+    T acc[VW];
+    spmv_rows_vec<T>(a, r, acc);
+    vstore<T>(a.y + r, acc);
+    if (DOT) {
+      T xc[VW];
+      vload<T>(a.x + r, xc);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) d[0] += (double)xc[e] * (double)acc[e];
+    }
+  }
+  // tail rows
+  for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.N; r += (i64)gridDim.x * blockDim.x) {
+    const T acc = spmv_row_scalar<T>(a, r);
+    a.y[r] = acc;
+    if (DOT) d[0] += (double)a.x[r] * (double)acc;
+  }
+  if (DOT) {
+    if (grid_sum<1>(d, rs) && threadIdx.x == 0) out_dot[0] = d[0];
+  }
+}
+
+// =============================================================================================
+// CG (device-resident scalars; the host only polls `done`)
+// =============================================================================================
+struct CgState {
+  double bb;        // sum b^2
+  double rr;        // gamma = dot(r,r) of the current residual
+  double pAp;
+  double rr_new;
+  double tol;       // value of a T
+  double tol_prev;  // x_solve_tol_ref carried between PARSDMM iterations (argmin_x.jl:33-37)
+  double relres;    // resvec[lastIter]
+  int iter;         // lastIter
+  int done;
+  int flag;         // 0 / -1 / -2 / -9 as cg.jl:29-37
+  int maxit;
+  int parsdmm_it;   // i of PARSDMM.jl:97 (selects the i<3 tolerance rule); 0 => plain cg with tol given
+};
+
+// r = b - Q x ; p = r ; (x_old = x) ; sums bb, rr
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __restrict__ b, T* __restrict__ r,
+                                                      T* __restrict__ p, T* __restrict__ x_old, RedScratch rs,
+                                                      CgState* st) {
+  constexpr int VW = Vec<T>::W;
+  double d[2] = {0.0, 0.0};
+  const i64 nvec = a.N / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+    const i64 row = iv * VW;
+    T acc[VW], bv[VW], rv[VW];
+    spmv_rows_vec<T>(a, row, acc);
+    vload_stream<T>(b + row, bv);
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      rv[e] = bv[e] - acc[e];
+      d[0] += (double)bv[e] * (double)bv[e];
+      d[1] += (double)rv[e] * (double)rv[e];
+    }
+    vstore<T>(r + row, rv);
+    vstore<T>(p + row, rv);
+    if (x_old) {
+      T xc[VW];
+      vload<T>(a.x + row, xc);
+      vstore<T>(x_old + row, xc);
+    }
+  }
+  for (i64 row = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < a.N;
+       row += (i64)gridDim.x * blockDim.x) {
+    const T acc = spmv_row_scalar<T>(a, row);
+    const T bv = b[row];
+    const T rv = bv - acc;
+    d[0] += (double)bv * (double)bv;
+    d[1] += (double)rv * (double)rv;
+    r[row] = rv;
+    p[row] = rv;
+    if (x_old) x_old[row] = a.x[row];
+  }
+  if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
+    st->bb = d[0];
+    st->rr = d[1];
+  }
+}
+
+// scalar epilogue of the init (after the optional all-reduce of bb, rr): tolerance rule of
+// argmin_x.jl:33-37 and the early exits of cg.jl:47,73-76
+template <typename T>
+__global__ void k_cg_init_fin(CgState* st) {
+  const T nb = (T)sqrt(st->bb);
+  const T nr = (T)sqrt(st->rr);
+  st->iter = 0;
+  st->done = 0;
+  st->flag = -1;
+  st->relres = 0.0;
+  if (st->parsdmm_it > 0) {
+    // TF(max(0.1*norm(Qx-rhs)/norm(rhs), 10*eps(TF))) evaluated in Float64; Julia's max propagates NaN
+    const double ratio = 0.1 * (double)nr / (double)nb;
+    const double floor_ = (double)((T)10 * (T)Eps<T>::v);
+    double cur = (ratio != ratio) ? ratio : (ratio > floor_ ? ratio : floor_);
+    if (st->parsdmm_it >= 3) {
+      const double prev = st->tol_prev;
+      cur = (cur != cur || prev != prev) ? (cur != cur ? cur : prev) : (cur < prev ? cur : prev);
+    }
+    st->tol = (double)(T)cur;
+    st->tol_prev = st->tol;
+  }
+  if (nb == (T)0) {            // cg.jl:47: rhs == 0 -> zeros, flag -9, iter 0 (host zero-fills x)
+    st->flag = -9;
+    st->done = 1;
+    return;
+  }
+  if (nr / nb <= (T)st->tol) {  // cg.jl:73-76
+    st->flag = 0;
+    st->iter = 1;
+    st->done = 1;
+  }
+}
+
+// x += alpha p ; r -= alpha Ap ; rr_new = dot(r,r)        (cg.jl:88-100)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T* __restrict__ r,
+                                                    const T* __restrict__ p, const T* __restrict__ Ap,
+                                                    RedScratch rs, CgState* st) {
+  if (st->done) return;
+  constexpr int VW = Vec<T>::W;
+  const T gamma = (T)st->rr;
+  const T alpha = gamma / (T)st->pAp;
+  const bool bad = (alpha == (T)INFINITY) || (alpha < (T)0);   // cg.jl:91
+  double d[1] = {0.0};
+  if (!bad) {
+    const i64 nvec = N / VW;
+    for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+      const i64 row = iv * VW;
+      T xv[VW], rv[VW], pv[VW], av[VW];
+      vload<T>(x + row, xv);
+      vload<T>(r + row, rv);
+      vload<T>(p + row, pv);
+      vload_stream<T>(Ap + row, av);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) {
+        xv[e] = xv[e] + alpha * pv[e];
+        rv[e] = rv[e] - alpha * av[e];
+        d[0] += (double)rv[e] * (double)rv[e];
+      }
+      vstore<T>(x + row, xv);
+      vstore<T>(r + row, rv);
+    }
+    for (i64 row = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < N;
+         row += (i64)gridDim.x * blockDim.x) {
+      const T xv = x[row] + alpha * p[row];
+      const T rv = r[row] - alpha * Ap[row];
+      d[0] += (double)rv * (double)rv;
+      x[row] = xv;
+      r[row] = rv;
+    }
+  }
+  if (grid_sum<1>(d, rs) && threadIdx.x == 0) {
+    if (bad) {
+      st->flag = -2;          // "Matrix A in cg has to be positive definite"
+      st->iter = st->iter + 1;
+      st->relres = 0.0;       // resvec[lastIter] never written
+      st->done = 1;
+    } else {
+      st->rr_new = d[0];
+    }
+  }
+}
+
+// convergence test + p = r + beta p          (cg.jl:100-114); the last block advances the state
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ r, T* __restrict__ p,
+                                                   RedScratch rs, CgState* st) {
+  if (st->done) return;
+  constexpr int VW = Vec<T>::W;
+  const T nb = (T)sqrt(st->bb);
+  const T res = (T)sqrt(st->rr_new) / nb;
+  const bool conv = res <= (T)st->tol;
+  const int it = st->iter + 1;
+  const bool last_it = it >= st->maxit;
+  if (!conv && !last_it) {
+    const T gamma = (T)st->rr;
+    const T beta = (T)st->rr_new / gamma;
+    const i64 nvec = N / VW;
+    for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+      const i64 row = iv * VW;
+      T rv[VW], pv[VW];
+      vload<T>(r + row, rv);
+      vload<T>(p + row, pv);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) pv[e] = rv[e] + beta * pv[e];
+      vstore<T>(p + row, pv);
+    }
+    for (i64 row = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < N;
+         row += (i64)gridDim.x * blockDim.x)
+      p[row] = r[row] + beta * p[row];
+  }
+  if (last_block_ticket(rs.counter) && threadIdx.x == 0) {
+    st->iter = it;
+    st->relres = (double)res;
+    if (conv) {
+      st->flag = 0;
+      st->done = 1;
+    } else if (last_it) {
+      st->flag = -1;
+      st->done = 1;
+    } else {
+      st->rr = st->rr_new;
+    }
+  }
+}
+
+// =============================================================================================
+// rhs = sum_i A_i' (rho_i y_i + l_i)        (rhs_compose.jl:24-36)
+// =============================================================================================
+template <typename T>
+struct SetRef {
+  OpDev op;
+  const T* y;
+  const T* l;
+  T rho;
+};
+template <typename T>
+struct RhsArgs {
+  int nsets;
+  unsigned n[3];
+  i64 npts;
+  i64 ncols;       // npts or 2*npts
+  T* rhs;
+  SetRef<T> sets[kMaxSets];
+};
+
+template <typename T, typename F>
+__device__ __forceinline__ T op_adjoint_f(const OpDev& op, i64 cc, unsigned i, unsigned j, unsigned k, F val) {
+  T acc = (T)0;
+  switch (op.kind) {
+    case SIPB_OP_IDENTITY:
+      return acc + val(cc);
+    case SIPB_OP_DXZ: {
+      const i64 w = (i64)op.n[0] - 1;
+      const T a = (T)op.a_xz;
+      const bool il = i >= 1u, ih_ = i < op.n[0] - 1u, jl = j >= 1u, jh = j < op.n[1] - 1u;
+      const i64 q = (i64)i + w * (i64)j;
+      if (il && jl) acc = acc + a * val(q - 1 - w);
+      if (ih_ && jl) acc = acc + (-a) * val(q - w);
+      if (il && jh) acc = acc + (-a) * val(q - 1);
+      if (ih_ && jh) acc = acc + a * val(q);
+      return acc;
+    }
+    default: {
+      for (int b = 0; b < op.nblk; ++b) {
+        const int a = op.axis[b];
+        const T ih = (T)op.ih[a];
+        const i64 base = op.row_start[b];
+        unsigned coord, na;
+        i64 q, st;
+        if (a == 0) {
+          coord = i; na = op.n[0];
+          q = cc - ((i64)j + (i64)op.n[1] * k);
+          st = 1;
+        } else if (a == 1) {
+          coord = j; na = op.n[1];
+          q = cc - (i64)op.n[0] * k;
+          st = op.n[0];
+        } else {
+          coord = k; na = op.n[2];
+          q = cc;
+          st = (i64)op.n[0] * op.n[1];
+        }
+        if (coord >= 1u) acc = acc + ih * val(base + q - st);
+        if (coord < na - 1u) acc = acc + (-ih) * val(base + q);
+      }
+      return acc;
+    }
+  }
+}
+
+__device__ __forceinline__ bool op_touches_half(int mode, bool upper) {
+  return mode == SIPB_BLOCK_PLAIN || mode == SIPB_BLOCK_BOTH || (mode == SIPB_BLOCK_LEFT && !upper) ||
+         (mode == SIPB_BLOCK_RIGHT && upper);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_rhs(const __grid_constant__ RhsArgs<T> a) {
+  for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < a.ncols; c += (i64)gridDim.x * blockDim.x) {
+    const bool upper = c >= a.npts;
+    const i64 cc = upper ? c - a.npts : c;
+    const unsigned q = (unsigned)cc;
+    const unsigned t = q / a.n[0];
+    const unsigned i = q - t * a.n[0];
+    const unsigned k = t / a.n[1];
+    const unsigned j = t - k * a.n[1];
+    T acc = (T)0;
+    for (int s = 0; s < a.nsets; ++s) {
+      const SetRef<T>& S = a.sets[s];
+      T tv = (T)0;
+      if (op_touches_half(S.op.mode, upper)) {
+        const T rho = S.rho;
+        const T* y = S.y;
+        const T* l = S.l;
+        tv = op_adjoint_f<T>(S.op, cc, i, j, k, [=](i64 row) -> T { return rho * y[row] + l[row]; });
+      }
+      acc = acc + tv;
+    }
+    a.rhs[c] = acc;
+  }
+}
+
+// =============================================================================================
+// projectors applied element-wise
+// =============================================================================================
+template <typename T>
+struct ProjDev {
+  int kind;          // SIPB_SET_*
+  T lo, hi;          // scalar bounds / (annulus: sigma_min, sigma_max) / l1 tau, l2 sigma in hi
+  const T* lo_vec;   // vector bounds
+  const T* hi_vec;
+  const T* m;        // distance term: the vector being projected
+  T rho;             // distance term / prox_l1: current rho
+  // parameters produced by the reduction passes:
+  T theta;           // l1 soft threshold (0 => identity)
+  T scale;           // l2 / annulus scale factor (1 => identity)
+  T fill;            // annulus zero-vector fill value (NaN => unused)
+  unsigned long long key_thr;   // cardinality: smallest kept magnitude key
+  int keep_all;      // cardinality: k >= M
+  int keep_none;     // cardinality: k <= 0
+};
+
+template <typename T> __device__ __forceinline__ unsigned long long mag_key(T v);
+template <> __device__ __forceinline__ unsigned long long mag_key<float>(float v) {
+  return (unsigned long long)(__float_as_uint(v) & 0x7fffffffu);
+}
+template <> __device__ __forceinline__ unsigned long long mag_key<double>(double v) {
+  return (unsigned long long)(__double_as_longlong(v) & 0x7fffffffffffffffll);
+}
+
+template <typename T> __device__ __forceinline__ T t_abs(T v);
+template <> __device__ __forceinline__ float t_abs<float>(float v) { return fabsf(v); }
+template <> __device__ __forceinline__ double t_abs<double>(double v) { return fabs(v); }
+template <typename T> __device__ __forceinline__ T t_sign(T v) {
+  return v > (T)0 ? (T)1 : (v < (T)0 ? (T)-1 : v);   // sign(0)=0, sign(NaN)=NaN like Julia
+}
+template <typename T> __device__ __forceinline__ T t_max(T a, T b) {   // Julia max (NaN-propagating)
+  return (a != a) ? a : ((b != b) ? b : (a > b ? a : b));
+}
+template <typename T> __device__ __forceinline__ T t_min(T a, T b) {
+  return (a != a) ? a : ((b != b) ? b : (a < b ? a : b));
+}
+
+// P(v) for element r with all reduction-derived parameters already known
+template <typename T>
+__device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
+  switch (P.kind) {
+    case SIPB_SET_BOUNDS_SCALAR:   // max(LB, min(x, UB))   project_bounds!.jl:9
+      return t_max<T>(P.lo, t_min<T>(v, P.hi));
+    case SIPB_SET_BOUNDS_VECTOR:   // min then max          project_bounds!.jl:21-22
+      return t_max<T>(P.lo_vec[r], t_min<T>(v, P.hi_vec[r]));
+    case SIPB_SET_DISTANCE: {      // (x*rho + m) / (rho + 1.0) in Float64   prox_l2s!.jl:4
+      const T num = v * P.rho + P.m[r];
+      return (T)((double)num / ((double)P.rho + 1.0));
+    }
+    case SIPB_SET_PROX_L1: {       // sign(x) * max(0, abs(x) - 1/rho)       prox_l1!.jl:9
+      const T thr = (T)1 / P.rho;
+      return t_sign<T>(v) * t_max<T>((T)0, t_abs<T>(v) - thr);
+    }
+    case SIPB_SET_L1:              // sign(v) * max(abs(v) - theta, 0)       project_l1_Duchi!.jl:49
+      if (P.theta < (T)0) return v;   // inside the ball: untouched
+      return t_sign<T>(v) * t_max<T>(t_abs<T>(v) - P.theta, (T)0);
+    case SIPB_SET_L2:
+    case SIPB_SET_ANNULUS:         // rmul!(x, sigma/nl2)   project_l2!.jl:11, project_annulus!.jl:11-17
+      if (P.fill == P.fill) return P.fill;
+      return (P.scale == (T)1) ? v : v * P.scale;
+    case SIPB_SET_CARDINALITY:     // zero everything below the k-th largest magnitude
+      if (P.keep_all) return v;
+      if (P.keep_none) return (T)0;
+      return (mag_key<T>(v) >= P.key_thr) ? v : (T)0;
+    default:
+      return v;
+  }
+}
+
+__host__ __device__ __forceinline__ bool proj_is_elementwise(int kind) {
+  return kind == SIPB_SET_BOUNDS_SCALAR || kind == SIPB_SET_BOUNDS_VECTOR || kind == SIPB_SET_DISTANCE ||
+         kind == SIPB_SET_PROX_L1;
+}
+
+// =============================================================================================
+// y / l update                               (update_y_l.jl:39-94)
+// =============================================================================================
+template <typename T>
+struct YlArgs {
+  OpDev op;
+  ProjDev<T> P;
+  const T* x;
+  T* y;
+  T* l;
+  T* y_old;
+  T* l_old;
+  T* s;
+  T rho, gamma;
+  int want_feas;     // also reduce ||P(s)-s||^2 and ||s||^2 (element-wise projectors only)
+};
+
+// MODE 0: element-wise projector, everything in one pass.
+//         sums: [0] ||y-s||^2, [1] ||P(s)-s||^2, [2] ||s||^2
+// MODE 1: reduction-type projector, pass 1: y <- v = x_hat - l/rho, s stored, y_old/l_old saved.
+//         sums: [0] sum|v|, [1] sum v^2, [2] count(v != 0)
+// MODE 2: reduction-type projector, pass 2: y <- P(v), l update.  sums: [0] ||y-s||^2
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
+  double d[3] = {0.0, 0.0, 0.0};
+  const T rho = a.rho, gamma = a.gamma;
+  const T rho1 = (T)1.0 / rho;                      // update_y_l.jl:34
+  const bool relaxed = !(gamma == (T)1);
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.op.rows; r += (i64)gridDim.x * blockDim.x) {
+    if (MODE == 0 || MODE == 1) {
+      const T s = op_forward<T>(a.op, r, a.x);
+      const T yo = a.y[r];
+      const T lo = a.l[r];
+      T xh = s;
+      if (relaxed) xh = gamma * s + ((T)1.0 - gamma) * yo;     // :72
+      const T v = xh - lo * rho1;                                // :67 / :74
+      a.y_old[r] = yo;
+      a.l_old[r] = lo;
+      a.s[r] = s;
+      if (MODE == 0) {
+        const T yn = proj_apply<T>(a.P, v, r);
+        const T rp = -s + yn;                                    // :69 / :76
+        const T ln = relaxed ? lo + rho * (-xh + yn) : lo + rho * rp;
+        a.y[r] = yn;
+        a.l[r] = ln;
+        d[0] += (double)rp * (double)rp;
+        if (a.want_feas) {
+          const T pf = proj_apply<T>(a.P, s, r) - s;
+          d[1] += (double)pf * (double)pf;
+          d[2] += (double)s * (double)s;
+        }
+      } else {
+        a.y[r] = v;
+        d[0] += (double)t_abs<T>(v);
+        d[1] += (double)v * (double)v;
+        d[2] += (v != (T)0) ? 1.0 : 0.0;
+      }
+    } else {
+      const T v = a.y[r];
+      const T s = a.s[r];
+      const T lo = a.l[r];
+      const T yn = proj_apply<T>(a.P, v, r);
+      const T rp = -s + yn;
+      T ln;
+      if (relaxed) {
+        const T xh = gamma * s + ((T)1.0 - gamma) * a.y_old[r];
+        ln = lo + rho * (-xh + yn);
+      } else {
+        ln = lo + rho * rp;
+      }
+      a.y[r] = yn;
+      a.l[r] = ln;
+      d[0] += (double)rp * (double)rp;
+    }
+  }
+  if (grid_sum<3>(d, rs) && threadIdx.x == 0) {
+    out[0] = d[0];
+    out[1] = d[1];
+    out[2] = d[2];
+  }
+}
+
+// forward operator only: s = A x      (initial feasibility, PARSDMM_initialize.jl:97-99; unit tests)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_op_forward(const __grid_constant__ OpDev op, const T* __restrict__ x,
+                                                         T* __restrict__ s) {
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < op.rows; r += (i64)gridDim.x * blockDim.x)
+    s[r] = op_forward<T>(op, r, x);
+}
+
+// adjoint only: t = A' v (unit tests / sipb_op_apply)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_op_adjoint(const __grid_constant__ OpDev op, const T* __restrict__ v,
+                                                         T* __restrict__ t) {
+  for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < op.cols; c += (i64)gridDim.x * blockDim.x) {
+    const bool upper = c >= op.npts;
+    const i64 cc = upper ? c - op.npts : c;
+    const unsigned q = (unsigned)cc;
+    const unsigned tq = q / op.n[0];
+    const unsigned i = q - tq * op.n[0];
+    const unsigned k = tq / op.n[1];
+    const unsigned j = tq - k * op.n[1];
+    T tv = (T)0;
+    if (op_touches_half(op.mode, upper)) tv = op_adjoint_f<T>(op, cc, i, j, k, [=](i64 row) -> T { return v[row]; });
+    t[c] = tv;
+  }
+}
+
+// sums of a stored vector: [0] sum|v|, [1] sum v^2, [2] count(v != 0)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_vec_stats(i64 M, const T* __restrict__ v, RedScratch rs, double* out) {
+  double d[3] = {0.0, 0.0, 0.0};
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const T t = v[r];
+    d[0] += (double)t_abs<T>(t);
+    d[1] += (double)t * (double)t;
+    d[2] += (t != (T)0) ? 1.0 : 0.0;
+  }
+  if (grid_sum<3>(d, rs) && threadIdx.x == 0) {
+    out[0] = d[0];
+    out[1] = d[1];
+    out[2] = d[2];
+  }
+}
+
+// feasibility of a stored s w.r.t. a projector with known parameters: [0] ||P(s)-s||^2, [1] ||s||^2
+// (update_y_l.jl:92-94).  `apply` != 0 writes P(s) back (sipb_project / initial feasibility).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_feas(i64 M, T* __restrict__ s, const __grid_constant__ ProjDev<T> P,
+                                                   int apply, RedScratch rs, double* out) {
+  double d[2] = {0.0, 0.0};
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const T t = s[r];
+    const T pt = proj_apply<T>(P, t, r);
+    const T pf = pt - t;
+    d[0] += (double)pf * (double)pf;
+    d[1] += (double)t * (double)t;
+    if (apply) s[r] = pt;
+  }
+  if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
+    out[0] = d[0];
+    out[1] = d[1];
+  }
+}
+
+// =============================================================================================
+// dual residual: || A' (y - y_old) ||^2      (update_y_l.jl:82-84)
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_rdual(const __grid_constant__ OpDev op, const T* __restrict__ y,
+                                                    const T* __restrict__ y_old, RedScratch rs, double* out) {
+  double d[1] = {0.0};
+  for (i64 cc = (i64)blockIdx.x * blockDim.x + threadIdx.x; cc < op.npts; cc += (i64)gridDim.x * blockDim.x) {
+    const unsigned q = (unsigned)cc;
+    const unsigned tq = q / op.n[0];
+    const unsigned i = q - tq * op.n[0];
+    const unsigned k = tq / op.n[1];
+    const unsigned j = tq - k * op.n[1];
+    const T t = op_adjoint_f<T>(op, cc, i, j, k, [=](i64 row) -> T { return y[row] - y_old[row]; });
+    d[0] += (double)t * (double)t;
+  }
+  if (grid_sum<1>(d, rs) && threadIdx.x == 0)
+    out[0] = (op.mode == SIPB_BLOCK_BOTH) ? 2.0 * d[0] : d[0];   // [A A]' v = [A'v; A'v]
+}
+
+// =============================================================================================
+// rho / gamma adaptation reductions + snapshots  (adapt_rho_gamma.jl:41-53, PARSDMM.jl:164-207)
+// =============================================================================================
+template <typename T>
+struct AdaptArgs {
+  i64 M;
+  const T* l_old; const T* y_old; const T* s; const T* l; const T* y;
+  T* lhat0; T* s0; T* l0; T* y0;
+  T rho;
+  int do_sums;       // compute the six reductions (needs the previous snapshots)
+  int do_snapshot;   // overwrite the snapshots afterwards
+};
+// out: [0] dot(dH,dlh) [1] ||dH||^2 [2] ||dlh||^2 [3] ||dl||^2 [4] ||dG||^2 [5] dot(dG,dl)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_adapt(const __grid_constant__ AdaptArgs<T> a, RedScratch rs,
+                                                    double* out) {
+  double d[6] = {0, 0, 0, 0, 0, 0};
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.M; r += (i64)gridDim.x * blockDim.x) {
+    const T s = a.s[r], yv = a.y[r], lv = a.l[r];
+    const T lhat = a.l_old[r] + a.rho * (-s + a.y_old[r]);    // adapt_rho_gamma.jl:41
+    if (a.do_sums) {
+      const T dlh = lhat - a.lhat0[r];
+      const T dH = s - a.s0[r];
+      const T dl = lv - a.l0[r];
+      const T dG = -(yv - a.y0[r]);
+      d[0] += (double)dH * (double)dlh;
+      d[1] += (double)dH * (double)dH;
+      d[2] += (double)dlh * (double)dlh;
+      d[3] += (double)dl * (double)dl;
+      d[4] += (double)dG * (double)dG;
+      d[5] += (double)dG * (double)dl;
+    }
+    if (a.do_snapshot) {
+      a.lhat0[r] = lhat;
+      a.y0[r] = yv;
+      a.s0[r] = s;
+      a.l0[r] = lv;
+    }
+  }
+  if (grid_sum<6>(d, rs) && threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i] = d[i];
+  }
+}
+
+// =============================================================================================
+// objective / evolution reductions              (PARSDMM.jl:139-145)
+// out: [0] ||x - m||^2 (or ||x1 + x2 - m||^2 for Minkowski)  [1] ||x_old - x||^2  [2] ||x||^2
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_stop(i64 N, i64 npts, int minkowski, const T* __restrict__ x,
+                                                   const T* __restrict__ x_old, const T* __restrict__ m,
+                                                   RedScratch rs, double* out) {
+  double d[3] = {0.0, 0.0, 0.0};
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x) {
+    const T xv = x[r];
+    const T e = x_old[r] - xv;
+    d[1] += (double)e * (double)e;
+    d[2] += (double)xv * (double)xv;
+    if (!minkowski) {
+      const T o = xv - m[r];
+      d[0] += (double)o * (double)o;
+    } else if (r < npts) {
+      const T sx = ((T)0 + xv) + x[r + npts];     // TD_OP[end]*x with TD_OP[end] = [I I]
+      const T o = sx - m[r];
+      d[0] += (double)o * (double)o;
+    }
+  }
+  if (grid_sum<3>(d, rs) && threadIdx.x == 0) {
+    out[0] = d[0];
+    out[1] = d[1];
+    out[2] = d[2];
+  }
+}
+
+// =============================================================================================
+// A[:,col] += alpha * B[:,k]                  (CDS_scaled_add!.jl:22; Q assembly)
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cds_axpy(i64 N, T* __restrict__ A, const T* __restrict__ B, T alpha) {
+  constexpr int VW = Vec<T>::W;
+  const i64 nvec = N / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+    const i64 r = iv * VW;
+    T av[VW], bv[VW];
+    vload<T>(A + r, av);
+    vload_stream<T>(B + r, bv);
+#pragma unroll
+    for (int e = 0; e < VW; ++e) av[e] = av[e] + alpha * bv[e];
+    vstore<T>(A + r, av);
+  }
+  for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x)
+    A[r] = A[r] + alpha * B[r];
+}
+
+// =============================================================================================
+// l1-ball threshold: sort-free Newton / Michelot iteration on
+//     f(theta) = sum max(|v| - theta, 0) - tau            (project_l1_Duchi!.jl:33-46)
+// Each pass reduces count and sum of the entries above the current theta; the last block performs
+// the Newton step theta <- (S - tau)/C.  From any start the first step lands left of the root
+// (f is convex), afterwards the iterates increase monotonically and reach the exact root of the
+// piecewise-linear f in finitely many steps (the fix point is detected bit-exactly because the
+// reductions are deterministic).
+// =============================================================================================
+struct L1State {
+  double theta;      // current iterate
+  double tau;
+  double S1;         // sum |v|
+  double M;          // number of elements
+  int on_left;       // iterate known to be <= root
+  int done;
+  int passes;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict__ v, RedScratch rs, L1State* st) {
+  if (st->done) return;
+  const double theta = st->theta;
+  double d[2] = {0.0, 0.0};
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const double a = (double)t_abs<T>(v[r]);
+    if (a > theta) {
+      d[0] += 1.0;
+      d[1] += a;
+    }
+  }
+  if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
+    const double C = d[0], S = d[1];
+    st->passes += 1;
+    if (C == 0.0) {            // theta at/above max|v|: restart from the left end
+      st->theta = 0.0;
+      st->on_left = 1;
+      // f(0) = S1 - tau > 0 is known; next pass from theta = 0
+      if (theta == 0.0) st->done = 1;   // all-zero vector
+    } else {
+      double tn = (S - st->tau) / C;
+      if (tn < 0.0) tn = 0.0;
+      if (st->on_left && tn <= theta) {
+        st->done = 1;          // fix point: theta is the exact root
+      } else {
+        st->theta = tn;
+        st->on_left = 1;
+      }
+    }
+    if (st->passes >= 200) st->done = 1;
+  }
+}
+
+// =============================================================================================
+// cardinality: radix select of the k-th largest magnitude key (8-bit digits, MSB first)
+// =============================================================================================
+struct SelState {
+  unsigned long long prefix;      // digits decided so far (high bits)
+  unsigned long long k_rem;       // rank still to locate inside the current prefix bucket (1-based)
+  unsigned long long count_eq;    // elements whose key == final threshold
+  unsigned long long hist[256];
+  int shift;                      // bit position of the digit to examine next (>= 0), -8 when finished
+  int key_bits;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_radix_hist(i64 M, const T* __restrict__ v, SelState* st,
+                                                         unsigned int* counter) {
+  __shared__ unsigned int sh[256];
+  const int shift = st->shift;
+  if (shift < 0) return;
+  const unsigned long long prefix = st->prefix;
+  const int hi_shift = shift + 8;
+  for (int t = threadIdx.x; t < 256; t += blockDim.x) sh[t] = 0u;
+  __syncthreads();
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const unsigned long long key = mag_key<T>(v[r]);
+    const bool match = (hi_shift >= st->key_bits) ? true : ((key >> hi_shift) == prefix);
+    if (match) atomicAdd(&sh[(unsigned)((key >> shift) & 0xffull)], 1u);
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 256; t += blockDim.x)
+    if (sh[t]) atomicAdd(&st->hist[t], (unsigned long long)sh[t]);
+  if (last_block_ticket(counter) && threadIdx.x == 0) {
+    // pick the digit bucket that contains the k_rem-th largest key
+    unsigned long long k = st->k_rem, cum = 0;
+    int bin = 0;
+    for (int b = 255; b >= 0; --b) {
+      const unsigned long long c = st->hist[b];
+      if (cum + c >= k) {
+        bin = b;
+        break;
+      }
+      cum += c;
+    }
+    st->k_rem = k - cum;
+    st->count_eq = st->hist[bin];
+    st->prefix = (prefix << 8) | (unsigned long long)bin;
+    st->shift = shift - 8;
+    for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
+  }
+}
+
+// fill helper
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_fill(i64 N, T* __restrict__ x, T val) {
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x) x[r] = val;
+}
+
+}  // namespace sipb

@@ -1,0 +1,1548 @@
+// solver.cu — host driver of the device-resident PARSDMM iteration + the C ABI (include/sipb200.h).
+//
+// Replaces, behind the reference's own call boundary, PARSDMM.jl:25-258, PARSDMM_initialize.jl:6-318,
+// argmin_x.jl, cg.jl, rhs_compose.jl, update_y_l.jl, adapt_rho_gamma.jl, stop_PARSDMM.jl, Q_update!.jl.
+// The whole iteration runs on the GPU; the host only
+//   * launches kernels,
+//   * polls a few device scalars (CG / threshold-search "done" flags, the per-iteration log sums),
+//   * evaluates the scalar branch logic of stop_PARSDMM.jl / adapt_rho_gamma.jl:55-126 in TF arithmetic.
+// There is no CPU compute fallback anywhere in this file.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <vector>
+
+#include "kernels.cuh"
+
+namespace sipb {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+#define SIPB_REQUIRE(cond, code, msg)   \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::sipb::set_error(msg);           \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernel classes (for the launch counter / CUDA-event table of sipb_log)
+// ---------------------------------------------------------------------------------------------
+enum KClass {
+  KC_SPMV_DOT = 0, KC_CG_INIT, KC_CG_FIN, KC_CG_XR, KC_CG_P, KC_RHS, KC_YL_FUSED, KC_YL_PASS1, KC_YL_PASS2,
+  KC_RDUAL, KC_ADAPT, KC_STOP, KC_Q_UPDATE, KC_L1_PASS, KC_RADIX_HIST, KC_TIES, KC_FEAS, KC_VEC_STATS,
+  KC_OP_APPLY, KC_PARAMS, KC_FILL, KC_SPMV, KC_COUNT
+};
+static_assert(KC_COUNT <= SIPB_N_KERNEL_CLASSES, "kernel table too small");
+static const char* kClassNames[SIPB_N_KERNEL_CLASSES] = {
+    "cds_spmv_dot", "cg_init", "cg_init_fin", "cg_update_xr", "cg_update_p", "rhs_compose", "yl_update_fused",
+    "yl_update_pass1", "yl_update_pass2", "r_dual", "adapt_reduce_snapshot", "stop_reduce", "cds_scaled_add",
+    "l1_threshold_pass", "topk_radix_hist", "topk_ties", "feasibility", "vec_stats", "op_apply", "proj_params",
+    "fill", "cds_spmv", "", ""};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  cudaError_t alloc(size_t count) {
+    release();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+};
+
+// dynamic (device-resident) projector parameters written by the small parameter kernels
+template <typename T>
+struct ProjParams {
+  T theta;
+  T scale;
+  T fill;
+  unsigned long long key_thr;
+  unsigned long long quota;
+  unsigned long long count_eq;
+  int keep_all, keep_none, need_ties;
+};
+
+}  // namespace sipb
+
+using namespace sipb;
+
+// =============================================================================================
+// context
+// =============================================================================================
+struct sipb_ctx {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  RedScratch rs{nullptr, nullptr};
+  double* d_scal = nullptr;   // device scalar slots
+  double* h_scal = nullptr;   // pinned mirror
+  CgState* d_cg = nullptr;
+  CgState* h_cg = nullptr;    // pinned
+  L1State* d_l1 = nullptr;
+  L1State* h_l1 = nullptr;
+  SelState* d_sel = nullptr;
+  unsigned long long* d_tie_counts = nullptr;
+  unsigned int* d_counter2 = nullptr;
+  int rank = 0, world = 1;
+  // launch accounting
+  bool profile = false;
+  int64_t launches[SIPB_N_KERNEL_CLASSES];
+  double ms[SIPB_N_KERNEL_CLASSES];
+  int64_t total_launches = 0;
+  struct EvPair { cudaEvent_t a, b; int cls; };
+  std::vector<EvPair> ev_used;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  void reset_accounting() {
+    for (int i = 0; i < SIPB_N_KERNEL_CLASSES; ++i) { launches[i] = 0; ms[i] = 0.0; }
+    total_launches = 0;
+  }
+  int max_grid() const { return std::min(num_sms * 8, kMaxBlocks); }
+  int grid_for(i64 work_items) const {
+    i64 g = (work_items + kThreads - 1) / kThreads;
+    if (g < 1) g = 1;
+    return (int)std::min<i64>(g, max_grid());
+  }
+  void pre_launch(int cls) {
+    launches[cls]++;
+    total_launches++;
+    if (profile) {
+      std::pair<cudaEvent_t, cudaEvent_t> pr;
+      if (!ev_pool.empty()) { pr = ev_pool.back(); ev_pool.pop_back(); }
+      else { cudaEventCreate(&pr.first); cudaEventCreate(&pr.second); }
+      cudaEventRecord(pr.first, stream);
+      ev_used.push_back({pr.first, pr.second, cls});
+    }
+  }
+  void post_launch() {
+    if (profile) cudaEventRecord(ev_used.back().b, stream);
+  }
+  void collect_profile() {
+    if (!profile) return;
+    cudaStreamSynchronize(stream);
+    for (auto& e : ev_used) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, e.a, e.b);
+      ms[e.cls] += t;
+      ev_pool.push_back({e.a, e.b});
+    }
+    ev_used.clear();
+  }
+};
+
+constexpr int kScalSlots = 512;
+constexpr int kSlotPerSet = 16;
+constexpr int kSlotGlobal = kMaxSets * kSlotPerSet;   // 256
+
+#define LAUNCH(ctx, cls, kern, grid, ...)                         \
+  do {                                                            \
+    (ctx)->pre_launch(cls);                                       \
+    kern<<<(grid), kThreads, 0, (ctx)->stream>>>(__VA_ARGS__);    \
+    (ctx)->post_launch();                                         \
+  } while (0)
+#define LAUNCH1(ctx, cls, kern, ...)                              \
+  do {                                                            \
+    (ctx)->pre_launch(cls);                                       \
+    kern<<<1, 1, 0, (ctx)->stream>>>(__VA_ARGS__);                \
+    (ctx)->post_launch();                                         \
+  } while (0)
+
+static int ctx_sync_scalars(sipb_ctx* c) {
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, kScalSlots * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+// =============================================================================================
+// small parameter kernels (1 thread)
+// =============================================================================================
+namespace sipb {
+
+template <typename T>
+__global__ void k_l1_begin(const double* stats, double tau, double M, const double* warm, L1State* st,
+                           ProjParams<T>* pp) {
+  const T s1 = (T)stats[0];
+  st->tau = tau;
+  st->S1 = stats[0];
+  st->M = M;
+  st->passes = 0;
+  if (s1 <= (T)tau) {          // norm(v,1) <= b && return v   (project_l1_Duchi!.jl:23)
+    st->done = 1;
+    st->theta = -1.0;
+    pp->theta = (T)-1;
+    return;
+  }
+  const double w = *warm;
+  st->done = 0;
+  st->theta = (w > 0.0) ? w : 0.0;
+  st->on_left = (w > 0.0) ? 0 : 1;
+}
+template <typename T>
+__global__ void k_l1_end(L1State* st, double* warm, ProjParams<T>* pp) {
+  if (st->theta < 0.0) return;   // untouched
+  const T th = (T)st->theta;
+  pp->theta = th > (T)0 ? th : (T)0;    // theta = max(0, ...)  (project_l1_Duchi!.jl:46)
+  *warm = st->theta;
+}
+
+// l2 ball / annulus parameters from sum v^2     (project_l2!.jl:8-13, project_annulus!.jl:8-18)
+template <typename T>
+__global__ void k_l2_params(const double* stats, int kind, double smin, double smax, double M, ProjParams<T>* pp) {
+  const T nl2 = (T)sqrt(stats[1]);
+  pp->scale = (T)1;
+  pp->fill = (T)NAN;
+  if (kind == SIPB_SET_L2) {
+    const T sigma = (T)smax;
+    if (!(nl2 <= sigma)) pp->scale = sigma / nl2;
+  } else {
+    const T lo = (T)smin, hi = (T)smax;
+    if (lo <= nl2 && nl2 <= hi) return;
+    if (nl2 > hi) pp->scale = hi / nl2;
+    else if (nl2 < lo && nl2 > (T)0) pp->scale = lo / nl2;
+    else if (nl2 < lo && nl2 == (T)0) pp->fill = (T)((double)lo / sqrt(M));
+  }
+}
+
+template <typename T>
+__global__ void k_sel_begin(long long k, long long M, SelState* st, ProjParams<T>* pp) {
+  pp->keep_all = (k >= M) ? 1 : 0;
+  pp->keep_none = (k <= 0) ? 1 : 0;
+  pp->need_ties = 0;
+  pp->key_thr = 0ull;
+  pp->quota = 0ull;
+  pp->count_eq = 0ull;
+  st->key_bits = (int)(sizeof(T) * 8);
+  st->prefix = 0ull;
+  st->k_rem = (unsigned long long)(k > 0 ? k : 0);
+  st->count_eq = 0ull;
+  for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
+  st->shift = (pp->keep_all || pp->keep_none) ? -8 : st->key_bits - 8;
+}
+template <typename T>
+__global__ void k_sel_end(SelState* st, ProjParams<T>* pp) {
+  if (pp->keep_all || pp->keep_none) return;
+  pp->key_thr = st->prefix;
+  pp->quota = st->k_rem;
+  pp->count_eq = st->count_eq;
+  pp->need_ties = (st->count_eq > st->k_rem && st->prefix > 0ull) ? 1 : 0;
+}
+
+// wrappers that read the tie parameters from device memory (no host round trip)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_tie_count_p(i64 M, const T* __restrict__ v, const ProjParams<T>* pp,
+                                                          i64 chunk, unsigned long long* counts) {
+  if (!pp->need_ties) return;
+  const unsigned long long key = pp->key_thr;
+  const i64 lo = (i64)blockIdx.x * chunk, hi = min(M, lo + chunk);
+  unsigned int c = 0;
+  for (i64 r = lo + threadIdx.x; r < hi; r += blockDim.x) c += (mag_key<T>(v[r]) == key) ? 1u : 0u;
+  __shared__ unsigned int sm[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) sm[w] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sm[i];
+    counts[blockIdx.x] = t;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_tie_zero_p(i64 M, T* __restrict__ v, const ProjParams<T>* pp, i64 chunk,
+                                                         const unsigned long long* __restrict__ counts) {
+  if (!pp->need_ties) return;
+  const unsigned long long key = pp->key_thr, quota = pp->quota;
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned int s_warp[32];
+  if (threadIdx.x == 0) {
+    unsigned long long b = 0;
+    for (unsigned i = 0; i < blockIdx.x; ++i) b += counts[i];
+    s_base = b;
+  }
+  __syncthreads();
+  unsigned long long base = s_base;
+  if (base + counts[blockIdx.x] <= quota) return;
+  const i64 lo = (i64)blockIdx.x * chunk, hi = min(M, lo + chunk);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (i64 t0 = lo; t0 < hi; t0 += blockDim.x) {
+    const i64 r = t0 + threadIdx.x;
+    const bool tie = (r < hi) && (mag_key<T>(v[r]) == key);
+    const unsigned bal = __ballot_sync(0xffffffffu, tie);
+    const unsigned before = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[w] = __popc(bal);
+    __syncthreads();
+    unsigned wbase = 0, tot = 0;
+    for (int i = 0; i < nw; ++i) {
+      if (i < w) wbase += s_warp[i];
+      tot += s_warp[i];
+    }
+    if (tie && base + wbase + before >= quota) v[r] = (T)0;
+    base += tot;
+    __syncthreads();
+  }
+}
+
+// element-wise projector with parameters read through a device pointer
+template <typename T>
+struct ProjRef {
+  ProjDev<T> P;                 // static part (kind, bounds, vectors, m, rho)
+  const ProjParams<T>* dyn;     // dynamic part (may be null for element-wise kinds)
+};
+template <typename T>
+__device__ __forceinline__ ProjDev<T> proj_resolve(const ProjRef<T>& R) {
+  ProjDev<T> P = R.P;
+  if (R.dyn) {
+    P.theta = R.dyn->theta;
+    P.scale = R.dyn->scale;
+    P.fill = R.dyn->fill;
+    P.key_thr = R.dyn->key_thr;
+    P.keep_all = R.dyn->keep_all;
+    P.keep_none = R.dyn->keep_none;
+  }
+  return P;
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads) k_yl_dyn(const __grid_constant__ YlArgs<T> a0, const ProjParams<T>* dyn,
+                                                     RedScratch rs, double* out) {
+  // identical to k_yl but resolves the dynamic projector parameters first
+  YlArgs<T> a = a0;
+  if (dyn) {
+    a.P.theta = dyn->theta; a.P.scale = dyn->scale; a.P.fill = dyn->fill;
+    a.P.key_thr = dyn->key_thr; a.P.keep_all = dyn->keep_all; a.P.keep_none = dyn->keep_none;
+  }
+  double d[3] = {0.0, 0.0, 0.0};
+  const T rho = a.rho, gamma = a.gamma;
+  const T rho1 = (T)1.0 / rho;
+  const bool relaxed = !(gamma == (T)1);
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.op.rows; r += (i64)gridDim.x * blockDim.x) {
+    const T v = a.y[r];
+    const T s = a.s[r];
+    const T lo = a.l[r];
+    const T yn = proj_apply<T>(a.P, v, r);
+    const T rp = -s + yn;
+    T ln;
+    if (relaxed) {
+      const T xh = gamma * s + ((T)1.0 - gamma) * a.y_old[r];
+      ln = lo + rho * (-xh + yn);
+    } else {
+      ln = lo + rho * rp;
+    }
+    a.y[r] = yn;
+    a.l[r] = ln;
+    d[0] += (double)rp * (double)rp;
+  }
+  if (grid_sum<3>(d, rs) && threadIdx.x == 0) {
+    out[0] = d[0];
+  }
+}
+
+// feasibility / in-place projection with dynamic parameters; `ref` (optional) is the vector P(v) is
+// compared with (cardinality ties are resolved on a scratch copy)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_feas_dyn(i64 M, T* __restrict__ v, const T* __restrict__ ref,
+                                                       const __grid_constant__ ProjDev<T> P0,
+                                                       const ProjParams<T>* dyn, int apply, RedScratch rs,
+                                                       double* out) {
+  ProjDev<T> P = P0;
+  if (dyn) {
+    P.theta = dyn->theta; P.scale = dyn->scale; P.fill = dyn->fill;
+    P.key_thr = dyn->key_thr; P.keep_all = dyn->keep_all; P.keep_none = dyn->keep_none;
+  }
+  double d[2] = {0.0, 0.0};
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const T t = v[r];
+    const T t0 = ref ? ref[r] : t;
+    const T pt = proj_apply<T>(P, t, r);
+    const T pf = pt - t0;
+    d[0] += (double)pf * (double)pf;
+    d[1] += (double)t0 * (double)t0;
+    if (apply) v[r] = pt;
+  }
+  if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
+    out[0] = d[0];
+    out[1] = d[1];
+  }
+}
+
+}  // namespace sipb
+
+// =============================================================================================
+// operator descriptors (host)
+// =============================================================================================
+static int64_t op_rows_host(int ndim, const int64_t* n, int op_kind) {
+  const int64_t n0 = n[0], n1 = n[1], n2 = (ndim == 3) ? n[2] : 1;
+  const int64_t N = n0 * n1 * n2;
+  switch (op_kind) {
+    case SIPB_OP_IDENTITY: return N;
+    case SIPB_OP_DX: return (n0 - 1) * n1 * n2;
+    case SIPB_OP_DY: return ndim == 3 ? n0 * (n1 - 1) * n2 : -1;
+    case SIPB_OP_DZ: return ndim == 3 ? n0 * n1 * (n2 - 1) : n0 * (n1 - 1);
+    case SIPB_OP_TV:
+      return ndim == 3 ? (n0 - 1) * n1 * n2 + n0 * (n1 - 1) * n2 + n0 * n1 * (n2 - 1)
+                       : (n0 - 1) * n1 + n0 * (n1 - 1);
+    case SIPB_OP_DXZ: return ndim == 2 ? (n0 - 1) * (n1 - 1) : -1;
+    default: return -1;
+  }
+}
+
+template <typename T>
+static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int block_mode, OpDev* out) {
+  SIPB_REQUIRE(ndim == 2 || ndim == 3, SIPB_E_INVALID, "ndim must be 2 or 3");
+  OpDev op;
+  memset(&op, 0, sizeof(op));
+  op.kind = op_kind;
+  op.mode = block_mode;
+  op.n[0] = (unsigned)n[0];
+  op.n[1] = (unsigned)n[1];
+  op.n[2] = (ndim == 3) ? (unsigned)n[2] : 1u;
+  op.npts = (i64)n[0] * n[1] * ((ndim == 3) ? n[2] : 1);
+  op.cols = (block_mode == SIPB_BLOCK_PLAIN) ? op.npts : 2 * op.npts;
+  for (int a = 0; a < 3; ++a) {
+    // (-1 or 1) ./ h evaluated in TF: get_discrete_Grad.jl:22-23,58-60 with h = TF(comp_grid.d[a])
+    const T hh = (a < ndim) ? (T)h[a] : (T)1;
+    op.ih[a] = (double)((T)1 / hh);
+  }
+  op.a_xz = (double)((T)op.ih[1] * (T)op.ih[0]);
+  const int64_t rows = op_rows_host(ndim, n, op_kind);
+  SIPB_REQUIRE(rows >= 0, SIPB_E_UNSUPPORTED, "operator kind not available for this grid dimensionality");
+  SIPB_REQUIRE(rows < (int64_t)4294967295ll && op.npts < (int64_t)4294967295ll, SIPB_E_UNSUPPORTED,
+               "operator with more than 2^32-1 rows");
+  op.rows = rows;
+  const int last_axis = ndim - 1;
+  auto blk_rows = [&](int a) -> i64 {
+    i64 r = 1;
+    for (int q = 0; q < 3; ++q) r *= (i64)(q == a ? op.n[q] - 1 : op.n[q]);
+    return r;
+  };
+  switch (op_kind) {
+    case SIPB_OP_IDENTITY: op.nblk = 1; break;
+    case SIPB_OP_DX: op.nblk = 1; op.axis[0] = 0; break;
+    case SIPB_OP_DY: op.nblk = 1; op.axis[0] = 1; break;
+    case SIPB_OP_DZ: op.nblk = 1; op.axis[0] = last_axis; break;
+    case SIPB_OP_TV:
+      op.nblk = ndim;
+      for (int b = 0; b < ndim; ++b) op.axis[b] = last_axis - b;   // vcat(D_z[,D_y],D_x)
+      break;
+    case SIPB_OP_DXZ: op.nblk = 1; break;
+    default: SIPB_REQUIRE(false, SIPB_E_UNSUPPORTED, "unknown operator kind");
+  }
+  op.row_start[0] = 0;
+  if (op_kind != SIPB_OP_IDENTITY && op_kind != SIPB_OP_DXZ) {
+    for (int b = 0; b < op.nblk; ++b) op.row_start[b + 1] = op.row_start[b] + blk_rows(op.axis[b]);
+  } else {
+    op.row_start[1] = rows;
+  }
+  for (int a = 0; a < ndim; ++a)
+    SIPB_REQUIRE(n[a] >= 2, SIPB_E_INVALID, "every grid dimension must be at least 2");
+  *out = op;
+  return SIPB_OK;
+}
+
+// =============================================================================================
+// problem
+// =============================================================================================
+struct sipb_problem {
+  sipb_ctx* ctx;
+  int dtype;
+  virtual ~sipb_problem() {}
+  virtual int add_set(const sipb_set_desc* d) = 0;
+  virtual int set_ata(int idx, const void* R, int64_t rows, const int64_t* offs, int nd) = 0;
+  virtual int finalize() = 0;
+  virtual int solve(const void* m, void* x, void* const* l, void* const* y, const sipb_options* o, sipb_log* log) = 0;
+  virtual int q_offsets(std::vector<int64_t>& out) = 0;
+};
+
+namespace sipb {
+
+static inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+struct SetT {
+  sipb_set_desc desc;
+  OpDev op;
+  i64 M = 0;
+  DevBuf<T> y, l, y_old, l_old, s, s0, y0, l0, lhat0;
+  DevBuf<T> lo_vec, hi_vec;
+  DevBuf<T> ata;              // [nd][ld]
+  int nd = 0;
+  std::vector<int64_t> offs;
+  std::vector<int> qcol;      // column of Q for each diagonal of AtA
+  bool has_ata = false;
+  DevBuf<ProjParams<T>> pp_y, pp_f;   // dynamic projector parameters: y-update / feasibility
+  DevBuf<double> warm;        // [2] warm-start thresholds (y-update, feasibility)
+};
+
+template <typename T>
+struct Problem : sipb_problem {
+  int ndim;
+  int64_t n[3];
+  double h[3];
+  bool minkowski, feas_only, finalized = false;
+  i64 npts, N;                // grid points, unknowns (2*npts for Minkowski)
+  i64 ld;                     // leading dimension of CDS arrays
+  std::vector<std::unique_ptr<SetT<T>>> sets;
+  std::vector<int64_t> q_offs;
+  DevBuf<T> Q, x, x_old, rhs, r, pvec, Ap, m, tmp;
+  i64 maxM = 0;
+
+  Problem(sipb_ctx* c, int dt, int nd_, const int64_t* n_, const double* h_, bool mk, bool fo) {
+    ctx = c; dtype = dt; ndim = nd_; minkowski = mk; feas_only = fo;
+    for (int a = 0; a < 3; ++a) { n[a] = (a < nd_) ? n_[a] : 1; h[a] = (a < nd_) ? h_[a] : 1.0; }
+    npts = n[0] * n[1] * n[2];
+    N = mk ? 2 * npts : npts;
+    ld = (N + 63) / 64 * 64;
+  }
+
+  int add_set(const sipb_set_desc* d) override {
+    SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
+    SIPB_REQUIRE((int)sets.size() < kMaxSets, SIPB_E_UNSUPPORTED, "too many sets");
+    SIPB_REQUIRE(d->set_kind >= SIPB_SET_BOUNDS_SCALAR && d->set_kind <= SIPB_SET_DISTANCE, SIPB_E_UNSUPPORTED,
+                 "set type is outside the device hot path (rank, nuclear, subspace, histogram and fiber/slice "
+                 "modes are rejected)");
+    SIPB_REQUIRE(minkowski ? d->block_mode != SIPB_BLOCK_PLAIN : d->block_mode == SIPB_BLOCK_PLAIN, SIPB_E_INVALID,
+                 "block_mode inconsistent with the Minkowski flag of the problem");
+    if (d->set_kind == SIPB_SET_L1) SIPB_REQUIRE(d->max > 0.0, SIPB_E_INVALID, "Radius of L1 ball is negative");
+    auto S = std::make_unique<SetT<T>>();
+    S->desc = *d;
+    int rc = make_op<T>(ndim, n, h, d->op_kind, d->block_mode, &S->op);
+    if (rc) return rc;
+    S->M = S->op.rows;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M); };
+    A(S->y); A(S->l); A(S->y_old); A(S->l_old); A(S->s); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
+    if (e == cudaSuccess) e = S->pp_y.alloc(1);
+    if (e == cudaSuccess) e = S->pp_f.alloc(1);
+    if (e == cudaSuccess) e = S->warm.alloc(2);
+    SIPB_CUDA_CHECK(e);
+    SIPB_CUDA_CHECK(cudaMemsetAsync(S->warm.p, 0, 2 * sizeof(double), ctx->stream));
+    SIPB_CUDA_CHECK(cudaMemsetAsync(S->pp_y.p, 0, sizeof(ProjParams<T>), ctx->stream));
+    SIPB_CUDA_CHECK(cudaMemsetAsync(S->pp_f.p, 0, sizeof(ProjParams<T>), ctx->stream));
+    if (d->set_kind == SIPB_SET_BOUNDS_VECTOR) {
+      SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
+      SIPB_CUDA_CHECK(S->lo_vec.alloc((size_t)S->M));
+      SIPB_CUDA_CHECK(S->hi_vec.alloc((size_t)S->M));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(S->lo_vec.p, d->min_vec, S->M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(S->hi_vec.p, d->max_vec, S->M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+      SIPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+      S->desc.min_vec = S->desc.max_vec = nullptr;
+    }
+    maxM = std::max<i64>(maxM, S->M);
+    sets.push_back(std::move(S));
+    return SIPB_OK;
+  }
+
+  int set_ata(int idx, const void* R, int64_t rows, const int64_t* offs, int nd) override {
+    SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
+    SIPB_REQUIRE(idx >= 0 && idx < (int)sets.size(), SIPB_E_INVALID, "set index out of range");
+    SIPB_REQUIRE(rows == N, SIPB_E_INVALID, "AtA must have N rows");
+    SIPB_REQUIRE(nd >= 1 && nd <= kMaxDiag, SIPB_E_UNSUPPORTED, "number of diagonals outside [1,32]");
+    SetT<T>& S = *sets[idx];
+    SIPB_CUDA_CHECK(S.ata.alloc((size_t)ld * nd));
+    SIPB_CUDA_CHECK(cudaMemsetAsync(S.ata.p, 0, (size_t)ld * nd * sizeof(T), ctx->stream));
+    SIPB_CUDA_CHECK(cudaMemcpy2DAsync(S.ata.p, ld * sizeof(T), R, N * sizeof(T), N * sizeof(T), nd,
+                                      cudaMemcpyHostToDevice, ctx->stream));
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    S.nd = nd;
+    S.offs.assign(offs, offs + nd);
+    S.has_ata = true;
+    return SIPB_OK;
+  }
+
+  int finalize() override {
+    SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
+    SIPB_REQUIRE(!sets.empty(), SIPB_E_INVALID, "no sets");
+    for (auto& S : sets) SIPB_REQUIRE(S->has_ata, SIPB_E_STATE, "AtA missing for a set");
+    if (!feas_only)
+      SIPB_REQUIRE(sets.back()->desc.set_kind == SIPB_SET_DISTANCE, SIPB_E_INVALID,
+                   "the last set must be the distance term unless feasibility_only");
+    for (size_t i = 0; i + 1 < sets.size(); ++i)
+      SIPB_REQUIRE(sets[i]->desc.set_kind != SIPB_SET_DISTANCE, SIPB_E_INVALID, "distance term must be last");
+    // Q_offsets = unique(all_offsets) over the zero-padded 999x99 table, column-major
+    // (PARSDMM_initialize.jl:217-221): offsets of AtA[1], then 0, then the unseen ones of AtA[2], ...
+    q_offs.clear();
+    auto push_unique = [&](int64_t o) {
+      if (std::find(q_offs.begin(), q_offs.end(), o) == q_offs.end()) q_offs.push_back(o);
+    };
+    SIPB_REQUIRE(sets.size() <= 99, SIPB_E_UNSUPPORTED, "more than 99 operators");
+    for (size_t i = 0; i < sets.size(); ++i) {
+      for (int64_t o : sets[i]->offs) push_unique(o);
+      push_unique(0);   // padding zeros of column i (every column is padded: nd <= 32 < 999)
+    }
+    SIPB_REQUIRE((int)q_offs.size() <= kMaxDiag, SIPB_E_UNSUPPORTED, "Q has more than 32 diagonals");
+    for (auto& S : sets) {
+      S->qcol.resize(S->nd);
+      for (int k = 0; k < S->nd; ++k) {
+        auto it = std::find(q_offs.begin(), q_offs.end(), S->offs[k]);
+        SIPB_REQUIRE(it != q_offs.end(), SIPB_E_MISSING_DIAG, "diagonal missing in Q");
+        S->qcol[k] = (int)(it - q_offs.begin());
+      }
+    }
+    cudaError_t e = cudaSuccess;
+    auto A = [&](DevBuf<T>& b, size_t cnt) { if (e == cudaSuccess) e = b.alloc(cnt); };
+    A(Q, (size_t)ld * q_offs.size());
+    const size_t halo = 0;
+    A(x, (size_t)N + halo); A(x_old, (size_t)N); A(rhs, (size_t)N); A(r, (size_t)N); A(pvec, (size_t)N);
+    A(Ap, (size_t)N); A(m, (size_t)N); A(tmp, (size_t)std::max<i64>(maxM, N));
+    SIPB_CUDA_CHECK(e);
+    finalized = true;
+    return SIPB_OK;
+  }
+
+  int q_offsets(std::vector<int64_t>& out) override {
+    SIPB_REQUIRE(finalized, SIPB_E_STATE, "problem not finalized");
+    out = q_offs;
+    return SIPB_OK;
+  }
+
+  // ---- helpers ------------------------------------------------------------------------------
+  SpmvArgs<T> spmv_args(const T* xin, T* yout) const {
+    SpmvArgs<T> a;
+    a.R = Q.p; a.ld = ld; a.nd = (int)q_offs.size();
+    for (int j = 0; j < a.nd; ++j) a.off[j] = q_offs[j];
+    a.N = N; a.row0 = 0; a.Nglob = N; a.x = xin; a.y = yout;
+    return a;
+  }
+
+  ProjDev<T> proj_static(const SetT<T>& S, T rho_dist) const {
+    ProjDev<T> P;
+    memset(&P, 0, sizeof(P));
+    P.kind = S.desc.set_kind;
+    P.lo = (T)S.desc.min;
+    P.hi = (T)S.desc.max;
+    P.lo_vec = S.lo_vec.p;
+    P.hi_vec = S.hi_vec.p;
+    P.m = m.p;
+    P.rho = (S.desc.set_kind == SIPB_SET_PROX_L1) ? (T)S.desc.max : rho_dist;
+    P.theta = (T)-1; P.scale = (T)1; P.fill = (T)NAN; P.key_thr = 0ull; P.keep_all = 1; P.keep_none = 0;
+    return P;
+  }
+
+  // Computes the dynamic parameters of a reduction-type projector for the vector `v` whose stats
+  // (sum|v|, sum v^2, nnz) sit in d_scal[stat_slot..].  No host synchronisation except the polling
+  // of the l1 Newton iteration.
+  int projector_params(SetT<T>& S, T* v, int stat_slot, ProjParams<T>* pp, double* warm, bool allow_tie_zero) {
+    sipb_ctx* c = ctx;
+    const int kind = S.desc.set_kind;
+    const i64 M = S.M;
+    double* stats = c->d_scal + stat_slot;
+    if (kind == SIPB_SET_L1) {
+      LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)M, warm, c->d_l1, pp);
+      int launched = 0;
+      for (;;) {
+        const int batch = (launched == 0) ? 6 : 8;
+        for (int b = 0; b < batch; ++b) LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for(M), M, v, c->rs, c->d_l1);
+        launched += batch;
+        SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_l1, c->d_l1, sizeof(L1State), cudaMemcpyDeviceToHost, c->stream));
+        SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (c->h_l1->done || launched >= 256) break;
+      }
+      LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
+    } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {
+      LAUNCH1(c, KC_PARAMS, k_l2_params<T>, stats, kind, S.desc.min, S.desc.max, (double)M, pp);
+    } else if (kind == SIPB_SET_CARDINALITY) {
+      LAUNCH1(c, KC_PARAMS, k_sel_begin<T>, (long long)S.desc.k, (long long)M, c->d_sel, pp);
+      const int npass = (int)sizeof(T);
+      for (int q = 0; q < npass; ++q)
+        LAUNCH(c, KC_RADIX_HIST, k_radix_hist<T>, c->grid_for(M), M, v, c->d_sel, c->d_counter2);
+      LAUNCH1(c, KC_PARAMS, k_sel_end<T>, c->d_sel, pp);
+      if (allow_tie_zero) {
+        const int g = c->max_grid();
+        const i64 chunk = ((M + g - 1) / g + kThreads - 1) / kThreads * kThreads;
+        LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, M, v, pp, chunk, c->d_tie_counts);
+        LAUNCH(c, KC_TIES, k_tie_zero_p<T>, g, M, v, pp, chunk, c->d_tie_counts);
+      }
+    }
+    return SIPB_OK;
+  }
+
+  // relative feasibility numerator/denominator of vector s (stored in S.s) -> d_scal[slot], [slot+1]
+  int feasibility_of(SetT<T>& S, int slot) {
+    sipb_ctx* c = ctx;
+    const i64 M = S.M;
+    ProjDev<T> P = proj_static(S, (T)0);
+    if (proj_is_elementwise(S.desc.set_kind)) {
+      LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, S.s.p, (const T*)nullptr, P, (const ProjParams<T>*)nullptr, 0,
+             c->rs, c->d_scal + slot);
+      return SIPB_OK;
+    }
+    const int stat_slot = slot + 10;
+    LAUNCH(c, KC_VEC_STATS, k_vec_stats<T>, c->grid_for(M), M, S.s.p, c->rs, c->d_scal + stat_slot);
+    T* vec = S.s.p;
+    const T* ref = nullptr;
+    if (S.desc.set_kind == SIPB_SET_CARDINALITY) {   // ties are resolved on a scratch copy
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(tmp.p, S.s.p, M * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+      vec = tmp.p;
+      ref = S.s.p;
+    }
+    int rc = projector_params(S, vec, stat_slot, S.pp_f.p, S.warm.p + 1, true);
+    if (rc) return rc;
+    LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, vec, ref, P, (const ProjParams<T>*)S.pp_f.p, 0, c->rs,
+           c->d_scal + slot);
+    return SIPB_OK;
+  }
+
+  // device CG on Q (cg.jl:44-128).  parsdmm_it > 0 selects the argmin_x tolerance rule.
+  int run_cg(const T* b, T* xv, T* x_old_out, int parsdmm_it, double tol, int max_iter, int predicted,
+             int* iters, double* relres, int* flag) {
+    sipb_ctx* c = ctx;
+    CgState* h = c->h_cg;
+    // only the control fields are (re)written; tol_prev persists on the device between calls
+    h->maxit = max_iter;
+    h->parsdmm_it = parsdmm_it;
+    h->tol = tol;
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->maxit, &h->maxit, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->parsdmm_it, &h->parsdmm_it, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (parsdmm_it == 0)
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol, &h->tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
+    LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g, spmv_args(xv, nullptr), b, r.p, pvec.p, x_old_out, c->rs, c->d_cg);
+    LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg);
+    int launched = 0;
+    int batch = std::max(1, predicted);
+    for (;;) {
+      if (launched > 0 || batch > 0) {
+        for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
+          LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args(pvec.p, Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done);
+          LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pvec.p, Ap.p, c->rs, c->d_cg);
+          LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pvec.p, c->rs, c->d_cg);
+        }
+      }
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+      SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (h->done || launched >= max_iter) break;
+      batch = std::max(2, launched / 2);
+    }
+    if (h->flag == -9) SIPB_CUDA_CHECK(cudaMemsetAsync(xv, 0, N * sizeof(T), c->stream));   // cg.jl:47
+    *iters = h->iter;
+    *relres = h->relres;
+    *flag = h->flag;
+    return SIPB_OK;
+  }
+
+  int solve(const void* m_h, void* x_h, void* const* l_h, void* const* y_h, const sipb_options* o,
+            sipb_log* log) override;
+};
+
+// ---------------------------------------------------------------------------------------------
+// scalar logic in TF arithmetic
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static void adapt_scalar(const double* sm, T& rho, T& gamma, bool adjust_rho, bool adjust_gamma) {
+  // adapt_rho_gamma.jl:31-126
+  const T safeguard = (sizeof(T) == 8) ? (T)1e-10 : (T)1e-6f;
+  const T eps_corr = (T)0.3;
+  const T d_dHh_dlh = (T)sm[0];
+  const T n_dH = (T)std::sqrt(sm[1]);
+  const T n_dlh = (T)std::sqrt(sm[2]);
+  const T n_dl = (T)std::sqrt(sm[3]);
+  const T n_dG = (T)std::sqrt(sm[4]);
+  const T d_dGh_dl = (T)sm[5];
+  bool alpha_rel = false, beta_rel = false;
+  T alpha_corr = 0, beta_corr = 0;
+  if ((n_dH * n_dlh) > safeguard && (n_dH * n_dH) > safeguard && d_dHh_dlh > safeguard) {
+    alpha_rel = true;
+    alpha_corr = d_dHh_dlh / (n_dH * n_dlh);
+  }
+  if ((n_dG * n_dl) > safeguard && (n_dG * n_dG) > safeguard && d_dGh_dl > safeguard) {
+    beta_rel = true;
+    beta_corr = d_dGh_dl / (n_dG * n_dl);
+  }
+  bool alpha_comp = false, beta_comp = false;
+  T alpha_hat = 0, beta_hat = 0;
+  if (alpha_rel && alpha_corr > eps_corr) {
+    alpha_comp = true;
+    const T mg = d_dHh_dlh / (n_dH * n_dH);
+    const T sd = (n_dlh * n_dlh) / d_dHh_dlh;
+    alpha_hat = ((T)2.0 * mg > sd) ? mg : sd - mg / (T)2.0;
+  }
+  if (beta_rel && beta_corr > eps_corr) {
+    beta_comp = true;
+    const T mg = d_dGh_dl / (n_dG * n_dG);
+    const T sd = (n_dl * n_dl) / d_dGh_dl;
+    beta_hat = ((T)2.0 * mg > sd) ? mg : sd - mg / (T)2.0;
+  }
+  if (adjust_rho) {
+    if (alpha_comp && beta_comp) rho = std::sqrt(alpha_hat * beta_hat);
+    else if (alpha_comp) rho = alpha_hat;
+    else if (beta_comp) rho = beta_hat;
+  }
+  if (adjust_gamma) {
+    if (alpha_comp && beta_comp)
+      gamma = (T)1.0 + (((T)2.0 * std::sqrt(alpha_hat * beta_hat)) / (alpha_hat + beta_hat));
+    else if (alpha_comp) gamma = (T)1.9;
+    else if (beta_comp) gamma = (T)1.1;
+    else gamma = (T)1.5;
+  }
+}
+
+static inline double jl_maximum(const double* a, int n, int stride = 1) {
+  double m = -std::numeric_limits<double>::infinity();
+  for (int i = 0; i < n; ++i) {
+    const double v = a[(size_t)i * stride];
+    if (v != v) return v;
+    if (v > m) m = v;
+  }
+  return m;
+}
+
+// =============================================================================================
+// the PARSDMM loop
+// =============================================================================================
+template <typename T>
+int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const* y_h, const sipb_options* o,
+                      sipb_log* log) {
+  SIPB_REQUIRE(finalized, SIPB_E_STATE, "problem not finalized");
+  SIPB_REQUIRE(m_h && x_h && o && log, SIPB_E_INVALID, "null argument");
+  sipb_ctx* c = ctx;
+  const double t_begin = now_s();
+  c->reset_accounting();
+  c->profile = o->profile_kernels != 0;
+  const int p = (int)sets.size();
+  const int pp = feas_only ? p : p - 1;
+  const int maxit = o->maxit;
+  SIPB_REQUIRE(maxit >= 1, SIPB_E_INVALID, "maxit must be >= 1");
+  SIPB_REQUIRE(o->n_rho_ini == 1 || o->n_rho_ini == p, SIPB_E_INVALID, "rho_ini must have 1 or p entries");
+  SIPB_REQUIRE(o->rho_update_frequency >= 1, SIPB_E_INVALID, "rho_update_frequency must be >= 1");
+  if (!o->zero_ini_guess) SIPB_REQUIRE(l_h && y_h, SIPB_E_INVALID, "warm start needs l and y");
+  if (o->return_ly) SIPB_REQUIRE(l_h && y_h, SIPB_E_INVALID, "return_ly needs l and y");
+  log->p = p; log->pp = pp; log->iters = 0; log->feas_rows = 1; log->stopped_feasible = 0;
+  log->h2d_bytes = 0; log->d2h_bytes = 0;
+  for (int q = 0; q < SIPB_N_PHASES; ++q) log->phase_seconds[q] = 0.0;
+  double t_phase = now_s();
+  auto phase_end = [&](int ph) { const double t = now_s(); log->phase_seconds[ph] += t - t_phase; t_phase = t; };
+
+  // ---------------- initialization (PARSDMM_initialize.jl) ------------------------------------
+  const T feas_tol = (T)o->feas_tol, obj_tol = (T)o->obj_tol, evol_rel_tol = (T)o->evol_rel_tol;
+  int rho_update_frequency = o->rho_update_frequency;
+  bool adjust_rho = o->adjust_rho != 0, adjust_gamma = o->adjust_gamma != 0;
+  bool adjust_feasibility_rho = o->adjust_feasibility_rho != 0;
+  T gamma_ini = (T)o->gamma_ini;
+  std::vector<T> rho(p), gamma(p);
+  for (int i = 0; i < p; ++i) rho[i] = (T)(o->n_rho_ini == 1 ? o->rho_ini[0] : o->rho_ini[i]);
+
+  // m (for Minkowski the feasibility check uses [m; 0], PARSDMM_initialize.jl:85-87)
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(m.p, m_h, npts * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  log->h2d_bytes += npts * sizeof(T);
+  if (minkowski) SIPB_CUDA_CHECK(cudaMemsetAsync(m.p + npts, 0, npts * sizeof(T), c->stream));
+
+  // initial feasibility  ||P(A m) - A m|| / (||A m|| + 100 eps)   (:97-99)
+  const int nP = pp;   // P_sub has one entry per non-distance set
+  for (int i = 0; i < nP; ++i) {
+    SetT<T>& S = *sets[i];
+    LAUNCH(c, KC_OP_APPLY, k_op_forward<T>, c->grid_for(S.M), S.op, (const T*)m.p, S.s.p);
+    int rc = feasibility_of(S, i * kSlotPerSet + 1);
+    if (rc) return rc;
+  }
+  { int rc = ctx_sync_scalars(c); if (rc) return rc; }
+  std::vector<double> feas0(std::max(nP, 1), 0.0);
+  const T eps100 = (T)100 * (T)Eps<T>::v;
+  for (int i = 0; i < nP; ++i) {
+    const T num = (T)std::sqrt(c->h_scal[i * kSlotPerSet + 1]);
+    const T den = (T)std::sqrt(c->h_scal[i * kSlotPerSet + 2]);
+    feas0[i] = (double)(num / (den + eps100));
+  }
+  for (int i = 0; i < nP; ++i) log->set_feasibility[i] = feas0[i];
+  bool stop = nP > 0 && (T)jl_maximum(feas0.data(), nP) < feas_tol;   // :101-104
+  if (o->fixed_iterations > 0) stop = false;
+
+  for (int i = 0; i < pp; ++i)                                     // :107-114
+    if (sets[i]->desc.ncvx) { rho_update_frequency = 3; adjust_gamma = false; gamma_ini = (T)0.75; }
+  for (int i = 0; i < p; ++i) gamma[i] = gamma_ini;
+
+  if (stop) {                                                      // PARSDMM.jl:63-82
+    // x = m (Minkowski: [m; 0]); device buffer m already holds exactly that
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, m.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    log->d2h_bytes += N * sizeof(T);
+    log->stopped_feasible = 1;
+    log->iters = 0;
+    log->feas_rows = 1;
+    log->total_launches = c->total_launches;
+    c->collect_profile();
+    for (int q = 0; q < SIPB_N_KERNEL_CLASSES; ++q) { log->kernel_launches[q] = c->launches[q]; log->kernel_ms[q] = c->ms[q]; }
+    phase_end(0);
+    log->solve_seconds = now_s() - t_begin;
+    log->device_seconds = 0.0;
+    return SIPB_OK;
+  }
+
+  // start vectors (:304-313 zero guess, otherwise the caller's x,l,y)
+  if (o->zero_ini_guess) {
+    SIPB_CUDA_CHECK(cudaMemsetAsync(x.p, 0, N * sizeof(T), c->stream));
+    for (auto& S : sets) {
+      SIPB_CUDA_CHECK(cudaMemsetAsync(S->y.p, 0, S->M * sizeof(T), c->stream));
+      SIPB_CUDA_CHECK(cudaMemsetAsync(S->l.p, 0, S->M * sizeof(T), c->stream));
+    }
+  } else {
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(x.p, x_h, N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    log->h2d_bytes += N * sizeof(T);
+    for (int i = 0; i < p; ++i) {
+      SetT<T>& S = *sets[i];
+      SIPB_REQUIRE(l_h[i] && y_h[i], SIPB_E_INVALID, "warm start needs every l[i], y[i]");
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(S.l.p, l_h[i], S.M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(S.y.p, y_h[i], S.M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+      log->h2d_bytes += 2 * S.M * sizeof(T);
+    }
+  }
+  for (auto& S : sets) {
+    // the 16 work vectors of PARSDMM_initialize.jl:158-184 collapse to these; all start at zero
+    for (DevBuf<T>* b : {&S->y_old, &S->l_old, &S->s, &S->s0, &S->y0, &S->l0, &S->lhat0})
+      SIPB_CUDA_CHECK(cudaMemsetAsync(b->p, 0, S->M * sizeof(T), c->stream));
+    SIPB_CUDA_CHECK(cudaMemsetAsync(S->warm.p, 0, 2 * sizeof(double), c->stream));
+  }
+  SIPB_CUDA_CHECK(cudaMemsetAsync(x_old.p, 0, N * sizeof(T), c->stream));
+
+  // Q = sum rho_i AtA_i, accumulated set by set, diagonal by diagonal (:223-229)
+  SIPB_CUDA_CHECK(cudaMemsetAsync(Q.p, 0, (size_t)ld * q_offs.size() * sizeof(T), c->stream));
+  const int gN = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
+  for (int i = 0; i < p; ++i) {
+    SetT<T>& S = *sets[i];
+    for (int k = 0; k < S.nd; ++k)
+      LAUNCH(c, KC_Q_UPDATE, k_cds_axpy<T>, gN, N, Q.p + (size_t)S.qcol[k] * ld, (const T*)(S.ata.p + (size_t)k * ld), rho[i]);
+  }
+  // reset tolerance memory (x_solve_tol_ref = TF(1.0), PARSDMM.jl:93)
+  c->h_cg->tol_prev = 1.0;
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol_prev, &c->h_cg->tol_prev, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+
+  int ind_ref = maxit;                                             // PARSDMM_initialize.jl:30
+  int counter = 2;                                                 // PARSDMM.jl:91
+  const int p_log = p;
+  auto LG = [&](double* arr, int it, int col, int ncol) -> double& { return arr[(size_t)it * ncol + col]; };
+  phase_end(0);
+
+  cudaEvent_t ev0, ev1;
+  SIPB_CUDA_CHECK(cudaEventCreate(&ev0));
+  SIPB_CUDA_CHECK(cudaEventCreate(&ev1));
+  SIPB_CUDA_CHECK(cudaEventRecord(ev0, c->stream));
+
+  int last_cg = 1;
+  int iters_done = 0;
+  const int it_limit = o->fixed_iterations > 0 ? std::min(o->fixed_iterations, maxit) : maxit;
+  for (int i = 1; i <= it_limit; ++i) {
+    // ---------------- rhs (rhs_compose.jl) ---------------------------------------------------
+    {
+      RhsArgs<T> ra;
+      memset(&ra, 0, sizeof(ra));
+      ra.nsets = p;
+      ra.n[0] = (unsigned)n[0]; ra.n[1] = (unsigned)n[1]; ra.n[2] = (unsigned)n[2];
+      ra.npts = npts; ra.ncols = N; ra.rhs = rhs.p;
+      for (int s = 0; s < p; ++s) {
+        ra.sets[s].op = sets[s]->op;
+        ra.sets[s].y = sets[s]->y.p;
+        ra.sets[s].l = sets[s]->l.p;
+        ra.sets[s].rho = rho[s];
+      }
+      LAUNCH(c, KC_RHS, k_rhs<T>, c->grid_for(N), ra);
+    }
+    phase_end(1);
+    // ---------------- x-minimisation (argmin_x.jl + cg.jl) -----------------------------------
+    int cg_it = 0, cg_flag = 0;
+    double cg_relres = 0.0;
+    {
+      int rc = run_cg(rhs.p, x.p, x_old.p, i, 0.0, 1000, last_cg + 1, &cg_it, &cg_relres, &cg_flag);
+      if (rc) return rc;
+      last_cg = cg_it;
+    }
+    log->cg_it[i - 1] = cg_it;
+    log->cg_relres[i - 1] = cg_relres;
+    phase_end(2);
+    // ---------------- y / l update (update_y_l.jl) --------------------------------------------
+    const bool feas_it = (i % 10 == 0);
+    for (int s = 0; s < p; ++s) {
+      SetT<T>& S = *sets[s];
+      const bool is_dist = S.desc.set_kind == SIPB_SET_DISTANCE;
+      const bool want_feas = feas_it && !is_dist;
+      YlArgs<T> ya;
+      memset(&ya, 0, sizeof(ya));
+      ya.op = S.op;
+      ya.P = proj_static(S, rho[s]);
+      ya.x = x.p; ya.y = S.y.p; ya.l = S.l.p; ya.y_old = S.y_old.p; ya.l_old = S.l_old.p; ya.s = S.s.p;
+      ya.rho = rho[s]; ya.gamma = gamma[s];
+      const int base = s * kSlotPerSet;
+      if (proj_is_elementwise(S.desc.set_kind)) {
+        ya.want_feas = want_feas ? 1 : 0;
+        LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0>), c->grid_for(S.M), ya, c->rs, c->d_scal + base);
+      } else {
+        ya.want_feas = 0;
+        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1>), c->grid_for(S.M), ya, c->rs, c->d_scal + base + 10);
+        int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
+        if (rc) return rc;
+        LAUNCH(c, KC_YL_PASS2, (k_yl_dyn<T, 2>), c->grid_for(S.M), ya, (const ProjParams<T>*)S.pp_y.p, c->rs,
+               c->d_scal + base);
+        if (want_feas) {
+          rc = feasibility_of(S, base + 1);
+          if (rc) return rc;
+        }
+      }
+      LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for(npts), S.op, (const T*)S.y.p, (const T*)S.y_old.p, c->rs,
+             c->d_scal + base + 3);
+    }
+    LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
+           (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
+    { int rc = ctx_sync_scalars(c); if (rc) return rc; }
+    {
+      T rp_tot = 0, rd_tot = 0;
+      for (int s = 0; s < p; ++s) {
+        const int base = s * kSlotPerSet;
+        const T rp = (T)std::sqrt(c->h_scal[base + 0]);            // update_y_l.jl:81
+        const T rd = rho[s] * (T)std::sqrt(c->h_scal[base + 3]);   // :84
+        LG(log->r_pri, i - 1, s, p_log) = (double)rp;
+        LG(log->r_dual, i - 1, s, p_log) = (double)rd;
+        rp_tot = rp_tot + rp;
+        rd_tot = rd_tot + rd;
+        if (feas_it && s < pp) {                                   // :90-94
+          const T num = (T)std::sqrt(c->h_scal[base + 1]);
+          const T den = (T)std::sqrt(c->h_scal[base + 2]);
+          LG(log->set_feasibility, counter - 1, s, pp) = (double)(num / (den + eps100));
+        }
+      }
+      if (feas_it) counter += 1;                                   // :103-105
+      log->r_dual_total[i - 1] = (double)rd_tot;                   // PARSDMM.jl:134
+      log->r_pri_total[i - 1] = (double)rp_tot;                    // :138
+      const double* g = c->h_scal + kSlotGlobal;
+      const T nxm = (T)std::sqrt(g[0]);
+      log->obj[i - 1] = (double)((T)0.5 * (nxm * nxm));            // :140/:142
+      log->evol_x[i - 1] = (double)((T)std::sqrt(g[1]) / (T)std::sqrt(g[2]));   // :145
+      for (int s = 0; s < p; ++s) {
+        LG(log->rho, i - 1, s, p_log) = (double)rho[s];
+        LG(log->gamma, i - 1, s, p_log) = (double)gamma[s];
+      }
+    }
+    iters_done = i;
+    phase_end(3);
+    // ---------------- stopping rules (stop_PARSDMM.jl:23-52) ---------------------------------
+    if (o->fixed_iterations <= 0) {
+      bool stp = false;
+      if (i > 6) {
+        double relmax = -std::numeric_limits<double>::infinity();
+        bool nan = false;
+        for (int q = i - 6; q < i; ++q) {   // 0-based rows i-6..i-1 vs previous
+          const T a = (T)log->obj[q], b = (T)log->obj[q - 1];
+          const T rel = std::fabs((a - b) / b);
+          if (rel != rel) nan = true;
+          if ((double)rel > relmax) relmax = (double)rel;
+        }
+        const double fmax = pp > 0 ? jl_maximum(log->set_feasibility + (size_t)(counter - 2) * pp, pp) : 0.0;
+        if (!nan && (T)fmax < feas_tol && (T)relmax < obj_tol) stp = true;
+      }
+      if (i > 5) {
+        const double emax = jl_maximum(log->evol_x + (i - 6), 6);
+        if ((T)emax < evol_rel_tol) stp = true;
+      }
+      {
+        const int lo = std::max(i - 50, 1);
+        if (i > 20 && adjust_rho &&
+            log->r_pri_total[i - 1] > jl_maximum(log->r_pri_total + (lo - 1), (i - 1) - (lo - 1))) {
+          adjust_rho = false; adjust_feasibility_rho = false; adjust_gamma = false;
+          ind_ref = i;
+        }
+        const int lo2 = std::max(ind_ref, std::max(i - 50, 1));
+        if (!adjust_rho && i > ind_ref + 25 &&
+            log->r_pri_total[i - 1] > jl_maximum(log->r_pri_total + (lo2 - 1), (i - 1) - (lo2 - 1)))
+          stp = true;
+      }
+      phase_end(4);
+      if (stp) break;
+    }
+    // ---------------- rho / gamma adaptation (PARSDMM.jl:164-226) ----------------------------
+    const bool do_adapt = (adjust_rho || adjust_gamma) && (i % rho_update_frequency == 0);
+    if (i == 1 || do_adapt) {
+      for (int s = 0; s < p; ++s) {
+        SetT<T>& S = *sets[s];
+        AdaptArgs<T> aa;
+        aa.M = S.M;
+        aa.l_old = S.l_old.p; aa.y_old = S.y_old.p; aa.s = S.s.p; aa.l = S.l.p; aa.y = S.y.p;
+        aa.lhat0 = S.lhat0.p; aa.s0 = S.s0.p; aa.l0 = S.l0.p; aa.y0 = S.y0.p;
+        aa.rho = rho[s];
+        if (i == 1 && do_adapt) {
+          // snapshot first (PARSDMM.jl:164-180), then the sums against that snapshot (all zero deltas)
+          aa.do_sums = 0; aa.do_snapshot = 1;
+          LAUNCH(c, KC_ADAPT, k_adapt<T>, c->grid_for(S.M), aa, c->rs, c->d_scal + s * kSlotPerSet + 4);
+          aa.do_sums = 1; aa.do_snapshot = 0;
+          LAUNCH(c, KC_ADAPT, k_adapt<T>, c->grid_for(S.M), aa, c->rs, c->d_scal + s * kSlotPerSet + 4);
+        } else {
+          aa.do_sums = do_adapt ? 1 : 0;
+          aa.do_snapshot = 1;    // i==1: first snapshot; i>1 after adapt: re-snapshot (:198-206)
+          LAUNCH(c, KC_ADAPT, k_adapt<T>, c->grid_for(S.M), aa, c->rs, c->d_scal + s * kSlotPerSet + 4);
+        }
+      }
+      if (do_adapt) {
+        int rc = ctx_sync_scalars(c);
+        if (rc) return rc;
+        for (int s = 0; s < p; ++s)
+          adapt_scalar<T>(c->h_scal + s * kSlotPerSet + 4, rho[s], gamma[s], adjust_rho, adjust_gamma);
+      }
+    }
+    if (adjust_feasibility_rho && i % 10 == 0 && i > 10 && pp > 0) {       // :213-223
+      const double* row = log->set_feasibility + (size_t)(counter - 2) * pp;
+      int idx = 0;
+      bool have_nan = false;
+      for (int s = 0; s < pp; ++s) {
+        if (row[s] != row[s]) { if (!have_nan) { idx = s; have_nan = true; } }
+        else if (!have_nan && row[s] > row[idx]) idx = s;
+      }
+      rho[idx] = (T)2.0 * rho[idx];
+    }
+    for (int s = 0; s < p; ++s) {                                           // :226
+      T v = rho[s];
+      v = (v != v) ? v : (v < (T)1e4 ? v : (T)1e4);
+      v = (v != v) ? v : (v > (T)1e-2 ? v : (T)1e-2);
+      rho[s] = v;
+    }
+    phase_end(5);
+    // ---------------- Q update (Q_update!.jl:45-49) -------------------------------------------
+    for (int s = 0; s < p; ++s) {
+      const T logged = (T)LG(log->rho, i - 1, s, p_log);
+      if (rho[s] != logged) {
+        SetT<T>& S = *sets[s];
+        const T alpha = rho[s] - logged;
+        for (int k = 0; k < S.nd; ++k)
+          LAUNCH(c, KC_Q_UPDATE, k_cds_axpy<T>, gN, N, Q.p + (size_t)S.qcol[k] * ld, (const T*)(S.ata.p + (size_t)k * ld), alpha);
+      }
+    }
+    phase_end(6);
+  }
+  SIPB_CUDA_CHECK(cudaEventRecord(ev1, c->stream));
+
+  // ---------------- results -------------------------------------------------------------------
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, x.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  log->d2h_bytes += N * sizeof(T);
+  if (o->return_ly) {
+    for (int i = 0; i < p; ++i) {
+      SetT<T>& S = *sets[i];
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(l_h[i], S.l.p, S.M * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(y_h[i], S.y.p, S.M * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+      log->d2h_bytes += 2 * S.M * sizeof(T);
+    }
+  }
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  log->device_seconds = ms * 1e-3;
+  log->iters = iters_done;
+  log->feas_rows = counter;       // output_check_PARSDMM keeps set_feasibility[1:counter,:]
+  c->collect_profile();
+  log->total_launches = c->total_launches;
+  for (int q = 0; q < SIPB_N_KERNEL_CLASSES; ++q) { log->kernel_launches[q] = c->launches[q]; log->kernel_ms[q] = c->ms[q]; }
+  log->solve_seconds = now_s() - t_begin;
+  return SIPB_OK;
+}
+
+}  // namespace sipb
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+int sipb_abi_version(void) { return SIPB_ABI_VERSION; }
+const char* sipb_last_error(void) { return g_err.c_str(); }
+const char* sipb_kernel_class_name(int cls) {
+  return (cls >= 0 && cls < SIPB_N_KERNEL_CLASSES) ? kClassNames[cls] : "";
+}
+
+int sipb_ctx_create(int device, sipb_ctx** out) {
+  SIPB_REQUIRE(out, SIPB_E_INVALID, "null out pointer");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error(std::string("no CUDA device available (") + cudaGetErrorString(e) +
+              "); this library has no CPU fallback");
+    return SIPB_E_CUDA;
+  }
+  SIPB_REQUIRE(device >= 0 && device < ndev, SIPB_E_INVALID, "device index out of range");
+  SIPB_CUDA_CHECK(cudaSetDevice(device));
+  auto* c = new sipb_ctx();
+  c->device = device;
+  c->reset_accounting();
+  cudaDeviceProp prop;
+  SIPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  c->num_sms = prop.multiProcessorCount;
+  SIPB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->rs.partials, sizeof(double) * kMaxRed * kMaxBlocks));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->rs.counter, sizeof(unsigned int)));
+  SIPB_CUDA_CHECK(cudaMemset(c->rs.counter, 0, sizeof(unsigned int)));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_counter2, sizeof(unsigned int)));
+  SIPB_CUDA_CHECK(cudaMemset(c->d_counter2, 0, sizeof(unsigned int)));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_scal, sizeof(double) * kScalSlots));
+  SIPB_CUDA_CHECK(cudaMemset(c->d_scal, 0, sizeof(double) * kScalSlots));
+  SIPB_CUDA_CHECK(cudaMallocHost(&c->h_scal, sizeof(double) * kScalSlots));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_cg, sizeof(CgState)));
+  SIPB_CUDA_CHECK(cudaMemset(c->d_cg, 0, sizeof(CgState)));
+  SIPB_CUDA_CHECK(cudaMallocHost(&c->h_cg, sizeof(CgState)));
+  memset(c->h_cg, 0, sizeof(CgState));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_l1, sizeof(L1State)));
+  SIPB_CUDA_CHECK(cudaMemset(c->d_l1, 0, sizeof(L1State)));
+  SIPB_CUDA_CHECK(cudaMallocHost(&c->h_l1, sizeof(L1State)));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_sel, sizeof(SelState)));
+  SIPB_CUDA_CHECK(cudaMemset(c->d_sel, 0, sizeof(SelState)));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_tie_counts, sizeof(unsigned long long) * kMaxBlocks));
+  *out = c;
+  return SIPB_OK;
+}
+
+int sipb_ctx_destroy(sipb_ctx* c) {
+  if (!c) return SIPB_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& e : c->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
+  cudaFreeHost(c->h_scal); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_l1); cudaFreeHost(c->h_l1);
+  cudaFree(c->d_sel); cudaFree(c->d_tie_counts);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return SIPB_OK;
+}
+
+int sipb_ctx_num_sms(sipb_ctx* c, int* out) {
+  SIPB_REQUIRE(c && out, SIPB_E_INVALID, "null argument");
+  *out = c->num_sms;
+  return SIPB_OK;
+}
+
+int sipb_comm_unique_id(void* out128) {
+  (void)out128;
+  set_error("multi-GPU slabs are not built into this library yet");
+  return SIPB_E_UNSUPPORTED;
+}
+int sipb_comm_init(sipb_ctx* ctx, int rank, int world, const void* uid128) {
+  (void)uid128;
+  SIPB_REQUIRE(ctx, SIPB_E_INVALID, "null ctx");
+  if (world == 1) { ctx->rank = 0; ctx->world = 1; return SIPB_OK; }
+  (void)rank;
+  set_error("multi-GPU slabs are not built into this library yet");
+  return SIPB_E_UNSUPPORTED;
+}
+
+int sipb_problem_create(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const double* h, int minkowski,
+                        int feasibility_only, sipb_problem** out) {
+  SIPB_REQUIRE(ctx && n && h && out, SIPB_E_INVALID, "null argument");
+  SIPB_REQUIRE(dtype == SIPB_F32 || dtype == SIPB_F64, SIPB_E_INVALID, "dtype must be SIPB_F32 or SIPB_F64");
+  SIPB_REQUIRE(ndim == 2 || ndim == 3, SIPB_E_INVALID, "ndim must be 2 or 3");
+  for (int a = 0; a < ndim; ++a) SIPB_REQUIRE(n[a] >= 2, SIPB_E_INVALID, "grid dimensions must be >= 2");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (dtype == SIPB_F32) *out = new Problem<float>(ctx, dtype, ndim, n, h, minkowski != 0, feasibility_only != 0);
+  else *out = new Problem<double>(ctx, dtype, ndim, n, h, minkowski != 0, feasibility_only != 0);
+  return SIPB_OK;
+}
+int sipb_problem_add_set(sipb_problem* pb, const sipb_set_desc* d) {
+  SIPB_REQUIRE(pb && d, SIPB_E_INVALID, "null argument");
+  return pb->add_set(d);
+}
+int sipb_problem_set_ata(sipb_problem* pb, int idx, const void* R, int64_t rows, const int64_t* offs, int nd) {
+  SIPB_REQUIRE(pb && R && offs, SIPB_E_INVALID, "null argument");
+  return pb->set_ata(idx, R, rows, offs, nd);
+}
+int sipb_problem_finalize(sipb_problem* pb) {
+  SIPB_REQUIRE(pb, SIPB_E_INVALID, "null argument");
+  return pb->finalize();
+}
+int sipb_problem_num_q_offsets(sipb_problem* pb, int* nd) {
+  SIPB_REQUIRE(pb && nd, SIPB_E_INVALID, "null argument");
+  std::vector<int64_t> v;
+  int rc = pb->q_offsets(v);
+  if (rc) return rc;
+  *nd = (int)v.size();
+  return SIPB_OK;
+}
+int sipb_problem_q_offsets(sipb_problem* pb, int64_t* out) {
+  SIPB_REQUIRE(pb && out, SIPB_E_INVALID, "null argument");
+  std::vector<int64_t> v;
+  int rc = pb->q_offsets(v);
+  if (rc) return rc;
+  for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+  return SIPB_OK;
+}
+int sipb_problem_destroy(sipb_problem* pb) {
+  if (pb) {
+    cudaSetDevice(pb->ctx->device);
+    cudaStreamSynchronize(pb->ctx->stream);
+    delete pb;
+  }
+  return SIPB_OK;
+}
+int sipb_solve(sipb_problem* pb, const void* m, void* x, void* const* l, void* const* y, const sipb_options* opt,
+               sipb_log* log) {
+  SIPB_REQUIRE(pb, SIPB_E_INVALID, "null problem");
+  SIPB_CUDA_CHECK(cudaSetDevice(pb->ctx->device));
+  return pb->solve(m, x, l, y, opt, log);
+}
+
+int sipb_op_rows(int ndim, const int64_t* n, int op_kind, int64_t* rows) {
+  SIPB_REQUIRE(n && rows, SIPB_E_INVALID, "null argument");
+  const int64_t r = op_rows_host(ndim, n, op_kind);
+  SIPB_REQUIRE(r >= 0, SIPB_E_UNSUPPORTED, "operator kind not available for this grid dimensionality");
+  *rows = r;
+  return SIPB_OK;
+}
+
+}  // extern "C"
+
+// ---- unit entry points (templated bodies) ------------------------------------------------------
+namespace sipb {
+
+template <typename T>
+static int upload_cds(sipb_ctx* c, int64_t N, int nd, const void* R, i64 ld, DevBuf<T>& d) {
+  SIPB_CUDA_CHECK(d.alloc((size_t)ld * nd));
+  SIPB_CUDA_CHECK(cudaMemsetAsync(d.p, 0, (size_t)ld * nd * sizeof(T), c->stream));
+  SIPB_CUDA_CHECK(cudaMemcpy2DAsync(d.p, ld * sizeof(T), R, N * sizeof(T), N * sizeof(T), nd, cudaMemcpyHostToDevice,
+                                    c->stream));
+  return SIPB_OK;
+}
+
+template <typename T>
+static int cds_spmv_impl(sipb_ctx* c, int64_t N, int nd, const void* R, const int64_t* offs, const void* x, void* y) {
+  const i64 ld = (N + 63) / 64 * 64;
+  DevBuf<T> dR, dx, dy;
+  int rc = upload_cds<T>(c, N, nd, R, ld, dR);
+  if (rc) return rc;
+  SIPB_CUDA_CHECK(dx.alloc((size_t)N));
+  SIPB_CUDA_CHECK(dy.alloc((size_t)N));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(dx.p, x, N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  SpmvArgs<T> a;
+  a.R = dR.p; a.ld = ld; a.nd = nd;
+  for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
+  a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
+  LAUNCH(c, KC_SPMV, (k_spmv<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), a, c->rs, (double*)nullptr,
+         (const int*)nullptr);
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(y, dy.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+// minimal stand-alone problem wrapper so that sipb_cds_cg can reuse Problem<T>::run_cg
+template <typename T>
+static int cds_cg_impl(sipb_ctx* c, int64_t N, int nd, const void* R, const int64_t* offs, const void* b, void* x,
+                       double tol, int max_iter, int* flag, double* relres, int* iters) {
+  int64_t nn[3] = {N, 1, 1};
+  double hh[3] = {1, 1, 1};
+  Problem<T> P(c, sizeof(T) == 4 ? SIPB_F32 : SIPB_F64, 2, nn, hh, false, true);
+  P.npts = N; P.N = N; P.ld = (N + 63) / 64 * 64;
+  int rc = upload_cds<T>(c, N, nd, R, P.ld, P.Q);
+  if (rc) return rc;
+  P.q_offs.assign(offs, offs + nd);
+  DevBuf<T> db;
+  SIPB_CUDA_CHECK(db.alloc((size_t)N));
+  SIPB_CUDA_CHECK(P.x.alloc((size_t)N));
+  SIPB_CUDA_CHECK(P.r.alloc((size_t)N));
+  SIPB_CUDA_CHECK(P.pvec.alloc((size_t)N));
+  SIPB_CUDA_CHECK(P.Ap.alloc((size_t)N));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(db.p, b, N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(P.x.p, x, N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  rc = P.run_cg(db.p, P.x.p, nullptr, 0, (double)(T)tol, max_iter, 4, iters, relres, flag);
+  if (rc) return rc;
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(x, P.x.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+template <typename T>
+static int project_impl(sipb_ctx* c, const sipb_set_desc* d, int64_t M, void* v, const void* m_vec) {
+  int64_t nn[3] = {M, 2, 1};
+  double hh[3] = {1, 1, 1};
+  Problem<T> P(c, sizeof(T) == 4 ? SIPB_F32 : SIPB_F64, 2, nn, hh, false, true);
+  SetT<T> S;
+  S.desc = *d;
+  S.M = M;
+  SIPB_CUDA_CHECK(S.s.alloc((size_t)M));
+  SIPB_CUDA_CHECK(S.pp_f.alloc(1));
+  SIPB_CUDA_CHECK(S.warm.alloc(2));
+  SIPB_CUDA_CHECK(P.tmp.alloc((size_t)M));
+  SIPB_CUDA_CHECK(cudaMemsetAsync(S.warm.p, 0, 2 * sizeof(double), c->stream));
+  SIPB_CUDA_CHECK(cudaMemsetAsync(S.pp_f.p, 0, sizeof(ProjParams<T>), c->stream));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(S.s.p, v, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  if (d->set_kind == SIPB_SET_BOUNDS_VECTOR) {
+    SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
+    SIPB_CUDA_CHECK(S.lo_vec.alloc((size_t)M));
+    SIPB_CUDA_CHECK(S.hi_vec.alloc((size_t)M));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.lo_vec.p, d->min_vec, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.hi_vec.p, d->max_vec, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (d->set_kind == SIPB_SET_DISTANCE) {
+    SIPB_REQUIRE(m_vec, SIPB_E_INVALID, "distance prox needs m");
+    SIPB_CUDA_CHECK(P.m.alloc((size_t)M));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(P.m.p, m_vec, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  }
+  if (d->set_kind == SIPB_SET_L1) SIPB_REQUIRE(d->max > 0.0, SIPB_E_INVALID, "Radius of L1 ball is negative");
+  ProjDev<T> PD = P.proj_static(S, (T)d->max);
+  const ProjParams<T>* dyn = nullptr;
+  if (!proj_is_elementwise(d->set_kind)) {
+    LAUNCH(c, KC_VEC_STATS, k_vec_stats<T>, c->grid_for(M), M, S.s.p, c->rs, c->d_scal + 10);
+    int rc = P.projector_params(S, S.s.p, 10, S.pp_f.p, S.warm.p, true);
+    if (rc) return rc;
+    dyn = S.pp_f.p;
+  }
+  LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, S.s.p, (const T*)nullptr, PD, dyn, 1, c->rs, c->d_scal);
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(v, S.s.p, M * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+template <typename T>
+static int op_apply_impl(sipb_ctx* c, int ndim, const int64_t* n, const double* h, int op_kind, int block_mode,
+                         int adjoint, const void* in, void* out) {
+  OpDev op;
+  int rc = make_op<T>(ndim, n, h, op_kind, block_mode, &op);
+  if (rc) return rc;
+  const i64 nin = adjoint ? op.rows : op.cols, nout = adjoint ? op.cols : op.rows;
+  DevBuf<T> di, dout;
+  SIPB_CUDA_CHECK(di.alloc((size_t)nin));
+  SIPB_CUDA_CHECK(dout.alloc((size_t)nout));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(di.p, in, nin * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  if (adjoint) LAUNCH(c, KC_OP_APPLY, k_op_adjoint<T>, c->grid_for(nout), op, (const T*)di.p, dout.p);
+  else LAUNCH(c, KC_OP_APPLY, k_op_forward<T>, c->grid_for(nout), op, (const T*)di.p, dout.p);
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(out, dout.p, nout * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+template <typename T>
+static int cds_scaled_add_impl(sipb_ctx* c, int64_t N, int nd_a, void* A, const int64_t* a_off, int nd_b, const void* B,
+                               const int64_t* b_off, double alpha) {
+  const i64 ld = (N + 63) / 64 * 64;
+  DevBuf<T> dA, dB;
+  int rc = upload_cds<T>(c, N, nd_a, A, ld, dA);
+  if (rc) return rc;
+  rc = upload_cds<T>(c, N, nd_b, B, ld, dB);
+  if (rc) return rc;
+  for (int k = 0; k < nd_b; ++k) {
+    int col = -1;
+    for (int j = 0; j < nd_a; ++j) if (a_off[j] == b_off[k]) { col = j; break; }
+    SIPB_REQUIRE(col >= 0, SIPB_E_MISSING_DIAG,
+                 "attempted to update a diagonal in A in CDS storage that does not exist. A and B need to have the "
+                 "same nonzero diagonals");
+    LAUNCH(c, KC_Q_UPDATE, k_cds_axpy<T>, c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), N, dA.p + (size_t)col * ld,
+           (const T*)(dB.p + (size_t)k * ld), (T)alpha);
+  }
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpy2DAsync(A, N * sizeof(T), dA.p, ld * sizeof(T), N * sizeof(T), nd_a, cudaMemcpyDeviceToHost,
+                                    c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+template <typename T>
+static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, int reps, int flush_l2, double* avg_ms,
+                           int64_t* alg_bytes) {
+  const i64 N = n[0] * n[1] * (ndim == 3 ? n[2] : 1);
+  const i64 ld = (N + 63) / 64 * 64;
+  std::vector<int64_t> offs;
+  // Q_offsets of bounds/identity + TV + distance in the reference's order: [0, -n1n2, -n1, -1, 1, n1, n1n2]
+  offs.push_back(0);
+  if (ndim == 3) offs.push_back(-n[0] * n[1]);
+  offs.push_back(-n[0]); offs.push_back(-1); offs.push_back(1); offs.push_back(n[0]);
+  if (ndim == 3) offs.push_back(n[0] * n[1]);
+  const int nd = (int)offs.size();
+  DevBuf<T> dR, dx, dy, flush;
+  SIPB_CUDA_CHECK(dR.alloc((size_t)ld * nd));
+  SIPB_CUDA_CHECK(dx.alloc((size_t)N));
+  SIPB_CUDA_CHECK(dy.alloc((size_t)N));
+  const size_t flush_elems = (size_t)(256u << 20) / sizeof(T);
+  if (flush_l2) SIPB_CUDA_CHECK(flush.alloc(flush_elems));
+  LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), (i64)ld * nd, dR.p, (T)0.25);
+  LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), N, dx.p, (T)1.5);
+  SpmvArgs<T> a;
+  a.R = dR.p; a.ld = ld; a.nd = nd;
+  for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
+  a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
+  const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
+  cudaEvent_t e0, e1;
+  SIPB_CUDA_CHECK(cudaEventCreate(&e0));
+  SIPB_CUDA_CHECK(cudaEventCreate(&e1));
+  double total = 0.0;
+  for (int it = 0; it < warmup + reps; ++it) {
+    if (flush_l2) LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), (i64)flush_elems, flush.p, (T)it);
+    SIPB_CUDA_CHECK(cudaEventRecord(e0, c->stream));
+    LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, a, c->rs, c->d_scal, (const int*)nullptr);
+    SIPB_CUDA_CHECK(cudaEventRecord(e1, c->stream));
+    SIPB_CUDA_CHECK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (it >= warmup) total += ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  *avg_ms = total / std::max(1, reps);
+  *alg_bytes = (int64_t)(nd + 2) * N * (int64_t)sizeof(T);
+  return SIPB_OK;
+}
+
+}  // namespace sipb
+
+extern "C" {
+
+#define DISPATCH(dtype, fn, ...)                                                  \
+  do {                                                                            \
+    if ((dtype) == SIPB_F32) return fn<float>(__VA_ARGS__);                       \
+    if ((dtype) == SIPB_F64) return fn<double>(__VA_ARGS__);                      \
+    set_error("dtype must be SIPB_F32 or SIPB_F64");                              \
+    return SIPB_E_INVALID;                                                        \
+  } while (0)
+
+int sipb_cds_spmv(sipb_ctx* ctx, int dtype, int64_t N, int nd, const void* R, const int64_t* offsets, const void* x,
+                  void* y) {
+  SIPB_REQUIRE(ctx && R && offsets && x && y, SIPB_E_INVALID, "null argument");
+  SIPB_REQUIRE(nd >= 1 && nd <= kMaxDiag, SIPB_E_UNSUPPORTED, "number of diagonals outside [1,32]");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, cds_spmv_impl, ctx, N, nd, R, offsets, x, y);
+}
+int sipb_cds_cg(sipb_ctx* ctx, int dtype, int64_t N, int nd, const void* R, const int64_t* offsets, const void* b,
+                void* x, double tol, int max_iter, int* flag, double* relres, int* iters) {
+  SIPB_REQUIRE(ctx && R && offsets && b && x && flag && relres && iters, SIPB_E_INVALID, "null argument");
+  SIPB_REQUIRE(nd >= 1 && nd <= kMaxDiag, SIPB_E_UNSUPPORTED, "number of diagonals outside [1,32]");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, cds_cg_impl, ctx, N, nd, R, offsets, b, x, tol, max_iter, flag, relres, iters);
+}
+int sipb_project(sipb_ctx* ctx, int dtype, const sipb_set_desc* desc, int64_t M, void* v, const void* m_vec) {
+  SIPB_REQUIRE(ctx && desc && v, SIPB_E_INVALID, "null argument");
+  SIPB_REQUIRE(desc->set_kind >= SIPB_SET_BOUNDS_SCALAR && desc->set_kind <= SIPB_SET_DISTANCE, SIPB_E_UNSUPPORTED,
+               "set type is outside the device hot path");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, project_impl, ctx, desc, M, v, m_vec);
+}
+int sipb_op_apply(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const double* h, int op_kind, int block_mode,
+                  int adjoint, const void* in, void* out) {
+  SIPB_REQUIRE(ctx && n && h && in && out, SIPB_E_INVALID, "null argument");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, op_apply_impl, ctx, ndim, n, h, op_kind, block_mode, adjoint, in, out);
+}
+int sipb_cds_scaled_add(sipb_ctx* ctx, int dtype, int64_t N, int nd_a, void* A, const int64_t* a_offsets, int nd_b,
+                        const void* B, const int64_t* b_offsets, double alpha) {
+  SIPB_REQUIRE(ctx && A && a_offsets && B && b_offsets, SIPB_E_INVALID, "null argument");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, cds_scaled_add_impl, ctx, N, nd_a, A, a_offsets, nd_b, B, b_offsets, alpha);
+}
+int sipb_bench_spmv(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, int warmup, int reps, int flush_l2,
+                    double* avg_ms, int64_t* algorithmic_bytes) {
+  SIPB_REQUIRE(ctx && n && avg_ms && algorithmic_bytes, SIPB_E_INVALID, "null argument");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, bench_spmv_impl, ctx, ndim, n, warmup, reps, flush_l2, avg_ms, algorithmic_bytes);
+}
+
+}  // extern "C"

@@ -1,0 +1,98 @@
+"""PARSDMM_precompute_distribute (+ Minkowski) — host side.
+
+Mirrors PARSDMM_precompute_distribute.jl:6-77 and PARSDMM_precompute_distribute_Minkowski.jl:3-157:
+appends the distance term, forms every A_i'A_i directly in compressed-diagonal storage and allocates
+l, y.  "Distribute" here means: the returned AtA list is what `PARSDMM` uploads once to the GPU and
+keeps resident (the device problem handle is cached on the list object).
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from . import _lib
+from .operators import TDOperator
+
+
+class CDSList(list):
+    """Vector{Array{TF,2}} of CDS matrices; carries the cached device problem built from it."""
+    _device = None
+
+
+def _require_device_operators(TD_OP):
+    for A in TD_OP:
+        if not isinstance(A, TDOperator):
+            raise NotImplementedError("only the banded operators built by get_TD_operator are on the device path; "
+                                      "got %r" % type(A))
+
+
+def PARSDMM_precompute_distribute(TD_OP, set_Prop, comp_grid, options):
+    """-> (TD_OP, AtA, l, y).  MUTATES TD_OP and set_Prop like the reference (push of the distance term,
+    :17-26; AtA_offsets filled by mat2CDS, :52-59)."""
+    if getattr(options, "parallel", False):
+        raise NotImplementedError("options.parallel=true (one Julia worker per set) is replaced by slab domain "
+                                  "decomposition on the device path and is rejected")
+    _require_device_operators(TD_OP)
+    TF = TD_OP[0].TF
+    if not options.feasibility_only:
+        TD_OP.append(TDOperator("identity", comp_grid.n, comp_grid.d, TF))
+        set_Prop.TD_n.append(tuple(comp_grid.n))
+        set_Prop.AtA_offsets.append(np.array([0], dtype=np.int64))
+        set_Prop.banded.append(True)
+        set_Prop.AtA_diag.append(True)
+        set_Prop.ncvx.append(False)
+        set_Prop.dense.append(False)
+        set_Prop.tag.append(("distance squared", "identity", "matrix", ""))
+    p = len(TD_OP)
+    AtA = CDSList()
+    for i in range(p):
+        R, offs = TD_OP[i].ata_cds()          # == mat2CDS(TD_OP[i]'*TD_OP[i]) (identity when AtA_diag)
+        AtA.append(R)
+        set_Prop.AtA_offsets[i] = offs
+    set_Prop.AtA_offsets = set_Prop.AtA_offsets[:p]
+    y = [np.zeros(TD_OP[i].rows, dtype=TF) for i in range(p)]
+    l = [np.zeros(TD_OP[i].rows, dtype=TF) for i in range(p)]
+    return TD_OP, AtA, l, y
+
+
+def PARSDMM_precompute_distribute_Minkowski(TD_OP_c1, TD_OP_c2, TD_OP_sum, set_Prop_c1, set_Prop_c2, set_Prop_sum,
+                                            comp_grid, options):
+    """-> (TD_OP, set_Prop, AtA, l, y) for a generalized Minkowski set (unknown [x1; x2]).
+    Operators become [A 0], [0 A], [A A]; the distance term is [I I] (:78-101)."""
+    if getattr(options, "parallel", False):
+        raise NotImplementedError("options.parallel=true is rejected on the device path")
+    for lst in (TD_OP_c1, TD_OP_c2, TD_OP_sum):
+        _require_device_operators(lst)
+    first = (TD_OP_c1 + TD_OP_c2 + TD_OP_sum)[0]
+    TF = first.TF
+    for i in range(len(TD_OP_c1)):
+        TD_OP_c1[i] = TD_OP_c1[i].with_block(_lib.BLOCK_LEFT)
+    for i in range(len(TD_OP_c2)):
+        TD_OP_c2[i] = TD_OP_c2[i].with_block(_lib.BLOCK_RIGHT)
+    for i in range(len(TD_OP_sum)):
+        TD_OP_sum[i] = TD_OP_sum[i].with_block(_lib.BLOCK_BOTH)
+    if not options.feasibility_only:
+        TD_OP_sum.append(TDOperator("identity", comp_grid.n, comp_grid.d, TF, _lib.BLOCK_BOTH))
+        set_Prop_sum.TD_n.append(tuple(comp_grid.n))
+        set_Prop_sum.AtA_offsets.append(np.array([0], dtype=np.int64))
+        set_Prop_sum.banded.append(True)
+        set_Prop_sum.AtA_diag.append(False)
+        set_Prop_sum.dense.append(False)
+        set_Prop_sum.ncvx.append(False)
+        set_Prop_sum.tag.append(("distance squared", "identity", "matrix", ""))
+    set_Prop = copy.deepcopy(set_Prop_c1)
+    for other in (set_Prop_c2, set_Prop_sum):
+        for name in ("AtA_diag", "AtA_offsets", "TD_n", "banded", "dense", "ncvx", "tag"):
+            getattr(set_Prop, name).extend(copy.deepcopy(getattr(other, name)))
+    TD_OP = list(TD_OP_c1) + list(TD_OP_c2) + list(TD_OP_sum)
+    s = len(TD_OP)
+    AtA = CDSList()
+    for i in range(s):
+        R, offs = TD_OP[i].ata_cds()
+        AtA.append(R)
+        set_Prop.AtA_offsets[i] = offs
+    set_Prop.AtA_offsets = set_Prop.AtA_offsets[:s]
+    y = [np.zeros(TD_OP[i].rows, dtype=TF) for i in range(s)]
+    l = [np.zeros(TD_OP[i].rows, dtype=TF) for i in range(s)]
+    return TD_OP, set_Prop, AtA, l, y

@@ -1,0 +1,196 @@
+"""PARSDMM(m,AtA,TD_OP,set_Prop,P_sub,comp_grid,options[,x,l,y]) — host wrapper over the C ABI.
+
+Drop-in for PARSDMM.jl:25-258: same arguments, same return tuple `(x, log_PARSDMM, l, y)`, same log
+fields (trimmed exactly like output_check_PARSDMM, PARSDMM.jl:261-278) and the seven timing sections.
+The whole iteration runs on the GPU inside `sipb_solve`; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import numpy as np
+
+from . import _lib
+from .constraints import Projector
+from .operators import TDOperator
+from .types import convert_options, log_type_PARSDMM
+
+
+class _DeviceProblem:
+    def __init__(self, handle, key, p, pp, N, rows, q_offsets):
+        self.handle, self.key, self.p, self.pp, self.N, self.rows, self.q_offsets = handle, key, p, pp, N, rows, q_offsets
+        self._fin = weakref.finalize(self, _destroy, handle)
+
+
+def _destroy(handle):
+    try:
+        _lib.load().sipb_problem_destroy(handle)
+    except Exception:
+        pass
+
+
+def _problem_key(TF, TD_OP, P_sub, set_Prop, options):
+    items = [np.dtype(TF).str, bool(options.feasibility_only), bool(options.Minkowski)]
+    for A in TD_OP:
+        items.append((A.kind, A.n, tuple(float(v) for v in A.h), A.block_mode))
+    for P in P_sub:
+        items.append((P.set_kind, float(P.min) if np.ndim(P.min) == 0 else None,
+                      float(P.max) if np.ndim(P.max) == 0 else None, P.k,
+                      None if P.min_vec is None else P.min_vec.ctypes.data))
+    items.append(tuple(bool(v) for v in set_Prop.ncvx))
+    return tuple(items)
+
+
+def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) -> _DeviceProblem:
+    """Upload operators descriptors + AtA (CDS) once; replaces the data movement of
+    PARSDMM_precompute_distribute.jl and the allocation part of PARSDMM_initialize.jl."""
+    lib = _lib.load()
+    p = len(TD_OP)
+    pp = p if options.feasibility_only else p - 1
+    if len(P_sub) != pp:
+        raise ValueError("P_sub must hold one projector per constraint set (%d), got %d" % (pp, len(P_sub)))
+    if len(AtA) != p:
+        raise ValueError("AtA must hold one CDS matrix per operator")
+    for A in TD_OP:
+        if not isinstance(A, TDOperator):
+            raise NotImplementedError("operator %r is not a banded TDOperator; rejected on the device path" % (A,))
+    for P in P_sub:
+        if not isinstance(P, Projector):
+            raise NotImplementedError("P_sub entries must be the Projector functors returned by setup_constraints")
+    op0 = TD_OP[0]
+    n = (C.c_int64 * 3)(*(list(op0.n) + [1] * (3 - op0.ndim)))
+    h = (C.c_double * 3)(*([float(v) for v in op0.h] + [1.0] * (3 - op0.ndim)))
+    handle = C.c_void_p()
+    _lib.check(lib.sipb_problem_create(_lib.ctx(), _lib.dtype_code(TF), op0.ndim, n, h, int(bool(options.Minkowski)),
+                                       int(bool(options.feasibility_only)), C.byref(handle)))
+    try:
+        for i in range(p):
+            if i < pp:
+                d = P_sub[i].descriptor(TD_OP[i].op_kind, TD_OP[i].block_mode, set_Prop.ncvx[i])
+            else:
+                d = _lib.SetDesc()
+                d.set_kind, d.op_kind, d.block_mode, d.ncvx = _lib.SET_DISTANCE, TD_OP[i].op_kind, TD_OP[i].block_mode, 0
+            _lib.check(lib.sipb_problem_add_set(handle, C.byref(d)))
+            R = np.asfortranarray(AtA[i], dtype=TF)
+            offs = np.ascontiguousarray(set_Prop.AtA_offsets[i], dtype=np.int64)
+            if R.shape[1] != offs.size:
+                raise ValueError("AtA[%d] has %d diagonals but %d offsets" % (i, R.shape[1], offs.size))
+            _lib.check(lib.sipb_problem_set_ata(handle, i, R.ctypes.data, R.shape[0],
+                                                offs.ctypes.data_as(C.POINTER(C.c_int64)), offs.size))
+        _lib.check(lib.sipb_problem_finalize(handle))
+        nd = C.c_int(0)
+        _lib.check(lib.sipb_problem_num_q_offsets(handle, C.byref(nd)))
+        qo = np.zeros(nd.value, dtype=np.int64)
+        _lib.check(lib.sipb_problem_q_offsets(handle, qo.ctypes.data_as(C.POINTER(C.c_int64))))
+    except Exception:
+        lib.sipb_problem_destroy(handle)
+        raise
+    N = op0.npts * (2 if options.Minkowski else 1)
+    return _DeviceProblem(handle, _problem_key(TF, TD_OP, P_sub, set_Prop, options), p, pp, N,
+                          [A.rows for A in TD_OP], qo)
+
+
+def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
+            profile_kernels=False, fixed_iterations=0, return_ly=True):
+    """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
+    Returns (x, log_PARSDMM, l, y)."""
+    if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
+        raise TypeError("m must be a Float32/Float64 vector")
+    TF = m.dtype.type
+    if np.iscomplexobj(m) or (x is not None and np.iscomplexobj(x)):
+        raise ValueError("input for PARSDMM is not real")                                  # PARSDMM.jl:50-52
+    if getattr(options, "parallel", False):
+        raise NotImplementedError("options.parallel=true is rejected on the device path (use slab decomposition)")
+    convert_options(options, TF)                                                           # PARSDMM.jl:43
+    key = _problem_key(TF, TD_OP, P_sub, set_Prop, options)
+    dev = getattr(AtA, "_device", None)
+    if dev is None or dev.key != key:
+        dev = build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options)
+        try:
+            AtA._device = dev
+        except AttributeError:
+            pass
+    p, pp, N = dev.p, dev.pp, dev.N
+    m = np.ascontiguousarray(m)
+    if options.Minkowski:
+        if m.size * 2 != N:
+            raise ValueError("Minkowski problems need length(m) == N/2")
+    elif m.size != N:
+        raise ValueError("m has %d entries, the operators have %d columns" % (m.size, N))
+    zero_guess = bool(options.zero_ini_guess)
+    if x is None:
+        x_out = np.zeros(N, dtype=TF)
+    else:
+        x_out = np.ascontiguousarray(x, dtype=TF)
+        if x_out.size != N:
+            if options.Minkowski and x_out.size * 2 == N:
+                x_out = np.concatenate([x_out, np.zeros(x_out.size, dtype=TF)])            # PARSDMM.jl:85-89
+            else:
+                raise ValueError("x has the wrong length")
+    have_ly = l is not None and len(l) > 0 and y is not None and len(y) > 0
+    if not zero_guess and not have_ly:
+        # PARSDMM_initialize.jl:120-127 allocates zeros when l / y are empty
+        l = [np.zeros(r, dtype=TF) for r in dev.rows]
+        y = [np.zeros(r, dtype=TF) for r in dev.rows]
+        have_ly = True
+    if return_ly and not have_ly:
+        l = [np.zeros(r, dtype=TF) for r in dev.rows]
+        y = [np.zeros(r, dtype=TF) for r in dev.rows]
+        have_ly = True
+    lp = yp = None
+    if have_ly:
+        l = [np.ascontiguousarray(v, dtype=TF) for v in l]
+        y = [np.ascontiguousarray(v, dtype=TF) for v in y]
+        for i in range(p):
+            if l[i].size != dev.rows[i] or y[i].size != dev.rows[i]:
+                raise ValueError("l[%d] / y[%d] have the wrong length" % (i, i))
+        lp = (C.c_void_p * p)(*[v.ctypes.data for v in l])
+        yp = (C.c_void_p * p)(*[v.ctypes.data for v in y])
+
+    maxit = int(options.maxit)
+    rho_ini = np.ascontiguousarray([float(v) for v in options.rho_ini], dtype=np.float64)
+    o = _lib.Options()
+    o.maxit, o.rho_update_frequency = maxit, int(options.rho_update_frequency)
+    o.adjust_rho, o.adjust_gamma = int(bool(options.adjust_rho)), int(bool(options.adjust_gamma))
+    o.adjust_feasibility_rho, o.zero_ini_guess = int(bool(options.adjust_feasibility_rho)), int(zero_guess)
+    o.n_rho_ini, o.profile_kernels = rho_ini.size, int(bool(profile_kernels))
+    o.evol_rel_tol, o.feas_tol, o.obj_tol = float(options.evol_rel_tol), float(options.feas_tol), float(options.obj_tol)
+    o.gamma_ini = float(options.gamma_ini)
+    o.rho_ini = rho_ini.ctypes.data_as(C.POINTER(C.c_double))
+    o.fixed_iterations, o.return_ly = int(fixed_iterations), int(bool(return_ly and have_ly))
+
+    arr = {
+        "set_feasibility": np.zeros((maxit + 2, max(pp, 1))), "r_dual": np.zeros((maxit, p)),
+        "r_pri": np.zeros((maxit, p)), "r_dual_total": np.zeros(maxit), "r_pri_total": np.zeros(maxit),
+        "obj": np.zeros(maxit), "evol_x": np.zeros(maxit), "rho": np.zeros((maxit, p)), "gamma": np.zeros((maxit, p)),
+        "cg_relres": np.zeros(maxit),
+    }
+    cg_it = np.zeros(maxit, dtype=np.int32)
+    lg = _lib.Log()
+    for name, a in arr.items():
+        setattr(lg, name, a.ctypes.data_as(C.POINTER(C.c_double)))
+    lg.cg_it = cg_it.ctypes.data_as(C.POINTER(C.c_int32))
+
+    lib = _lib.load()
+    _lib.check(lib.sipb_solve(dev.handle, m.ctypes.data, x_out.ctypes.data, lp, yp, C.byref(o), C.byref(lg)))
+
+    it = max(int(lg.iters), 1)       # feasible input: logs trimmed to row 1 (PARSDMM.jl:70-80)
+    rows_f = int(lg.feas_rows)
+    timing = {name: float(lg.phase_seconds[i]) for i, name in enumerate(_lib.PHASE_NAMES)}
+    timing["solve_seconds"] = float(lg.solve_seconds)
+    timing["device_seconds"] = float(lg.device_seconds)
+    timing["total_launches"] = int(lg.total_launches)
+    timing["h2d_bytes"], timing["d2h_bytes"] = int(lg.h2d_bytes), int(lg.d2h_bytes)
+    timing["kernels"] = {lib.sipb_kernel_class_name(i).decode(): (int(lg.kernel_launches[i]), float(lg.kernel_ms[i]))
+                         for i in range(_lib.N_KERNEL_CLASSES) if lg.kernel_launches[i]}
+    timing["stopped_feasible"] = bool(lg.stopped_feasible)
+    log = log_type_PARSDMM(
+        set_feasibility=arr["set_feasibility"][:rows_f, :pp], r_dual=arr["r_dual"][:it], r_pri=arr["r_pri"][:it],
+        r_dual_total=arr["r_dual_total"][:it], r_pri_total=arr["r_pri_total"][:it], obj=arr["obj"][:it],
+        evol_x=arr["evol_x"][:it], rho=arr["rho"][:it], gamma=arr["gamma"][:it], cg_it=cg_it[:it].astype(np.int64),
+        cg_relres=arr["cg_relres"][:it], timing=timing)
+    if x is not None and isinstance(x, np.ndarray) and x.size == x_out.size and x is not x_out:
+        x[:] = x_out                                                                       # in-place like the reference
+        x_out = x
+    return x_out, log, l, y

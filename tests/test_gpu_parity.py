@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): final x relative L2 error <= 1e-5 in Float64 and <= 1e-3 in
+Float32, with matching iteration counts; bit-exact for index work (offsets, support sets)."""
+import copy
+
+import numpy as np
+import pytest
+
+import problems as pr
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float32: 1e-3, np.float64: 1e-5}
+
+
+def relerr(a, b):
+    return float(np.linalg.norm(a.astype(np.float64) - b.astype(np.float64)) / max(np.linalg.norm(b.astype(np.float64)), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return pr.OracleAPI()
+
+
+# ---------------------------------------------------------------------------------------------
+# kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+@pytest.mark.parametrize("n,kind", [((9, 6), "TV"), ((9, 6), "D_x"), ((9, 6), "D_z"), ((9, 6), "D_xz"),
+                                    ((9, 6), "identity"), ((4, 6, 5), "TV"), ((4, 6, 5), "D_x"),
+                                    ((4, 6, 5), "D_y"), ((4, 6, 5), "D_z"), ((33, 17, 9), "TV")])
+def test_operator_forward_adjoint_bit_exact(sip, orc, TF, n, kind):
+    d = (0.99, 1.123, 1.7)[: len(n)]
+    cg = orc.compgrid(d, n)
+    A = orc.get_TD_operator(cg, kind, TF)[0]
+    op = sip.get_TD_operator(sip.compgrid(d, n), kind, TF)[0]
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(A.shape[1]).astype(TF)
+    v = rng.standard_normal(A.shape[0]).astype(TF)
+    assert np.array_equal(op @ x, orc.ops.spmv(A, x))
+    assert np.array_equal(op.T @ v, orc.ops.spmv_t(A, v))
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_operator_minkowski_blocks(sip, orc, TF):
+    import scipy.sparse as sp
+    n, d = (7, 5), (2.0, 3.0)
+    A = orc.get_TD_operator(orc.compgrid(d, n), "TV", TF)[0]
+    op = sip.get_TD_operator(sip.compgrid(d, n), "TV", TF)[0]
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(2 * A.shape[1]).astype(TF)
+    v = rng.standard_normal(A.shape[0]).astype(TF)
+    Z = sp.csc_matrix(A.shape, dtype=TF)
+    for mode, blocks in ((1, [A, Z]), (2, [Z, A]), (3, [A, A])):
+        B = sp.hstack(blocks, format="csc", dtype=TF)
+        B.sort_indices()
+        o = op.with_block(mode)
+        assert np.array_equal(o @ x, orc.ops.spmv(B, x))
+        assert np.array_equal(o.T @ v, orc.ops.spmv_t(B, v))
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [(30, 20), (13, 11, 7), (64, 50, 3)])
+def test_cds_spmv_bit_exact(sip, orc, TF, n):
+    """test_CDS_Mvp.jl:13-22 on TV'TV, plus bit-exactness w.r.t. the per-diagonal accumulation order."""
+    d = (25.0,) * len(n)
+    A = orc.get_TD_operator(orc.compgrid(d, n), "TV", TF)[0]
+    R, off = orc.mat2CDS(orc.ops.AtA_sparse(A))
+    # reorder like Q_offsets (0 first) to exercise a non-sorted accumulation order
+    order = np.argsort(np.where(off == 0, -10**12, off), kind="stable")
+    R, off = np.asfortranarray(R[:, order]), off[order]
+    N = R.shape[0]
+    x = np.random.default_rng(3).standard_normal(N).astype(TF)
+    want = orc.ops.CDS_MVp(N, R.shape[1], R, off, x, np.zeros(N, dtype=TF))
+    got = sip.CDS_MVp(N, R.shape[1], R, off, x, np.zeros(N, dtype=TF))
+    assert np.array_equal(got, want)
+    native = np.asarray(orc.ops.AtA_sparse(A) @ x).ravel()
+    assert np.allclose(got, native, rtol=0, atol=10 * np.finfo(TF).eps * np.abs(native).max())
+
+
+def test_cds_spmv_random_offsets(sip, orc):
+    """random banded matrix (test_CDS_Mvp.jl:13-22 second half), Float64."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(4)
+    N = 1000
+    A = sp.random(N, N, density=0.01, random_state=5, format="csc", dtype=np.float64)
+    R, off = orc.mat2CDS(A)
+    if R.shape[1] > 32:       # device limit on diagonals: keep the 32 first
+        R, off = np.asfortranarray(R[:, :32]), off[:32]
+    x = rng.standard_normal(N)
+    want = orc.ops.CDS_MVp(N, R.shape[1], R, off, x, np.zeros(N))
+    got = sip.CDS_MVp(N, R.shape[1], R, off, x, np.zeros(N))
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_cds_scaled_add(sip, orc, TF):
+    """test_CDS_scaled_add.jl:24-39: CDS(A) + CDS(B) == CDS(A+B) exactly; missing diagonal raises."""
+    n, d = (30, 20), (25.0, 25.0)
+    TV = orc.get_TD_operator(orc.compgrid(d, n), "TV", TF)[0]
+    Dz = orc.get_TD_operator(orc.compgrid(d, n), "D_z", TF)[0]
+    A, B = orc.ops.AtA_sparse(TV), orc.ops.AtA_sparse(Dz)
+    RA, oA = orc.mat2CDS(A)
+    RB, oB = orc.mat2CDS(B)
+    RC, oC = orc.mat2CDS((A + B).astype(TF))
+    got = sip.CDS_scaled_add(RA.copy(order="F"), RB, oA, oB, 1.0)
+    assert np.array_equal(got, RC) and np.array_equal(oA, oC)
+    with pytest.raises(Exception):
+        sip.CDS_scaled_add(RB.copy(order="F"), RA, oB, oA, 1.0)
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_cg_matches_oracle(sip, orc, TF):
+    """cg.jl semantics: residual <= tol, exact start => iter == 1 and x untouched (test_cg.jl:25-29),
+    zero rhs => flag -9, iterates close to the oracle's."""
+    n, d = (24, 20), (1.0, 1.0)
+    TV = orc.get_TD_operator(orc.compgrid(d, n), "TV", TF)[0]
+    R, off = orc.mat2CDS(orc.ops.AtA_sparse(TV))
+    R[:, list(off).index(0)] += TF(1.0)        # Q = TV'TV + I  (SPD)
+    N = R.shape[0]
+    rng = np.random.default_rng(6)
+    xt = rng.standard_normal(N).astype(TF)
+    b = orc.ops.Ax_CDS(xt, R, off)
+    tol = 1e-5 if TF == np.float32 else 1e-10
+    x, flag, relres, it = sip.cg(R, off, b, tol=tol, maxIter=1000)
+    assert flag == 0 and np.linalg.norm(orc.ops.Ax_CDS(x, R, off) - b) / np.linalg.norm(b) <= 2 * tol
+    xo, fo, ro, ito = orc.parsdmm.cg(lambda v: orc.ops.Ax_CDS(v, R, off), b.copy(), TF(tol), 1000, np.zeros(N, dtype=TF))
+    assert it == ito and relerr(x, xo) < TOL[TF]
+    assert abs(float(relres) - float(ro)) <= 1e-2 * float(ro) + 1e-30
+    x2, flag2, relres2, it2 = sip.cg(R, off, b, tol=tol, maxIter=1000, x=xt.copy())
+    assert it2 == 1 and flag2 == 0 and np.array_equal(x2, xt) and relres2 == 0
+    x3, flag3, relres3, it3 = sip.cg(R, off, np.zeros(N, dtype=TF), tol=tol, maxIter=10, x=xt.copy())
+    assert flag3 == -9 and it3 == 0 and not x3.any()
+
+
+# ---------------------------------------------------------------------------------------------
+# projectors
+# ---------------------------------------------------------------------------------------------
+def _P(sip, st, lo, hi, TF, n=(50, 2)):
+    cons = [sip.set_definitions(st, "identity", lo, hi, ("matrix", ""))]
+    return sip.setup_constraints(cons, sip.compgrid((1.0, 1.0), n), TF)[0][0]
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_projectors_match_oracle(sip, orc, TF):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(100).astype(TF)
+    # bounds (bit exact)
+    assert np.array_equal(_P(sip, "bounds", -0.11, 0.01, TF)(x.copy()), orc.proj.project_bounds(x.copy(), TF(-0.11), TF(0.01)))
+    lo = (rng.standard_normal(100) - 1).astype(TF)
+    hi = (rng.standard_normal(100) + 1).astype(TF)
+    assert np.array_equal(_P(sip, "bounds", lo, hi, TF)(x.copy()), orc.proj.project_bounds(x.copy(), lo, hi))
+    # l1: untouched inside the ball, ||x||_1 == tau outside (test_projectors.jl:22-35), close to Duchi
+    tau = TF(np.abs(x).sum() * 2)
+    assert np.array_equal(_P(sip, "l1", 0.0, tau, TF)(x.copy()), x)
+    tau = TF(np.abs(x).sum() * 0.234)
+    got = _P(sip, "l1", 0.0, tau, TF)(x.copy())
+    assert abs(np.abs(got.astype(np.float64)).sum() - float(tau)) <= 20 * np.finfo(TF).eps * float(tau)
+    assert relerr(got, orc.proj.project_l1_Duchi(x.copy(), tau)) < 20 * np.finfo(TF).eps
+    # l2 / annulus
+    # (the 2-norm is a reduction: summation order differs, so agreement is to a few ulps)
+    ulps = 8 * np.finfo(TF).eps
+    got = _P(sip, "l2", 0.0, 0.123, TF)(x.copy())
+    assert relerr(got, orc.proj.project_l2(x.copy(), TF(0.123))) < ulps
+    assert abs(np.linalg.norm(got.astype(np.float64)) - 0.123) < 10 * np.finfo(TF).eps
+    assert np.array_equal(_P(sip, "l2", 0.0, 1e3, TF)(x.copy()), x)
+    for lo_, hi_ in ((20.0, 30.0), (0.1, 0.2), (1.0, 100.0)):
+        assert relerr(_P(sip, "annulus", lo_, hi_, TF)(x.copy()), orc.proj.project_annulus(x.copy(), TF(lo_), TF(hi_))) < ulps
+    z = np.zeros(100, dtype=TF)
+    assert np.array_equal(_P(sip, "annulus", 2.0, 3.0, TF)(z.copy()), orc.proj.project_annulus(z.copy(), TF(2.0), TF(3.0)))
+    # cardinality: literals of test_projectors.jl:49-56 and support equality with stable ties
+    for lit, k, want in (([0, 0, 1, 2, 3], 2, [0, 0, 0, 2, 3]), ([0, 0, -1, 2, -3], 2, [0, 0, 0, 2, -3])):
+        got = _P(sip, "cardinality", 0, k, TF, n=(5, 2))(np.array(lit, dtype=TF))
+        assert np.array_equal(got, np.array(want, dtype=TF))
+    got = _P(sip, "cardinality", 0, 5, TF)(x.copy())
+    assert np.count_nonzero(got) == 5 and np.array_equal(got, orc.proj.project_cardinality(x.copy(), 5))
+    t = np.round(rng.standard_normal(4000) * 3).astype(TF)      # many exact ties
+    for k in (0, 1, 17, 500, 1999, 3999, 4000, 5000):
+        got = _P(sip, "cardinality", 0, k, TF, n=(2000, 2))(t.copy())
+        assert np.array_equal(got, orc.proj.project_cardinality(t.copy(), k)), k
+    # prox_l1
+    assert np.array_equal(_P(sip, "prox_l1", 0.0, 3.0, TF)(x.copy()), orc.proj.prox_l1(x.copy(), TF(3.0)))
+
+
+def test_rejected_sets(sip):
+    for st in ("rank", "nuclear", "subspace", "histogram"):
+        with pytest.raises(NotImplementedError):
+            _P(sip, st, 0.0, 3.0, np.float32)
+    with pytest.raises(NotImplementedError):
+        cons = [sip.set_definitions("bounds", "DFT", 0.0, 1.0, ("matrix", ""))]
+        sip.setup_constraints(cons, sip.compgrid((1.0, 1.0), (8, 8)), np.float32)
+    with pytest.raises(Exception):
+        _P(sip, "l1", 0.0, -1.0, np.float32)(np.ones(100, dtype=np.float32))
+
+
+# ---------------------------------------------------------------------------------------------
+# full PARSDMM
+# ---------------------------------------------------------------------------------------------
+def run_both(sip, orc, spec, tweak=None, **kw):
+    o_opt = orc.PARSDMM_options()
+    s_opt = sip.PARSDMM_options()
+    if tweak:
+        tweak(o_opt)
+        tweak(s_opt)
+    ob = pr.build(orc, copy.deepcopy(spec), o_opt)
+    sb = pr.build(sip, copy.deepcopy(spec), s_opt)
+    m = spec["m"]
+    xo, lo, ll, yy = orc.PARSDMM(m.copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"])
+    xs, ls, l2, y2 = sip.PARSDMM(m.copy(), sb["AtA"], sb["TD_OP"], sb["set_Prop"], sb["P_sub"], sb["cg"], sb["opt"], **kw)
+    return (xo, lo, ll, yy, ob), (xs, ls, l2, y2, sb)
+
+
+def check_parity(o, s, TF, iters_exact=True):
+    xo, lo, ll, yy, ob = o
+    xs, ls, l2, y2, sb = s
+    assert np.array_equal(ob["set_Prop"].AtA_offsets[1], sb["set_Prop"].AtA_offsets[1])
+    if iters_exact:
+        assert len(ls.obj) == len(lo.obj), (len(ls.obj), len(lo.obj))
+        assert np.array_equal(ls.cg_it, lo.cg_it), (ls.cg_it, lo.cg_it)
+        assert ls.set_feasibility.shape == lo.set_feasibility.shape
+        tol = TOL[TF]
+        assert np.allclose(ls.set_feasibility, lo.set_feasibility, rtol=50 * tol, atol=1e-12)
+        assert np.allclose(ls.rho, lo.rho, rtol=50 * tol)
+        assert np.allclose(ls.gamma, lo.gamma, rtol=50 * tol)
+        assert np.allclose(ls.obj, lo.obj, rtol=50 * tol)
+        assert np.allclose(ls.r_pri, lo.r_pri, rtol=1e-2, atol=1e-6 * np.abs(lo.r_pri).max())
+        for a, b, yb in zip(l2, ll, yy):
+            # multipliers of inactive sets are pure rounding noise: absolute floor relative to ||y||
+            floor = 1e4 * np.finfo(TF).eps * np.linalg.norm(yb.astype(np.float64))
+            assert np.linalg.norm(a.astype(np.float64) - b) <= 100 * tol * np.linalg.norm(b.astype(np.float64)) + floor
+        for a, b in zip(y2, yy):
+            assert relerr(a, b) < 100 * tol
+    assert relerr(xs, xo) < TOL[TF], relerr(xs, xo)
+
+
+@pytest.mark.parametrize("TF", [np.float64, np.float32])
+def test_parsdmm_config1_2d(sip, orc, TF):
+    o, s = run_both(sip, orc, pr.spec_config1((64, 64), TF))
+    check_parity(o, s, TF)
+    assert np.isnan(s[1].evol_x[0]) and s[1].cg_it[0] == 0       # quirk: iteration 1 has rhs == 0
+
+
+def test_parsdmm_config1_f64_accurate(sip, orc):
+    """test_PARSDMM.jl:97-111-style accurate settings: every set feasible to 1.5*feas_tol."""
+    def tw(o):
+        o.obj_tol, o.feas_tol, o.evol_rel_tol, o.maxit = 1e-9, 1e-9, 1e-12, 400
+    o, s = run_both(sip, orc, pr.spec_config1((32, 32), np.float64), tw)
+    check_parity(o, s, np.float64)
+
+
+@pytest.mark.parametrize("n", [(24, 24, 24), (40, 28, 20)])
+def test_parsdmm_config2_3d_f32(sip, orc, n):
+    def tw(o):
+        o.evol_rel_tol = 10 * np.finfo(np.float32).eps       # examples/test_scaling_3D.jl:25
+        o.maxit = 60
+    o, s = run_both(sip, orc, pr.spec_config2(n, np.float32), tw)
+    check_parity(o, s, np.float32)
+
+
+def test_parsdmm_config3_cardinality(sip, orc):
+    def tw(o):
+        o.maxit = 40
+    o, s = run_both(sip, orc, pr.spec_config3((20, 20, 20), np.float32), tw)
+    check_parity(o, s, np.float32)
+    # non-convex overrides (PARSDMM_initialize.jl:107-114): gamma fixed at 0.75
+    assert np.all(s[1].gamma == np.float32(0.75))
+    # bit-exact support of the cardinality-projected auxiliary vector
+    assert np.array_equal(s[3][2] != 0, o[3][2] != 0)
+
+
+def test_parsdmm_config4_bounds_only(sip, orc):
+    def tw(o):
+        o.rho_ini = [1.0, 1000.0, 1000.0, 1000.0, 1.0]        # examples/test_scaling_3D.jl:97
+        o.evol_rel_tol = 10 * np.finfo(np.float32).eps
+        o.maxit = 50
+    o, s = run_both(sip, orc, pr.spec_config4((20, 22, 24), np.float32), tw)
+    check_parity(o, s, np.float32)
+
+
+def test_parsdmm_feasible_input_returned(sip, orc):
+    """test_PARSDMM.jl:17-36: a feasible model comes back unchanged with one-row logs."""
+    TF = np.float64
+    m = pr.synthetic_model((20, 30), TF)
+    spec = dict(n=(20, 30), d=(1.0, 1.0), TF=TF, m=m, sets=[("bounds", "identity", float(m.min()), float(m.max()))],
+                mode="matrix")
+    o, s = run_both(sip, orc, spec)
+    assert np.array_equal(s[0], m) and np.array_equal(o[0], m)
+    assert len(s[1].obj) == 1 and s[1].set_feasibility.shape == (1, 1)
+
+
+def test_parsdmm_option_variants(sip, orc):
+    """test_PARSDMM.jl:113-189: option variants keep every set feasible and match the oracle."""
+    spec = pr.spec_config1((40, 36), np.float64)
+    for kw in (dict(adjust_gamma=False), dict(adjust_rho=False), dict(adjust_rho=False, adjust_gamma=False),
+               dict(adjust_feasibility_rho=False), dict(rho_update_frequency=1), dict(gamma_ini=1.5)):
+        def tw(o, kw=kw):
+            for k, v in kw.items():
+                setattr(o, k, v)
+            o.maxit = 80
+        o, s = run_both(sip, orc, spec, tw)
+        check_parity(o, s, np.float64)
+
+
+def test_parsdmm_warm_start(sip, orc):
+    """Warm start x,l,y (zero_ini_guess=false, PARSDMM_initialize.jl:304-313): restart == oracle restart."""
+    spec = pr.spec_config1((32, 32), np.float64)
+    def tw(o):
+        o.maxit = 8
+    o, s = run_both(sip, orc, spec, tw)
+    xo, lo, ll, yy, ob = o
+    xs, ls, l2, y2, sb = s
+    ob["opt"].zero_ini_guess = False
+    sb["opt"].zero_ini_guess = False
+    ob["opt"].maxit = sb["opt"].maxit = 40
+    m = spec["m"]
+    xo2, lo2, _, _ = orc.PARSDMM(m.copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"], xo.copy(),
+                                 [v.copy() for v in ll], [v.copy() for v in yy])
+    xs2, ls2, _, _ = sip.PARSDMM(m.copy(), sb["AtA"], sb["TD_OP"], sb["set_Prop"], sb["P_sub"], sb["cg"], sb["opt"], xs.copy(),
+                                 [v.copy() for v in l2], [v.copy() for v in y2])
+    assert len(ls2.obj) == len(lo2.obj) and relerr(xs2, xo2) < 1e-5
+
+
+def test_parallel_option_rejected(sip):
+    spec = pr.spec_config1((16, 16), np.float32)
+    opt = sip.PARSDMM_options()
+    opt.parallel = True
+    with pytest.raises(NotImplementedError):
+        pr.build(sip, spec, opt)

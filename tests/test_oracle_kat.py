@@ -1,0 +1,274 @@
+"""Pins the CPU oracle against every deterministic known-answer / property test the reference's own
+test-suite holds for the hot path.  Runs without a GPU."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import problems as pr
+
+orc = pr.OracleAPI()
+ops, proj, par, T = orc.ops, orc.proj, orc.parsdmm, orc.types
+
+
+# ---- test/test_TD_OPs.jl:5-40 ---------------------------------------------------------------------
+def test_TD_OPs_2d_cross_image():
+    n1, n2, h1, h2 = 9, 6, np.float64(0.99), np.float64(1.123)
+    D2D = ops.get_discrete_Grad(n1, n2, h1, h2, "TV")
+    D2x = ops.get_discrete_Grad(n1, n2, h1, h2, "D_x")
+    D2z = ops.get_discrete_Grad(n1, n2, h1, h2, "D_z")
+    x = np.zeros((n1, n2))
+    x[:, 2] = 1.0
+    x[3, :] = 1.0
+    v = x.ravel(order="F")
+    a1 = (D2x @ v).reshape((n1 - 1, n2), order="F")
+    a2 = (D2z @ v).reshape((n1, n2 - 1), order="F")
+    a3 = D2D @ v
+    a3a = a3[: (n2 - 1) * n1].reshape((n1, n2 - 1), order="F")
+    a3b = a3[(n2 - 1) * n1:].reshape((n1 - 1, n2), order="F")
+    assert np.array_equal(a1, np.diff(x, axis=0) / h1)
+    assert np.array_equal(a2, np.diff(x, axis=1) / h2)
+    assert np.count_nonzero(a1[:, 2]) == 0
+    for i in (0, 1, 3, 4, 5):
+        assert np.array_equal(a1[:, 0], a1[:, i])
+    assert np.count_nonzero(a2[3, :]) == 0
+    for i in (0, 1, 2, 4, 5, 6, 7, 8):
+        assert np.array_equal(a2[0, :], a2[i, :])
+    assert np.array_equal(a3a, a2) and np.array_equal(a3b, a1)      # TV block order: D_z then D_x
+
+
+# ---- test/test_TD_OPs.jl:43-81 --------------------------------------------------------------------
+def test_TD_OPs_3d_cross_image():
+    n1, n2, n3 = 4, 6, 5
+    h1, h2, h3 = np.float64(0.99), np.float64(1.123), np.float64(1.0)
+    D3x = ops.get_discrete_Grad(n1, n2, n3, h1, h2, h3, "D_x")
+    D3y = ops.get_discrete_Grad(n1, n2, n3, h1, h2, h3, "D_y")
+    D3z = ops.get_discrete_Grad(n1, n2, n3, h1, h2, h3, "D_z")
+    D3D = ops.get_discrete_Grad(n1, n2, n3, h1, h2, h3, "TV")
+    x = np.zeros((n1, n2, n3))
+    x[1, :, :] = 1.0
+    x[:, 3, :] = 1.0
+    x[:, :, 2] = 1.0
+    v = x.ravel(order="F")
+    a1 = (D3x @ v).reshape((n1 - 1, n2, n3), order="F")
+    a2 = (D3y @ v).reshape((n1, n2 - 1, n3), order="F")
+    a3 = (D3z @ v).reshape((n1, n2, n3 - 1), order="F")
+    assert np.array_equal(a1, np.diff(x, axis=0) / h1)
+    assert np.array_equal(a2, np.diff(x, axis=1) / h2)
+    assert np.array_equal(a3, np.diff(x, axis=2) / h3)
+    assert np.array_equal(D3D @ v, np.concatenate([D3z @ v, D3y @ v, D3x @ v]))   # vcat(D3z,D3y,D3x)
+
+
+# ---- test/test_CDS_Mvp.jl:13-22 -------------------------------------------------------------------
+def test_CDS_MVp_mat2CDS():
+    TF = np.float32
+    n1, n2 = 30, 20
+    N = n1 * n2
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(N).astype(TF)
+    TV = ops.get_TD_operator(T.compgrid((TF(25), TF(25)), (n1, n2)), "TV", TF)[0]
+    A = ops.AtA_sparse(TV)
+    R, off = ops.mat2CDS(A)
+    assert list(off) == [-n1, -1, 0, 1, n1]
+    got = ops.CDS_MVp(N, R.shape[1], R, off, x, np.zeros(N, dtype=TF))
+    assert np.allclose(got, A @ x, rtol=0, atol=10 * np.finfo(TF).eps * np.abs(A @ x).max())
+    A = sp.random(1000, 1000, density=0.1, random_state=1, format="csc")
+    x = rng.standard_normal(1000)
+    R, off = ops.mat2CDS(A)
+    got = ops.CDS_MVp(1000, R.shape[1], R, off, x, np.zeros(1000))
+    assert np.allclose(got, A @ x, rtol=1e-13, atol=1e-13)
+
+
+# ---- test/test_CDS_scaled_add.jl:24-67 ------------------------------------------------------------
+def test_CDS_scaled_add():
+    TF = np.float64
+    cg = T.compgrid((TF(25), TF(25)), (30, 20))
+    TV = ops.get_TD_operator(cg, "TV", TF)[0]
+    Dz = ops.get_TD_operator(cg, "D_z", TF)[0]
+    A, B = ops.AtA_sparse(TV), ops.AtA_sparse(Dz)
+    RA, oA = ops.mat2CDS(A)
+    RB, oB = ops.mat2CDS(B)
+    RC, oC = ops.mat2CDS(A + B)
+    ops.CDS_scaled_add(RA, RB, oA, oB, 1.0)
+    assert np.array_equal(RC, RA) and np.array_equal(oC, oA)
+    with pytest.raises(RuntimeError):
+        ops.CDS_scaled_add(RB, RA, oB, oA, 1.0)       # CDS_scaled_add!.jl:18-20
+
+
+# ---- test/test_Q_update.jl:41-59 (CDS branch) -----------------------------------------------------
+def test_Q_update_and_assembly_order():
+    TF = np.float64
+    spec = pr.spec_config1((12, 10), TF)
+    b = pr.build(orc, spec)
+    rho = np.array([1.0, 2.0, 3.0, 4.0])
+    Q, Qo = ops.assemble_Q(b["AtA"], b["set_Prop"].AtA_offsets, rho)
+    # unique() over the zero-padded table: offsets of AtA[1] (=[0]), then new ones of AtA[2] ascending ...
+    assert list(Qo) == [0, -12, -1, 1, 12]
+    rho2 = np.array([1.5, 2.0, 0.5, 4.0])
+    Q2, _ = ops.assemble_Q(b["AtA"], b["set_Prop"].AtA_offsets, rho2)
+    ops.Q_update(Q, b["AtA"], b["set_Prop"], rho2, [0, 2], rho, Qo)
+    assert np.allclose(Q, Q2, rtol=1e-14, atol=1e-14)
+    x = np.random.default_rng(2).standard_normal(Q.shape[0])
+    dense = sum(r * (A.T @ A) for r, A in zip(rho2, b["TD_OP"]))
+    assert np.allclose(ops.Ax_CDS(x, Q, Qo), dense @ x, rtol=1e-12, atol=1e-12)
+
+
+# ---- test/test_prox_l2s!.jl:4-19 ------------------------------------------------------------------
+def test_prox_l2s():
+    rng = np.random.default_rng(3)
+    m, x = rng.standard_normal(10), rng.standard_normal(10)
+    assert np.array_equal(proj.prox_l2s(x.copy(), 0.0, m), m)
+    assert np.allclose(proj.prox_l2s(x.copy(), 1e10, m), x, rtol=1e-9)
+    assert proj.prox_l2s(np.array([2.0]), 3.0, np.array([1.0]))[0] == 7 / 4
+
+
+# ---- test/test_projectors.jl:6-104 (hot-path projectors) -------------------------------------------
+def test_projectors():
+    rng = np.random.default_rng(123)
+    x = rng.standard_normal(100)
+    proj.project_bounds(x, -0.11, 0.01)
+    assert x.max() <= 0.01 and x.min() >= -0.11
+    x = 100.0 * rng.standard_normal(100)
+    lo, hi = rng.standard_normal(100) - 10, rng.standard_normal(100) + 10
+    proj.project_bounds(x, lo, hi)
+    assert np.all(x <= hi) and np.all(x >= lo)
+    x = rng.standard_normal(100)
+    y = x.copy()
+    assert np.array_equal(proj.project_l1_Duchi(x, np.abs(x).sum() * 2), y)
+    x = rng.standard_normal(100)
+    tau = np.abs(x).sum() * 0.234
+    proj.project_l1_Duchi(x, tau)
+    assert np.isclose(np.abs(x).sum(), tau, rtol=10 * np.finfo(np.float64).eps)
+    with pytest.raises(ValueError):
+        proj.project_l1_Duchi(x, -1.0)
+    x = rng.standard_normal(100)
+    assert np.count_nonzero(proj.project_cardinality(x, 5)) == 5
+    assert np.array_equal(proj.project_cardinality(np.array([0., 0, 1, 2, 3]), 2), [0, 0, 0, 2, 3])
+    assert np.array_equal(proj.project_cardinality(np.array([0., 0, -1, 2, -3]), 2), [0, 0, 0, 2, -3])
+    assert np.array_equal(proj.project_cardinality(np.array([1., -1, 1, -1]), 2), [1, -1, 0, 0])   # stable ties
+    x = rng.standard_normal(100)
+    assert np.isclose(np.linalg.norm(proj.project_l2(x, 0.123)), 0.123, rtol=10 * np.finfo(np.float64).eps)
+    x = rng.standard_normal(100)
+    y = x.copy()
+    assert np.array_equal(proj.project_l2(x, 1.234 * np.linalg.norm(x)), y)
+
+
+def test_julia_pairwise_cumsum_matches_exact_sum():
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 127, 128, 129, 1000, 40000):
+        u = np.sort(np.abs(rng.standard_normal(n)).astype(np.float32))[::-1].copy()
+        sv = proj.julia_cumsum(u)
+        ref = np.cumsum(u.astype(np.float64))
+        assert sv.dtype == np.float32 and np.allclose(sv, ref, rtol=2e-6)
+    u = np.arange(1, 300, dtype=np.float64)
+    assert np.array_equal(proj.julia_cumsum(u), np.cumsum(u))
+
+
+# ---- test/test_cg.jl:5-36 -------------------------------------------------------------------------
+def test_cg():
+    rng = np.random.default_rng(6)
+    A = rng.standard_normal((200, 100))
+    A = A.T @ A
+    xt = rng.standard_normal(100)
+    b = A @ xt
+    Af = lambda v: A @ v        # noqa: E731
+    x, flag, relres, it1 = par.cg(Af, b, 1e-5, 1000, np.zeros(100))
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1e-5
+    x, flag, relres, it = par.cg(Af, b, 1e-14, 1000, np.zeros(100))
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) <= 1.01e-14 * 10
+    x, flag, relres, it2 = par.cg(Af, b, 1e-5, 1000, xt + np.finfo(np.float64).eps)
+    assert it2 < it1
+    x, flag, relres, it2 = par.cg(Af, b, 1e-14, 1000, xt.copy())
+    assert it2 == 1 and np.array_equal(x, xt)                     # test_cg.jl:25-29
+    x, flag, relres, it0 = par.cg(Af, np.zeros(100), 1e-5, 10, xt.copy())
+    assert flag == -9 and it0 == 0 and not x.any()               # cg.jl:47
+
+
+# ---- test/test_update_y_l.jl:56-87 (formulas are the spec) -----------------------------------------
+def test_update_y_l_formulas():
+    TF = np.float64
+    spec = pr.spec_config1((12, 10), TF)
+    b = pr.build(orc, spec)
+    p = len(b["TD_OP"])
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(b["TD_OP"][0].shape[1])
+    mk = lambda: [rng.standard_normal(A.shape[0]) for A in b["TD_OP"]]     # noqa: E731
+    y, l = mk(), mk()
+    y0, l0 = [v.copy() for v in y], [v.copy() for v in l]
+    rho = np.array([1.0, 2.0, 3.0, 4.0])
+    gamma = np.array([1.0, 1.5, 1.0, 0.75])
+    m = spec["m"]
+    prox = list(b["P_sub"]) + [lambda v: proj.prox_l2s(v, rho[-1], m)]
+    log = T.log_type_PARSDMM(np.zeros((5, p - 1)), np.zeros((5, p)), np.zeros((5, p)), np.zeros(5), np.zeros(5),
+                             np.zeros(5), np.zeros(5), np.zeros((5, p)), np.zeros((5, p)), np.zeros(5), np.zeros(5), {})
+    zl = lambda: [np.zeros_like(v) for v in y]     # noqa: E731
+    y_old, l_old, x_hat, r_pri, s = zl(), zl(), zl(), zl(), zl()
+    counter = par.update_y_l(x, p, 1, y, y_old, l, l_old, rho.copy(), gamma.copy(), prox, b["TD_OP"], log, b["P_sub"],
+                             2, x_hat, r_pri, s, False)
+    assert counter == 2
+    for i in range(p):
+        si = b["TD_OP"][i] @ x
+        xh = gamma[i] * si + (1 - gamma[i]) * y0[i]
+        yi = prox[i](xh - l0[i] / rho[i])
+        li = l0[i] + rho[i] * (yi - xh)
+        assert np.allclose(s[i], si, atol=1e-14) and np.allclose(y[i], yi, atol=1e-12)
+        assert np.allclose(l[i], li, atol=1e-11) and np.allclose(r_pri[i], yi - si, atol=1e-12)
+        assert np.array_equal(y_old[i], y0[i]) and np.array_equal(l_old[i], l0[i])
+
+
+# ---- test/test_PARSDMM.jl:17-189 (properties) ------------------------------------------------------
+def test_PARSDMM_feasible_input_unchanged():
+    TF = np.float64
+    m = pr.synthetic_model((20, 30), TF)
+    spec = dict(n=(20, 30), d=(1.0, 1.0), TF=TF, m=m, sets=[("bounds", "identity", float(m.min()), float(m.max()))],
+                mode="matrix")
+    b = pr.build(orc, spec)
+    x, log, _, _ = orc.PARSDMM(m.copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+    assert np.array_equal(x, m) and len(log.obj) == 1 and log.set_feasibility.shape == (1, 1)
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(Blas_active=False), dict(adjust_gamma=False),
+                                     dict(adjust_rho=False), dict(adjust_rho=False, adjust_gamma=False),
+                                     dict(adjust_feasibility_rho=False)])
+def test_PARSDMM_sets_feasible_after_projection(variant):
+    """100x201 F64, bounds ∩ D_z-bounds ∩ TV-l1 (test_PARSDMM.jl:38-189; smaller grid, NumPy RNG)."""
+    TF = np.float64
+    n = (40, 51)
+    rng = np.random.default_rng(123)
+    x0 = rng.standard_normal(int(np.prod(n)))
+    cg = T.compgrid((1.0, 1.0), n)
+    Dz = ops.get_TD_operator(cg, "D_z", TF)[0]
+    TV = ops.get_TD_operator(cg, "TV", TF)[0]
+    sets = [("bounds", "identity", 0.5 * x0.min(), 0.5 * x0.max()),
+            ("bounds", "D_z", 0.5 * (Dz @ x0).min(), 0.5 * (Dz @ x0).max()),
+            ("l1", "TV", 0.0, 0.5 * np.abs(TV @ x0).sum())]
+    spec = dict(n=n, d=(1.0, 1.0), TF=TF, m=x0, sets=sets, mode="matrix")
+    opt = T.PARSDMM_options()
+    # fixed-rho ADMM converges slowly on this problem: looser target for those variants
+    opt.obj_tol = opt.feas_tol = 1e-8 if variant.get("adjust_rho", True) else 1e-5
+    opt.evol_rel_tol = 10 * np.finfo(TF).eps
+    opt.maxit = 3000
+    for k, v in variant.items():
+        setattr(opt, k, v)
+    b = pr.build(orc, spec, opt)
+    x, log, _, _ = orc.PARSDMM(x0.copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+    for i in range(len(b["TD_OP"]) - 1):
+        s = b["TD_OP"][i] @ x
+        assert np.linalg.norm(b["P_sub"][i](s.copy()) - s) / np.linalg.norm(s) <= 1.5 * opt.feas_tol
+    assert log.cg_it[0] == 0 and np.isnan(log.evol_x[0])          # quirk Q1 of SURVEY §8a
+    assert log.set_feasibility.shape[0] == (len(log.obj) // 10) + 2   # quirk Q2: one trailing zero row
+
+
+def test_reduction_mode_sensitivity():
+    """Iteration counts are robust to the (unpinned) summation order of the reference's BLAS:
+    f64-accumulated and native-TF reductions agree to the Float32 parity tolerance."""
+    spec = pr.spec_config2((16, 16, 16), np.float32)
+    out = {}
+    for mode in ("f64acc", "native"):
+        T.set_reduction_mode(mode)
+        try:
+            b = pr.build(orc, dict(spec))
+            out[mode] = orc.PARSDMM(spec["m"].copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+        finally:
+            T.set_reduction_mode("f64acc")
+    xa, xb = out["f64acc"][0], out["native"][0]
+    assert np.linalg.norm(xa - xb) / np.linalg.norm(xa) < 1e-3
