@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py — PARSDMM iterations/s on the 3-D intersection-projection workload of BASELINE.json.
+
+A "step" is one complete PARSDMM projection (initial feasibility check, Q assembly, iterations until the
+reference's stopping rules fire) of the configs[1] workload: 3-D 200^3 Float32, bounds ∩ anisotropic-TV
+l1 ball ∩ lateral slope bounds (examples/test_scaling_3D.jl-style).  value = PARSDMM iterations / second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 200] [--impl reference]
+
+* device arm (default): `value` with the problem and m resident in HBM (CUDA-event time of the solves),
+  `e2e` through the public API `sip_b200.PARSDMM(m, ...)` with host buffers (H2D of m, D2H of x and log
+  inside the timed region), the roofline of the dominant kernel (CDS SpMV + dot) from a CUDA-event
+  kernel table, and a bounded CPU baseline (the NumPy oracle, rank 0, N=1 only).
+* --impl reference: the reference's CPU algorithm (oracle port; Julia is not installable here) on the
+  host cores, same workload/metric, each step a bounded sample (a few PARSDMM iterations).
+
+Multi-GPU (N>1, torchrun): one process per GPU; until slab decomposition lands every rank projects its
+own independent model ("replicas", weak scaling); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def workload(n, TF=np.float32, seed=1234):
+    import problems as pr
+    spec = pr.spec_config2((n, n, n), TF)
+    if seed != 1234:
+        spec["m"] = pr.synthetic_model((n, n, n), TF, seed)
+    return spec
+
+
+def tweak_options(o):
+    o.evol_rel_tol = 10 * float(np.finfo(np.float32).eps)      # examples/test_scaling_3D.jl:25
+    o.maxit = 200
+    return o
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = "/tmp/sipb_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                t = [v.strip() for v in line.split(",")]
+                if len(t) < 9:
+                    continue
+                try:
+                    sm.append(float(t[1]))
+                    mx.append(float(t[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+            out["sm_mhz"] = float(np.median(busy))
+            out["sm_max_mhz"] = float(max(mx))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU side (oracle port of the reference algorithm)
+# --------------------------------------------------------------------------------------------------
+def cpu_sample(n, iters):
+    """Run `iters` PARSDMM iterations of the workload with the CPU oracle; returns (its/s over the
+    iteration phases, seconds of the iteration phases, setup seconds)."""
+    import problems as pr
+    orc = pr.OracleAPI()
+    spec = workload(n)
+    opt = tweak_options(orc.PARSDMM_options())
+    opt.maxit = iters
+    t0 = time.perf_counter()
+    ob = pr.build(orc, spec, opt)
+    t_setup = time.perf_counter() - t0
+    x, log, _, _ = orc.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"])
+    t_iter = sum(v for k, v in log.timing.items() if k != "initialization")
+    done = len(log.obj)
+    return done / t_iter, t_iter, t_setup + log.timing.get("initialization", 0.0), done
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    n = args.n
+    cores = os.cpu_count() or 1
+    iters = args.cpu_iters
+    vals, secs = [], []
+    for s in range(args.warmup + args.steps):
+        v, t_iter, t_setup, done = cpu_sample(n, iters)
+        if s >= args.warmup:
+            vals.append(v)
+            secs.append(t_iter)
+    value = float(sum(iters for _ in vals) / sum(secs))
+    sample = ("first %d PARSDMM iterations of the %d^3 Float32 workload per step; rate counts the iteration phases "
+              "only (problem set-up and PARSDMM_initialize excluded, which favours the CPU)" % (iters, n))
+    line = {
+        "impl": "reference", "metric": "parsdmm_iterations_per_second", "value": value, "unit": "iterations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(secs)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D %d^3 Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1])" % n,
+                   "grid": [n, n, n], "note": "CPU restatement of the reference algorithm (NumPy/SciPy oracle); the Julia "
+                   "reference cannot be installed in this image"},
+        "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": 1, "kind": "port", "sample": sample,
+                         "host_cores_available": cores},
+        "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# device arm
+# --------------------------------------------------------------------------------------------------
+def run_device(args, rank, world, local_rank):
+    import torch
+    import sip_b200 as sip
+    import problems as pr
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the product has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.n
+    N = n ** 3
+    spec = workload(n, seed=1234 + rank)
+    opt = tweak_options(sip.PARSDMM_options())
+    sb = pr.build(sip, spec, opt)
+    m = spec["m"]
+    call = lambda **kw: sip.PARSDMM(m, sb["AtA"], sb["TD_OP"], sb["set_Prop"], sb["P_sub"], sb["cg"], sb["opt"],   # noqa: E731
+                                    return_ly=False, **kw)
+    # first call uploads the operators (the "distribute" of PARSDMM_precompute_distribute)
+    x, log, _, _ = call()
+    iters_per_step = len(log.obj)
+    for _ in range(max(args.warmup - 1, 0)):
+        call(resident_io=True)
+
+    # ---- timed: resident (value) ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_s, its, launches = 0.0, 0, 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, lg, _, _ = call(resident_io=True)
+        dev_s += lg.timing["device_seconds"]
+        its += len(lg.obj)
+        launches += lg.timing["total_launches"]
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    # ---- timed: end to end through the public API with host buffers -------------------------------
+    barrier()
+    t0 = time.perf_counter()
+    e2e_its, h2d, d2h = 0, 0, 0
+    for _ in range(args.steps):
+        xk, lg, _, _ = call()
+        e2e_its += len(lg.obj)
+        h2d += lg.timing["h2d_bytes"]
+        d2h += lg.timing["d2h_bytes"]
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # max over ranks (device time for `value`, wall for e2e)
+    tm = torch.tensor([dev_s, wall_e2e, wall_resident], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([its, e2e_its, launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_s_max, wall_e2e_max, wall_res_max = [float(v) for v in tm.tolist()]
+    its_all, e2e_its_all, launches_all = [float(v) for v in cnt.tolist()]
+
+    # ---- roofline of the dominant kernel from one profiled solve (CUDA events around every launch) --
+    roof = None
+    kernels = {}
+    if rank == 0:
+        _, lgp, _, _ = call(resident_io=True, profile_kernels=True)
+        kernels = lgp.timing["kernels"]
+        nd = len(sb["AtA"]._device.q_offsets)
+        alg = (nd + 2) * N * 4
+        cnt_k, ms_k = kernels.get("cds_spmv_dot", (0, 0.0))
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+        else:
+            peak, which = 6650.0, "fallback"
+        if cnt_k:
+            avg_ms = ms_k / cnt_k
+            ach = alg / (avg_ms * 1e-3) / 1e9
+            tot_ms = sum(v[1] for v in kernels.values())
+            roof = {"bound": "hbm", "kernel": "cds_spmv_dot", "achieved": ach, "peak": peak, "peak_source": which,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                    "avg_launch_ms": avg_ms, "launches": cnt_k, "share_of_kernel_time": ms_k / tot_ms if tot_ms else None}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        v, t_iter, t_setup, done = cpu_sample(n, args.cpu_iters)
+        cpu = {"value": v, "unit": "iterations/s", "cores": 1, "kind": "port",
+               "sample": "first %d PARSDMM iterations of the same %d^3 workload with the NumPy oracle (%.1f s of iteration "
+                         "phases; %.1f s of set-up and initialization excluded)" % (done, n, t_iter, t_setup),
+               "host_cores_available": os.cpu_count()}
+
+    value = its_all / dev_s_max
+    line = {
+        "metric": "parsdmm_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "3D %d^3 Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1], "
+                               "test_scaling_3D-style)" % n, "grid": [n, n, n],
+                   "step": "one full PARSDMM projection to the reference's stopping rules",
+                   "parsdmm_iterations_per_step": iters_per_step, "time_to_tolerance_ms": 1e3 * dev_s_max / args.steps,
+                   "cache": "working set %.1f GB (Q + AtA + 9 vectors per set) >> 126 MB L2, no flush needed" % (N * 4 * 105 / 1e9),
+                   "parallelism": "single GPU" if world == 1 else "replicas x%d (independent models per GPU)" % world},
+        "e2e": {"value": e2e_its_all / wall_e2e_max, "unit": "iterations/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * wall_e2e_max / args.steps},
+        "gpu_launches": int(launches_all),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "kernel_table_ms": {k: [v[0], round(v[1], 3)] for k, v in kernels.items()},
+        "resident_wall_ms_per_step": 1e3 * wall_res_max / args.steps,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="device", choices=["device", "reference"])
+    ap.add_argument("--n", type=int, default=200, help="grid width (BASELINE configs[1] uses 200)")
+    ap.add_argument("--cpu-iters", type=int, default=4, help="PARSDMM iterations in the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_device(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

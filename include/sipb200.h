@@ -97,6 +97,9 @@ typedef struct sipb_options {
   const double* rho_ini;        /* n_rho_ini values, already rounded to TF                      */
   int32_t fixed_iterations;     /* >0: ignore the stop rules and run exactly this many iterations (benchmarks) */
   int32_t return_ly;            /* 1: copy l and y back to the host arrays                      */
+  int32_t resident_io;          /* 1: benchmark mode — m is taken from the device buffer left by the previous
+                                   solve of this problem and x/l/y are not copied back (no H2D/D2H at all)   */
+  int32_t reserved;
 } sipb_options;
 
 #define SIPB_N_PHASES 7         /* TimerOutputs sections of PARSDMM.jl:40,100,105,113,152,163,229 */
@@ -124,7 +127,8 @@ typedef struct sipb_log {
   double* cg_relres;
   double  phase_seconds[SIPB_N_PHASES];   /* host wall time per TimerOutputs section, same order   */
   double  solve_seconds;                  /* whole sipb_solve call incl. H2D/D2H                    */
-  double  device_seconds;                 /* CUDA-event time of the iteration loop on the stream    */
+  double  device_seconds;                 /* CUDA-event time of the whole solve on the stream, after the
+                                             H2D of m is enqueued and before the D2H of x                 */
   /* kernel table (profile_kernels=1): launches and summed CUDA-event milliseconds per class */
   int64_t kernel_launches[SIPB_N_KERNEL_CLASSES];
   double  kernel_ms[SIPB_N_KERNEL_CLASSES];

@@ -44,7 +44,8 @@ class Options(C.Structure):
                 ("n_rho_ini", C.c_int32), ("profile_kernels", C.c_int32),
                 ("evol_rel_tol", C.c_double), ("feas_tol", C.c_double), ("obj_tol", C.c_double),
                 ("gamma_ini", C.c_double), ("rho_ini", C.POINTER(C.c_double)),
-                ("fixed_iterations", C.c_int32), ("return_ly", C.c_int32)]
+                ("fixed_iterations", C.c_int32), ("return_ly", C.c_int32), ("resident_io", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class Log(C.Structure):

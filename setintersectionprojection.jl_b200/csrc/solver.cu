@@ -503,6 +503,7 @@ struct Problem : sipb_problem {
   std::vector<int64_t> q_offs;
   DevBuf<T> Q, x, x_old, rhs, r, pvec, Ap, m, tmp;
   i64 maxM = 0;
+  bool m_resident = false;
 
   Problem(sipb_ctx* c, int dt, int nd_, const int64_t* n_, const double* h_, bool mk, bool fo) {
     ctx = c; dtype = dt; ndim = nd_; minkowski = mk; feas_only = fo;
@@ -840,9 +841,20 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   for (int i = 0; i < p; ++i) rho[i] = (T)(o->n_rho_ini == 1 ? o->rho_ini[0] : o->rho_ini[i]);
 
   // m (for Minkowski the feasibility check uses [m; 0], PARSDMM_initialize.jl:85-87)
-  SIPB_CUDA_CHECK(cudaMemcpyAsync(m.p, m_h, npts * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-  log->h2d_bytes += npts * sizeof(T);
-  if (minkowski) SIPB_CUDA_CHECK(cudaMemsetAsync(m.p + npts, 0, npts * sizeof(T), c->stream));
+  const bool resident = o->resident_io != 0;
+  if (resident) {
+    SIPB_REQUIRE(m_resident, SIPB_E_STATE, "resident_io needs a previous regular solve of this problem");
+    SIPB_REQUIRE(o->zero_ini_guess, SIPB_E_INVALID, "resident_io requires zero_ini_guess");
+  } else {
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(m.p, m_h, npts * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    log->h2d_bytes += npts * sizeof(T);
+    if (minkowski) SIPB_CUDA_CHECK(cudaMemsetAsync(m.p + npts, 0, npts * sizeof(T), c->stream));
+    m_resident = true;
+  }
+  cudaEvent_t ev0, ev1;
+  SIPB_CUDA_CHECK(cudaEventCreate(&ev0));
+  SIPB_CUDA_CHECK(cudaEventCreate(&ev1));
+  SIPB_CUDA_CHECK(cudaEventRecord(ev0, c->stream));
 
   // initial feasibility  ||P(A m) - A m|| / (||A m|| + 100 eps)   (:97-99)
   const int nP = pp;   // P_sub has one entry per non-distance set
@@ -870,9 +882,13 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
 
   if (stop) {                                                      // PARSDMM.jl:63-82
     // x = m (Minkowski: [m; 0]); device buffer m already holds exactly that
-    SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, m.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    if (!resident) {
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, m.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+      log->d2h_bytes += N * sizeof(T);
+    }
     SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    log->d2h_bytes += N * sizeof(T);
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
     log->stopped_feasible = 1;
     log->iters = 0;
     log->feas_rows = 1;
@@ -928,11 +944,6 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   const int p_log = p;
   auto LG = [&](double* arr, int it, int col, int ncol) -> double& { return arr[(size_t)it * ncol + col]; };
   phase_end(0);
-
-  cudaEvent_t ev0, ev1;
-  SIPB_CUDA_CHECK(cudaEventCreate(&ev0));
-  SIPB_CUDA_CHECK(cudaEventCreate(&ev1));
-  SIPB_CUDA_CHECK(cudaEventRecord(ev0, c->stream));
 
   int last_cg = 1;
   int iters_done = 0;
@@ -1124,9 +1135,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   SIPB_CUDA_CHECK(cudaEventRecord(ev1, c->stream));
 
   // ---------------- results -------------------------------------------------------------------
-  SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, x.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
-  log->d2h_bytes += N * sizeof(T);
-  if (o->return_ly) {
+  if (!resident) {
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, x.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    log->d2h_bytes += N * sizeof(T);
+  }
+  if (o->return_ly && !resident) {
     for (int i = 0; i < p; ++i) {
       SetT<T>& S = *sets[i];
       SIPB_CUDA_CHECK(cudaMemcpyAsync(l_h[i], S.l.p, S.M * sizeof(T), cudaMemcpyDeviceToHost, c->stream));

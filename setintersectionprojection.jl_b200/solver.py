@@ -92,7 +92,7 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
 
 
 def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
-            profile_kernels=False, fixed_iterations=0, return_ly=True):
+            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False):
     """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
     Returns (x, log_PARSDMM, l, y)."""
     if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
@@ -159,6 +159,7 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
     o.gamma_ini = float(options.gamma_ini)
     o.rho_ini = rho_ini.ctypes.data_as(C.POINTER(C.c_double))
     o.fixed_iterations, o.return_ly = int(fixed_iterations), int(bool(return_ly and have_ly))
+    o.resident_io = int(bool(resident_io))      # benchmark mode: no H2D/D2H (see include/sipb200.h)
 
     arr = {
         "set_feasibility": np.zeros((maxit + 2, max(pp, 1))), "r_dual": np.zeros((maxit, p)),
