@@ -20,7 +20,7 @@ typedef long long i64;
 
 constexpr int kThreads = 256;          // threads per CTA for every streaming kernel
 constexpr int kMaxBlocks = 148 * 16;   // upper bound on the grid of any reducing kernel
-constexpr int kMaxRed = 8;             // max number of simultaneous reductions per kernel
+constexpr int kMaxRed = 10;            // max number of simultaneous reductions per kernel
 
 // ---------------------------------------------------------------------------------------------
 // vector types: 16-byte accesses (float4 / double2)

@@ -371,29 +371,75 @@ __device__ __forceinline__ bool op_touches_half(int mode, bool upper) {
          (mode == SIPB_BLOCK_RIGHT && upper);
 }
 
+// grid-point coordinates with carry; cc is the index inside one N-block, `upper` the Minkowski half
+struct GridIdx {
+  i64 cc;
+  unsigned i, j, k;
+  bool upper;
+};
+__device__ __forceinline__ GridIdx grid_decode(i64 c, i64 npts, const unsigned (&n)[3]) {
+  GridIdx g;
+  g.upper = c >= npts;
+  g.cc = g.upper ? c - npts : c;
+  const unsigned q = (unsigned)g.cc;
+  const unsigned t = q / n[0];
+  g.i = q - t * n[0];
+  g.k = t / n[1];
+  g.j = t - g.k * n[1];
+  return g;
+}
+__device__ __forceinline__ void grid_next(GridIdx& g, i64 npts, const unsigned (&n)[3]) {
+  g.cc += 1;
+  if (g.cc == npts) {          // crossed into the second Minkowski half
+    g.cc = 0; g.i = 0; g.j = 0; g.k = 0; g.upper = true;
+    return;
+  }
+  if (++g.i == n[0]) {
+    g.i = 0;
+    if (++g.j == n[1]) { g.j = 0; ++g.k; }
+  }
+}
+
+// W consecutive columns per thread: the gathers of the W columns are independent, which gives the
+// memory system W x (rows per column) loads in flight per thread; rhs is written with 16-byte stores.
+template <typename T, int W>
+__device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W]) {
+  GridIdx g[W];
+  g[0] = grid_decode(c0, a.npts, a.n);
+#pragma unroll
+  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], a.npts, a.n); }
+#pragma unroll
+  for (int e = 0; e < W; ++e) acc[e] = (T)0;
+  for (int s = 0; s < a.nsets; ++s) {
+    const SetRef<T>& S = a.sets[s];
+    const T rho = S.rho;
+    const T* __restrict__ y = S.y;
+    const T* __restrict__ l = S.l;
+    T tv[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      tv[e] = (T)0;
+      if (op_touches_half(S.op.mode, g[e].upper))
+        tv[e] = op_adjoint_f<T>(S.op, g[e].cc, g[e].i, g[e].j, g[e].k, [=](i64 row) -> T { return rho * y[row] + l[row]; });
+    }
+#pragma unroll
+    for (int e = 0; e < W; ++e) acc[e] = acc[e] + tv[e];
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_rhs(const __grid_constant__ RhsArgs<T> a) {
-  for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < a.ncols; c += (i64)gridDim.x * blockDim.x) {
-    const bool upper = c >= a.npts;
-    const i64 cc = upper ? c - a.npts : c;
-    const unsigned q = (unsigned)cc;
-    const unsigned t = q / a.n[0];
-    const unsigned i = q - t * a.n[0];
-    const unsigned k = t / a.n[1];
-    const unsigned j = t - k * a.n[1];
-    T acc = (T)0;
-    for (int s = 0; s < a.nsets; ++s) {
-      const SetRef<T>& S = a.sets[s];
-      T tv = (T)0;
-      if (op_touches_half(S.op.mode, upper)) {
-        const T rho = S.rho;
-        const T* y = S.y;
-        const T* l = S.l;
-        tv = op_adjoint_f<T>(S.op, cc, i, j, k, [=](i64 row) -> T { return rho * y[row] + l[row]; });
-      }
-      acc = acc + tv;
-    }
-    a.rhs[c] = acc;
+  constexpr int VW = Vec<T>::W;
+  const i64 nvec = a.ncols / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+    T acc[VW];
+    rhs_cols<T, VW>(a, iv * VW, acc);
+    vstore<T>(a.rhs + iv * VW, acc);
+  }
+  for (i64 c = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; c < a.ncols; c += (i64)gridDim.x * blockDim.x) {
+    T acc[1];
+    rhs_cols<T, 1>(a, c, acc);
+    a.rhs[c] = acc[0];
   }
 }
 
@@ -477,83 +523,178 @@ __host__ __device__ __forceinline__ bool proj_is_elementwise(int kind) {
 
 // =============================================================================================
 // y / l update                               (update_y_l.jl:39-94)
+// fused with the rho/gamma adaptation reductions and snapshots
+//                                            (adapt_rho_gamma.jl:41-53, PARSDMM.jl:164-207)
 // =============================================================================================
+template <typename T>
+struct ProjParams {       // device-resident projector parameters written by the parameter kernels
+  T theta;
+  T scale;
+  T fill;
+  unsigned long long key_thr;
+  unsigned long long quota;
+  unsigned long long count_eq;
+  int keep_all, keep_none, need_ties;
+};
+
 template <typename T>
 struct YlArgs {
   OpDev op;
   ProjDev<T> P;
+  const ProjParams<T>* dyn;   // reduction-type projectors: parameters produced on the device
   const T* x;
   T* y;
   T* l;
   T* y_old;
-  T* l_old;
-  T* s;
+  T* s;                       // only reduction-type projectors keep s between their two passes
+  T* lhat0; T* s0; T* l0; T* y0;   // snapshots of the adaptation scheme
   T rho, gamma;
   int want_feas;     // also reduce ||P(s)-s||^2 and ||s||^2 (element-wise projectors only)
+  int do_sums;       // the six adaptation reductions against the previous snapshots
+  int do_snapshot;   // overwrite the snapshots (l_hat_0, y_0, s_0, l_0)
 };
 
+template <typename T, int W> __device__ __forceinline__ void load_n(const T* p, T (&v)[W]) {
+  if constexpr (W == Vec<T>::W) vload<T>(p, v);
+  else {
+#pragma unroll
+    for (int e = 0; e < W; ++e) v[e] = p[e];
+  }
+}
+template <typename T, int W> __device__ __forceinline__ void store_n(T* p, const T (&v)[W]) {
+  if constexpr (W == Vec<T>::W) vstore<T>(p, v);
+  else {
+#pragma unroll
+    for (int e = 0; e < W; ++e) p[e] = v[e];
+  }
+}
+
+// Processes W consecutive rows starting at r0.
 // MODE 0: element-wise projector, everything in one pass.
-//         sums: [0] ||y-s||^2, [1] ||P(s)-s||^2, [2] ||s||^2
-// MODE 1: reduction-type projector, pass 1: y <- v = x_hat - l/rho, s stored, y_old/l_old saved.
-//         sums: [0] sum|v|, [1] sum v^2, [2] count(v != 0)
-// MODE 2: reduction-type projector, pass 2: y <- P(v), l update.  sums: [0] ||y-s||^2
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
-  double d[3] = {0.0, 0.0, 0.0};
+// MODE 1: reduction-type projector, pass 1: y <- v = x_hat - l/rho, s stored, y_old saved.
+// MODE 2: reduction-type projector, pass 2: y <- P(v), l update.
+// d[]: MODE 0/2: [0] ||y-s||^2, [1] ||P(s)-s||^2, [2] ||s||^2 ; MODE 1: [0] sum|v|, [1] sum v^2, [2] nnz(v)
+//      ADAPT   : [3] dot(dH,dlh) [4] ||dH||^2 [5] ||dlh||^2 [6] ||dl||^2 [7] ||dG||^2 [8] dot(dG,dl)
+template <typename T, int MODE, bool ADAPT, int W>
+__device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P, i64 r0, double* d) {
   const T rho = a.rho, gamma = a.gamma;
   const T rho1 = (T)1.0 / rho;                      // update_y_l.jl:34
   const bool relaxed = !(gamma == (T)1);
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.op.rows; r += (i64)gridDim.x * blockDim.x) {
-    if (MODE == 0 || MODE == 1) {
-      const T s = op_forward<T>(a.op, r, a.x);
-      const T yo = a.y[r];
-      const T lo = a.l[r];
-      T xh = s;
-      if (relaxed) xh = gamma * s + ((T)1.0 - gamma) * yo;     // :72
-      const T v = xh - lo * rho1;                                // :67 / :74
-      a.y_old[r] = yo;
-      a.l_old[r] = lo;
-      a.s[r] = s;
+  T s[W], yo[W], lo[W], yn[W], ln[W];
+  if (MODE == 0 || MODE == 1) {
+    load_n<T, W>(a.y + r0, yo);
+    load_n<T, W>(a.l + r0, lo);
+#pragma unroll
+    for (int e = 0; e < W; ++e) s[e] = op_forward<T>(a.op, r0 + e, a.x);
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      T xh = s[e];
+      if (relaxed) xh = gamma * s[e] + ((T)1.0 - gamma) * yo[e];     // :72
+      const T v = xh - lo[e] * rho1;                                    // :67 / :74
       if (MODE == 0) {
-        const T yn = proj_apply<T>(a.P, v, r);
-        const T rp = -s + yn;                                    // :69 / :76
-        const T ln = relaxed ? lo + rho * (-xh + yn) : lo + rho * rp;
-        a.y[r] = yn;
-        a.l[r] = ln;
+        yn[e] = proj_apply<T>(P, v, r0 + e);
+        const T rp = -s[e] + yn[e];                                     // :69 / :76
+        ln[e] = relaxed ? lo[e] + rho * (-xh + yn[e]) : lo[e] + rho * rp;
         d[0] += (double)rp * (double)rp;
         if (a.want_feas) {
-          const T pf = proj_apply<T>(a.P, s, r) - s;
+          const T pf = proj_apply<T>(P, s[e], r0 + e) - s[e];
           d[1] += (double)pf * (double)pf;
-          d[2] += (double)s * (double)s;
+          d[2] += (double)s[e] * (double)s[e];
         }
       } else {
-        a.y[r] = v;
+        yn[e] = v;
         d[0] += (double)t_abs<T>(v);
         d[1] += (double)v * (double)v;
         d[2] += (v != (T)0) ? 1.0 : 0.0;
       }
-    } else {
-      const T v = a.y[r];
-      const T s = a.s[r];
-      const T lo = a.l[r];
-      const T yn = proj_apply<T>(a.P, v, r);
-      const T rp = -s + yn;
-      T ln;
+    }
+    store_n<T, W>(a.y + r0, yn);
+    store_n<T, W>(a.y_old + r0, yo);
+    if (MODE == 0) store_n<T, W>(a.l + r0, ln);
+    else store_n<T, W>(a.s + r0, s);
+  } else {
+    T v[W];
+    load_n<T, W>(a.y + r0, v);
+    load_n<T, W>(a.s + r0, s);
+    load_n<T, W>(a.l + r0, lo);
+    if (relaxed || ADAPT) load_n<T, W>(a.y_old + r0, yo);
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      yn[e] = proj_apply<T>(P, v[e], r0 + e);
+      const T rp = -s[e] + yn[e];
       if (relaxed) {
-        const T xh = gamma * s + ((T)1.0 - gamma) * a.y_old[r];
-        ln = lo + rho * (-xh + yn);
+        const T xh = gamma * s[e] + ((T)1.0 - gamma) * yo[e];
+        ln[e] = lo[e] + rho * (-xh + yn[e]);
       } else {
-        ln = lo + rho * rp;
+        ln[e] = lo[e] + rho * rp;
       }
-      a.y[r] = yn;
-      a.l[r] = ln;
       d[0] += (double)rp * (double)rp;
     }
+    store_n<T, W>(a.y + r0, yn);
+    store_n<T, W>(a.l + r0, ln);
   }
-  if (grid_sum<3>(d, rs) && threadIdx.x == 0) {
+  if (ADAPT && MODE != 1) {
+    T lh[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) lh[e] = lo[e] + rho * (-s[e] + yo[e]);     // adapt_rho_gamma.jl:41
+    if (a.do_sums) {
+      T lh0[W], s0[W], l0[W], y0[W];
+      load_n<T, W>(a.lhat0 + r0, lh0);
+      load_n<T, W>(a.s0 + r0, s0);
+      load_n<T, W>(a.l0 + r0, l0);
+      load_n<T, W>(a.y0 + r0, y0);
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        const T dlh = lh[e] - lh0[e];
+        const T dH = s[e] - s0[e];
+        const T dl = ln[e] - l0[e];
+        const T dG = -(yn[e] - y0[e]);
+        d[3] += (double)dH * (double)dlh;
+        d[4] += (double)dH * (double)dH;
+        d[5] += (double)dlh * (double)dlh;
+        d[6] += (double)dl * (double)dl;
+        d[7] += (double)dG * (double)dG;
+        d[8] += (double)dG * (double)dl;
+      }
+    }
+    if (a.do_snapshot) {
+      store_n<T, W>(a.lhat0 + r0, lh);
+      store_n<T, W>(a.y0 + r0, yn);
+      store_n<T, W>(a.s0 + r0, s);
+      store_n<T, W>(a.l0 + r0, ln);
+    }
+  }
+}
+
+// out: [0..2] as d[0..2] (MODE 2 writes only [0]); ADAPT sums go to out[4..9]
+template <typename T, int MODE, bool ADAPT>
+__global__ void __launch_bounds__(kThreads) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
+  constexpr int VW = Vec<T>::W;
+  constexpr int NR = ADAPT ? 9 : 3;
+  ProjDev<T> P = a.P;
+  if (a.dyn) {
+    P.theta = a.dyn->theta; P.scale = a.dyn->scale; P.fill = a.dyn->fill;
+    P.key_thr = a.dyn->key_thr; P.keep_all = a.dyn->keep_all; P.keep_none = a.dyn->keep_none;
+  }
+  double d[NR];
+#pragma unroll
+  for (int i = 0; i < NR; ++i) d[i] = 0.0;
+  const i64 M = a.op.rows;
+  const i64 nvec = M / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x)
+    yl_rows<T, MODE, ADAPT, VW>(a, P, iv * VW, d);
+  for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x)
+    yl_rows<T, MODE, ADAPT, 1>(a, P, r, d);
+  if (grid_sum<NR>(d, rs) && threadIdx.x == 0) {
     out[0] = d[0];
-    out[1] = d[1];
-    out[2] = d[2];
+    if (MODE != 2) {
+      out[1] = d[1];
+      out[2] = d[2];
+    }
+    if (ADAPT) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) out[4 + i] = d[3 + i];
+    }
   }
 }
 
@@ -623,66 +764,33 @@ __global__ void __launch_bounds__(kThreads) k_feas(i64 M, T* __restrict__ s, con
 // =============================================================================================
 // dual residual: || A' (y - y_old) ||^2      (update_y_l.jl:82-84)
 // =============================================================================================
+template <typename T, int W>
+__device__ __forceinline__ void rdual_cols(const OpDev& op, const T* __restrict__ y, const T* __restrict__ y_old,
+                                           i64 c0, double* d) {
+  GridIdx g[W];
+  g[0] = grid_decode(c0, op.npts, op.n);
+#pragma unroll
+  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], op.npts + 1, op.n); }
+  T t[W];
+#pragma unroll
+  for (int e = 0; e < W; ++e)
+    t[e] = op_adjoint_f<T>(op, g[e].cc, g[e].i, g[e].j, g[e].k, [=](i64 row) -> T { return y[row] - y_old[row]; });
+#pragma unroll
+  for (int e = 0; e < W; ++e) d[0] += (double)t[e] * (double)t[e];
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_rdual(const __grid_constant__ OpDev op, const T* __restrict__ y,
                                                     const T* __restrict__ y_old, RedScratch rs, double* out) {
+  constexpr int VW = Vec<T>::W;
   double d[1] = {0.0};
-  for (i64 cc = (i64)blockIdx.x * blockDim.x + threadIdx.x; cc < op.npts; cc += (i64)gridDim.x * blockDim.x) {
-    const unsigned q = (unsigned)cc;
-    const unsigned tq = q / op.n[0];
-    const unsigned i = q - tq * op.n[0];
-    const unsigned k = tq / op.n[1];
-    const unsigned j = tq - k * op.n[1];
-    const T t = op_adjoint_f<T>(op, cc, i, j, k, [=](i64 row) -> T { return y[row] - y_old[row]; });
-    d[0] += (double)t * (double)t;
-  }
+  const i64 nvec = op.npts / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x)
+    rdual_cols<T, VW>(op, y, y_old, iv * VW, d);
+  for (i64 cc = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; cc < op.npts; cc += (i64)gridDim.x * blockDim.x)
+    rdual_cols<T, 1>(op, y, y_old, cc, d);
   if (grid_sum<1>(d, rs) && threadIdx.x == 0)
     out[0] = (op.mode == SIPB_BLOCK_BOTH) ? 2.0 * d[0] : d[0];   // [A A]' v = [A'v; A'v]
-}
-
-// =============================================================================================
-// rho / gamma adaptation reductions + snapshots  (adapt_rho_gamma.jl:41-53, PARSDMM.jl:164-207)
-// =============================================================================================
-template <typename T>
-struct AdaptArgs {
-  i64 M;
-  const T* l_old; const T* y_old; const T* s; const T* l; const T* y;
-  T* lhat0; T* s0; T* l0; T* y0;
-  T rho;
-  int do_sums;       // compute the six reductions (needs the previous snapshots)
-  int do_snapshot;   // overwrite the snapshots afterwards
-};
-// out: [0] dot(dH,dlh) [1] ||dH||^2 [2] ||dlh||^2 [3] ||dl||^2 [4] ||dG||^2 [5] dot(dG,dl)
-template <typename T>
-__global__ void __launch_bounds__(kThreads) k_adapt(const __grid_constant__ AdaptArgs<T> a, RedScratch rs,
-                                                    double* out) {
-  double d[6] = {0, 0, 0, 0, 0, 0};
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.M; r += (i64)gridDim.x * blockDim.x) {
-    const T s = a.s[r], yv = a.y[r], lv = a.l[r];
-    const T lhat = a.l_old[r] + a.rho * (-s + a.y_old[r]);    // adapt_rho_gamma.jl:41
-    if (a.do_sums) {
-      const T dlh = lhat - a.lhat0[r];
-      const T dH = s - a.s0[r];
-      const T dl = lv - a.l0[r];
-      const T dG = -(yv - a.y0[r]);
-      d[0] += (double)dH * (double)dlh;
-      d[1] += (double)dH * (double)dH;
-      d[2] += (double)dlh * (double)dlh;
-      d[3] += (double)dl * (double)dl;
-      d[4] += (double)dG * (double)dG;
-      d[5] += (double)dG * (double)dl;
-    }
-    if (a.do_snapshot) {
-      a.lhat0[r] = lhat;
-      a.y0[r] = yv;
-      a.s0[r] = s;
-      a.l0[r] = lv;
-    }
-  }
-  if (grid_sum<6>(d, rs) && threadIdx.x == 0) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) out[i] = d[i];
-  }
 }
 
 // =============================================================================================

@@ -66,18 +66,6 @@ struct DevBuf {
   }
 };
 
-// dynamic (device-resident) projector parameters written by the small parameter kernels
-template <typename T>
-struct ProjParams {
-  T theta;
-  T scale;
-  T fill;
-  unsigned long long key_thr;
-  unsigned long long quota;
-  unsigned long long count_eq;
-  int keep_all, keep_none, need_ties;
-};
-
 }  // namespace sipb
 
 using namespace sipb;
@@ -318,41 +306,6 @@ __device__ __forceinline__ ProjDev<T> proj_resolve(const ProjRef<T>& R) {
   return P;
 }
 
-template <typename T, int MODE>
-__global__ void __launch_bounds__(kThreads) k_yl_dyn(const __grid_constant__ YlArgs<T> a0, const ProjParams<T>* dyn,
-                                                     RedScratch rs, double* out) {
-  // identical to k_yl but resolves the dynamic projector parameters first
-  YlArgs<T> a = a0;
-  if (dyn) {
-    a.P.theta = dyn->theta; a.P.scale = dyn->scale; a.P.fill = dyn->fill;
-    a.P.key_thr = dyn->key_thr; a.P.keep_all = dyn->keep_all; a.P.keep_none = dyn->keep_none;
-  }
-  double d[3] = {0.0, 0.0, 0.0};
-  const T rho = a.rho, gamma = a.gamma;
-  const T rho1 = (T)1.0 / rho;
-  const bool relaxed = !(gamma == (T)1);
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.op.rows; r += (i64)gridDim.x * blockDim.x) {
-    const T v = a.y[r];
-    const T s = a.s[r];
-    const T lo = a.l[r];
-    const T yn = proj_apply<T>(a.P, v, r);
-    const T rp = -s + yn;
-    T ln;
-    if (relaxed) {
-      const T xh = gamma * s + ((T)1.0 - gamma) * a.y_old[r];
-      ln = lo + rho * (-xh + yn);
-    } else {
-      ln = lo + rho * rp;
-    }
-    a.y[r] = yn;
-    a.l[r] = ln;
-    d[0] += (double)rp * (double)rp;
-  }
-  if (grid_sum<3>(d, rs) && threadIdx.x == 0) {
-    out[0] = d[0];
-  }
-}
-
 // feasibility / in-place projection with dynamic parameters; `ref` (optional) is the vector P(v) is
 // compared with (cardinality ties are resolved on a scratch copy)
 template <typename T>
@@ -480,7 +433,7 @@ struct SetT {
   sipb_set_desc desc;
   OpDev op;
   i64 M = 0;
-  DevBuf<T> y, l, y_old, l_old, s, s0, y0, l0, lhat0;
+  DevBuf<T> y, l, y_old, s, s0, y0, l0, lhat0;   // s only for reduction-type projectors
   DevBuf<T> lo_vec, hi_vec;
   DevBuf<T> ata;              // [nd][ld]
   int nd = 0;
@@ -529,7 +482,8 @@ struct Problem : sipb_problem {
     S->M = S->op.rows;
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M); };
-    A(S->y); A(S->l); A(S->y_old); A(S->l_old); A(S->s); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
+    A(S->y); A(S->l); A(S->y_old); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
+    if (!proj_is_elementwise(d->set_kind)) A(S->s);
     if (e == cudaSuccess) e = S->pp_y.alloc(1);
     if (e == cudaSuccess) e = S->pp_f.alloc(1);
     if (e == cudaSuccess) e = S->warm.alloc(2);
@@ -675,24 +629,24 @@ struct Problem : sipb_problem {
     return SIPB_OK;
   }
 
-  // relative feasibility numerator/denominator of vector s (stored in S.s) -> d_scal[slot], [slot+1]
-  int feasibility_of(SetT<T>& S, int slot) {
+  // relative feasibility numerator/denominator of the vector sv (= A x) -> d_scal[slot], [slot+1]
+  int feasibility_of(SetT<T>& S, T* sv, int slot) {
     sipb_ctx* c = ctx;
     const i64 M = S.M;
     ProjDev<T> P = proj_static(S, (T)0);
     if (proj_is_elementwise(S.desc.set_kind)) {
-      LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, S.s.p, (const T*)nullptr, P, (const ProjParams<T>*)nullptr, 0,
+      LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, sv, (const T*)nullptr, P, (const ProjParams<T>*)nullptr, 0,
              c->rs, c->d_scal + slot);
       return SIPB_OK;
     }
     const int stat_slot = slot + 10;
-    LAUNCH(c, KC_VEC_STATS, k_vec_stats<T>, c->grid_for(M), M, S.s.p, c->rs, c->d_scal + stat_slot);
-    T* vec = S.s.p;
+    LAUNCH(c, KC_VEC_STATS, k_vec_stats<T>, c->grid_for(M), M, sv, c->rs, c->d_scal + stat_slot);
+    T* vec = sv;
     const T* ref = nullptr;
     if (S.desc.set_kind == SIPB_SET_CARDINALITY) {   // ties are resolved on a scratch copy
-      SIPB_CUDA_CHECK(cudaMemcpyAsync(tmp.p, S.s.p, M * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(tmp.p, sv, M * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
       vec = tmp.p;
-      ref = S.s.p;
+      ref = sv;
     }
     int rc = projector_params(S, vec, stat_slot, S.pp_f.p, S.warm.p + 1, true);
     if (rc) return rc;
@@ -860,8 +814,9 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   const int nP = pp;   // P_sub has one entry per non-distance set
   for (int i = 0; i < nP; ++i) {
     SetT<T>& S = *sets[i];
-    LAUNCH(c, KC_OP_APPLY, k_op_forward<T>, c->grid_for(S.M), S.op, (const T*)m.p, S.s.p);
-    int rc = feasibility_of(S, i * kSlotPerSet + 1);
+    T* sv = S.s.p ? S.s.p : tmp.p;    // element-wise sets do not keep s: use the scratch vector
+    LAUNCH(c, KC_OP_APPLY, k_op_forward<T>, c->grid_for(S.M), S.op, (const T*)m.p, sv);
+    int rc = feasibility_of(S, sv, i * kSlotPerSet + 1);
     if (rc) return rc;
   }
   { int rc = ctx_sync_scalars(c); if (rc) return rc; }
@@ -920,9 +875,10 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     }
   }
   for (auto& S : sets) {
-    // the 16 work vectors of PARSDMM_initialize.jl:158-184 collapse to these; all start at zero
-    for (DevBuf<T>* b : {&S->y_old, &S->l_old, &S->s, &S->s0, &S->y0, &S->l0, &S->lhat0})
-      SIPB_CUDA_CHECK(cudaMemsetAsync(b->p, 0, S->M * sizeof(T), c->stream));
+    // the 16 work vectors per set of PARSDMM_initialize.jl:158-184 collapse to 7 (8 for reduction-type
+    // projectors): x_hat, r_pri, l_hat, l_old, d_* are register temporaries of the fused kernel
+    for (DevBuf<T>* b : {&S->y_old, &S->s, &S->s0, &S->y0, &S->l0, &S->lhat0})
+      if (b->p) SIPB_CUDA_CHECK(cudaMemsetAsync(b->p, 0, S->M * sizeof(T), c->stream));
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->warm.p, 0, 2 * sizeof(double), c->stream));
   }
   SIPB_CUDA_CHECK(cudaMemsetAsync(x_old.p, 0, N * sizeof(T), c->stream));
@@ -962,7 +918,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         ra.sets[s].l = sets[s]->l.p;
         ra.sets[s].rho = rho[s];
       }
-      LAUNCH(c, KC_RHS, k_rhs<T>, c->grid_for(N), ra);
+      LAUNCH(c, KC_RHS, k_rhs<T>, c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), ra);
     }
     phase_end(1);
     // ---------------- x-minimisation (argmin_x.jl + cg.jl) -----------------------------------
@@ -978,6 +934,10 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     phase_end(2);
     // ---------------- y / l update (update_y_l.jl) --------------------------------------------
     const bool feas_it = (i % 10 == 0);
+    // rho/gamma adaptation is fused into the y/l kernels: the flags are known before the update; if
+    // stop_PARSDMM switches adaptation off in this very iteration the sums are simply discarded
+    const bool do_adapt = (adjust_rho || adjust_gamma) && (i % rho_update_frequency == 0);
+    const bool fuse_adapt = (i == 1) || do_adapt;
     for (int s = 0; s < p; ++s) {
       SetT<T>& S = *sets[s];
       const bool is_dist = S.desc.set_kind == SIPB_SET_DISTANCE;
@@ -986,26 +946,32 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       memset(&ya, 0, sizeof(ya));
       ya.op = S.op;
       ya.P = proj_static(S, rho[s]);
-      ya.x = x.p; ya.y = S.y.p; ya.l = S.l.p; ya.y_old = S.y_old.p; ya.l_old = S.l_old.p; ya.s = S.s.p;
+      ya.x = x.p; ya.y = S.y.p; ya.l = S.l.p; ya.y_old = S.y_old.p; ya.s = S.s.p;
+      ya.lhat0 = S.lhat0.p; ya.s0 = S.s0.p; ya.l0 = S.l0.p; ya.y0 = S.y0.p;
       ya.rho = rho[s]; ya.gamma = gamma[s];
+      ya.do_sums = (do_adapt && i > 1) ? 1 : 0;     // i == 1: snapshot only (all deltas are zero)
+      ya.do_snapshot = fuse_adapt ? 1 : 0;
       const int base = s * kSlotPerSet;
+      const int g = c->grid_for((S.M + Vec<T>::W - 1) / Vec<T>::W);
       if (proj_is_elementwise(S.desc.set_kind)) {
         ya.want_feas = want_feas ? 1 : 0;
-        LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0>), c->grid_for(S.M), ya, c->rs, c->d_scal + base);
+        if (fuse_adapt) LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, true>), g, ya, c->rs, c->d_scal + base);
+        else LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, false>), g, ya, c->rs, c->d_scal + base);
       } else {
         ya.want_feas = 0;
-        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1>), c->grid_for(S.M), ya, c->rs, c->d_scal + base + 10);
+        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), g, ya, c->rs, c->d_scal + base + 10);
         int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
         if (rc) return rc;
-        LAUNCH(c, KC_YL_PASS2, (k_yl_dyn<T, 2>), c->grid_for(S.M), ya, (const ProjParams<T>*)S.pp_y.p, c->rs,
-               c->d_scal + base);
+        ya.dyn = S.pp_y.p;
+        if (fuse_adapt) LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, true>), g, ya, c->rs, c->d_scal + base);
+        else LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, false>), g, ya, c->rs, c->d_scal + base);
         if (want_feas) {
-          rc = feasibility_of(S, base + 1);
+          rc = feasibility_of(S, S.s.p, base + 1);
           if (rc) return rc;
         }
       }
-      LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for(npts), S.op, (const T*)S.y.p, (const T*)S.y_old.p, c->rs,
-             c->d_scal + base + 3);
+      LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
+             (const T*)S.y_old.p, c->rs, c->d_scal + base + 3);
     }
     LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
            (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
@@ -1075,33 +1041,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       if (stp) break;
     }
     // ---------------- rho / gamma adaptation (PARSDMM.jl:164-226) ----------------------------
-    const bool do_adapt = (adjust_rho || adjust_gamma) && (i % rho_update_frequency == 0);
-    if (i == 1 || do_adapt) {
-      for (int s = 0; s < p; ++s) {
-        SetT<T>& S = *sets[s];
-        AdaptArgs<T> aa;
-        aa.M = S.M;
-        aa.l_old = S.l_old.p; aa.y_old = S.y_old.p; aa.s = S.s.p; aa.l = S.l.p; aa.y = S.y.p;
-        aa.lhat0 = S.lhat0.p; aa.s0 = S.s0.p; aa.l0 = S.l0.p; aa.y0 = S.y0.p;
-        aa.rho = rho[s];
-        if (i == 1 && do_adapt) {
-          // snapshot first (PARSDMM.jl:164-180), then the sums against that snapshot (all zero deltas)
-          aa.do_sums = 0; aa.do_snapshot = 1;
-          LAUNCH(c, KC_ADAPT, k_adapt<T>, c->grid_for(S.M), aa, c->rs, c->d_scal + s * kSlotPerSet + 4);
-          aa.do_sums = 1; aa.do_snapshot = 0;
-          LAUNCH(c, KC_ADAPT, k_adapt<T>, c->grid_for(S.M), aa, c->rs, c->d_scal + s * kSlotPerSet + 4);
-        } else {
-          aa.do_sums = do_adapt ? 1 : 0;
-          aa.do_snapshot = 1;    // i==1: first snapshot; i>1 after adapt: re-snapshot (:198-206)
-          LAUNCH(c, KC_ADAPT, k_adapt<T>, c->grid_for(S.M), aa, c->rs, c->d_scal + s * kSlotPerSet + 4);
-        }
-      }
-      if (do_adapt) {
-        int rc = ctx_sync_scalars(c);
-        if (rc) return rc;
-        for (int s = 0; s < p; ++s)
-          adapt_scalar<T>(c->h_scal + s * kSlotPerSet + 4, rho[s], gamma[s], adjust_rho, adjust_gamma);
-      }
+    // the reductions were produced by the fused y/l kernels of this iteration (h_scal already synced)
+    if ((adjust_rho || adjust_gamma) && (i % rho_update_frequency == 0)) {
+      static const double zeros6[6] = {0, 0, 0, 0, 0, 0};
+      for (int s = 0; s < p; ++s)
+        adapt_scalar<T>(i > 1 ? c->h_scal + s * kSlotPerSet + 4 : zeros6, rho[s], gamma[s], adjust_rho, adjust_gamma);
     }
     if (adjust_feasibility_rho && i % 10 == 0 && i > 10 && pp > 0) {       // :213-223
       const double* row = log->set_feasibility + (size_t)(counter - 2) * pp;
