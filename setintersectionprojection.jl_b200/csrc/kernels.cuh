@@ -304,11 +304,13 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
 // =============================================================================================
 // rhs = sum_i A_i' (rho_i y_i + l_i)        (rhs_compose.jl:24-36)
 // =============================================================================================
+constexpr int kRdualSets = 8;   // the fused rhs + dual-residual kernel handles up to 8 terms
 template <typename T>
 struct SetRef {
   OpDev op;
   const T* y;
   const T* l;
+  const T* y_old;
   T rho;
 };
 template <typename T>
@@ -321,93 +323,14 @@ struct RhsArgs {
   SetRef<T> sets[kMaxSets];
 };
 
-template <typename T, typename F>
-__device__ __forceinline__ T op_adjoint_f(const OpDev& op, i64 cc, unsigned i, unsigned j, unsigned k, F val) {
-  T acc = (T)0;
-  switch (op.kind) {
-    case SIPB_OP_IDENTITY:
-      return acc + val(cc);
-    case SIPB_OP_DXZ: {
-      const i64 w = (i64)op.n[0] - 1;
-      const T a = (T)op.a_xz;
-      const bool il = i >= 1u, ih_ = i < op.n[0] - 1u, jl = j >= 1u, jh = j < op.n[1] - 1u;
-      const i64 q = (i64)i + w * (i64)j;
-      if (il && jl) acc = acc + a * val(q - 1 - w);
-      if (ih_ && jl) acc = acc + (-a) * val(q - w);
-      if (il && jh) acc = acc + (-a) * val(q - 1);
-      if (ih_ && jh) acc = acc + a * val(q);
-      return acc;
-    }
-    default: {
-      for (int b = 0; b < op.nblk; ++b) {
-        const int a = op.axis[b];
-        const T ih = (T)op.ih[a];
-        const i64 base = op.row_start[b];
-        unsigned coord, na;
-        i64 q, st;
-        if (a == 0) {
-          coord = i; na = op.n[0];
-          q = cc - ((i64)j + (i64)op.n[1] * k);
-          st = 1;
-        } else if (a == 1) {
-          coord = j; na = op.n[1];
-          q = cc - (i64)op.n[0] * k;
-          st = op.n[0];
-        } else {
-          coord = k; na = op.n[2];
-          q = cc;
-          st = (i64)op.n[0] * op.n[1];
-        }
-        if (coord >= 1u) acc = acc + ih * val(base + q - st);
-        if (coord < na - 1u) acc = acc + (-ih) * val(base + q);
-      }
-      return acc;
-    }
-  }
-}
-
-__device__ __forceinline__ bool op_touches_half(int mode, bool upper) {
-  return mode == SIPB_BLOCK_PLAIN || mode == SIPB_BLOCK_BOTH || (mode == SIPB_BLOCK_LEFT && !upper) ||
-         (mode == SIPB_BLOCK_RIGHT && upper);
-}
-
-// grid-point coordinates with carry; cc is the index inside one N-block, `upper` the Minkowski half
-struct GridIdx {
-  i64 cc;
-  unsigned i, j, k;
-  bool upper;
-};
-__device__ __forceinline__ GridIdx grid_decode(i64 c, i64 npts, const unsigned (&n)[3]) {
-  GridIdx g;
-  g.upper = c >= npts;
-  g.cc = g.upper ? c - npts : c;
-  const unsigned q = (unsigned)g.cc;
-  const unsigned t = q / n[0];
-  g.i = q - t * n[0];
-  g.k = t / n[1];
-  g.j = t - g.k * n[1];
-  return g;
-}
-__device__ __forceinline__ void grid_next(GridIdx& g, i64 npts, const unsigned (&n)[3]) {
-  g.cc += 1;
-  if (g.cc == npts) {          // crossed into the second Minkowski half
-    g.cc = 0; g.i = 0; g.j = 0; g.k = 0; g.upper = true;
-    return;
-  }
-  if (++g.i == n[0]) {
-    g.i = 0;
-    if (++g.j == n[1]) { g.j = 0; ++g.k; }
-  }
-}
-
 // W consecutive columns per thread: the gathers of the W columns are independent, which gives the
 // memory system W x (rows per column) loads in flight per thread; rhs is written with 16-byte stores.
-template <typename T, int W>
-__device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W]) {
+template <typename T, int W, bool RDUAL>
+__device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W], double* d) {
   GridIdx g[W];
   g[0] = grid_decode(c0, a.npts, a.n);
 #pragma unroll
-  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], a.npts, a.n); }
+  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], (unsigned)a.npts, a.n); }
 #pragma unroll
   for (int e = 0; e < W; ++e) acc[e] = (T)0;
   for (int s = 0; s < a.nsets; ++s) {
@@ -416,30 +339,47 @@ __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W
     const T* __restrict__ y = S.y;
     const T* __restrict__ l = S.l;
     T tv[W];
-#pragma unroll
-    for (int e = 0; e < W; ++e) {
-      tv[e] = (T)0;
-      if (op_touches_half(S.op.mode, g[e].upper))
-        tv[e] = op_adjoint_f<T>(S.op, g[e].cc, g[e].i, g[e].j, g[e].k, [=](i64 row) -> T { return rho * y[row] + l[row]; });
-    }
+    op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](unsigned row) -> T { return rho * y[row] + l[row]; }, tv);
 #pragma unroll
     for (int e = 0; e < W; ++e) acc[e] = acc[e] + tv[e];
+    if (RDUAL) {
+      // dual residual of the PREVIOUS iteration, ||A'(y - y_old)||^2 (update_y_l.jl:82-84), rides on the
+      // same gather: y_old still holds y^{k-1} until the next y/l update overwrites it
+      const T* __restrict__ yo = S.y_old;
+      T td[W];
+      op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](unsigned row) -> T { return y[row] - yo[row]; }, td);
+      double sq = 0.0;
+#pragma unroll
+      for (int e = 0; e < W; ++e) sq += (double)td[e] * (double)td[e];
+#pragma unroll
+      for (int q = 0; q < kRdualSets; ++q) d[q] += (q == s) ? sq : 0.0;
+    }
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kThreads) k_rhs(const __grid_constant__ RhsArgs<T> a) {
+// RDUAL: additionally reduce, per set s < kRdualSets, ||A_s'(y_s - y_old_s)||^2 -> out[s]
+template <typename T, bool RDUAL>
+__global__ void __launch_bounds__(kThreads) k_rhs(const __grid_constant__ RhsArgs<T> a, RedScratch rs, double* out) {
   constexpr int VW = Vec<T>::W;
+  double d[kRdualSets];
+#pragma unroll
+  for (int q = 0; q < kRdualSets; ++q) d[q] = 0.0;
   const i64 nvec = a.ncols / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     T acc[VW];
-    rhs_cols<T, VW>(a, iv * VW, acc);
+    rhs_cols<T, VW, RDUAL>(a, iv * VW, acc, d);
     vstore<T>(a.rhs + iv * VW, acc);
   }
   for (i64 c = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; c < a.ncols; c += (i64)gridDim.x * blockDim.x) {
     T acc[1];
-    rhs_cols<T, 1>(a, c, acc);
+    rhs_cols<T, 1, RDUAL>(a, c, acc, d);
     a.rhs[c] = acc[0];
+  }
+  if (RDUAL) {
+    if (grid_sum<kRdualSets>(d, rs) && threadIdx.x == 0) {
+#pragma unroll
+      for (int q = 0; q < kRdualSets; ++q) out[q] = d[q];
+    }
   }
 }
 
@@ -584,8 +524,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
   if (MODE == 0 || MODE == 1) {
     load_n<T, W>(a.y + r0, yo);
     load_n<T, W>(a.l + r0, lo);
-#pragma unroll
-    for (int e = 0; e < W; ++e) s[e] = op_forward<T>(a.op, r0 + e, a.x);
+    op_forward_n<T, W>(a.op, (unsigned)r0, a.x, s);
 #pragma unroll
     for (int e = 0; e < W; ++e) {
       T xh = s[e];
@@ -711,16 +650,11 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) k_op_adjoint(const __grid_constant__ OpDev op, const T* __restrict__ v,
                                                          T* __restrict__ t) {
   for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < op.cols; c += (i64)gridDim.x * blockDim.x) {
-    const bool upper = c >= op.npts;
-    const i64 cc = upper ? c - op.npts : c;
-    const unsigned q = (unsigned)cc;
-    const unsigned tq = q / op.n[0];
-    const unsigned i = q - tq * op.n[0];
-    const unsigned k = tq / op.n[1];
-    const unsigned j = tq - k * op.n[1];
-    T tv = (T)0;
-    if (op_touches_half(op.mode, upper)) tv = op_adjoint_f<T>(op, cc, i, j, k, [=](i64 row) -> T { return v[row]; });
-    t[c] = tv;
+    GridIdx g[1];
+    g[0] = grid_decode(c, op.npts, op.n);
+    T tv[1];
+    op_adjoint_n<T, 1>(op, op.mode, g, [=](unsigned row) -> T { return v[row]; }, tv);
+    t[c] = tv[0];
   }
 }
 
@@ -770,11 +704,10 @@ __device__ __forceinline__ void rdual_cols(const OpDev& op, const T* __restrict_
   GridIdx g[W];
   g[0] = grid_decode(c0, op.npts, op.n);
 #pragma unroll
-  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], op.npts + 1, op.n); }
+  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], 0xffffffffu, op.n); }
+  // the dual residual runs over one N-block only: evaluate the operator as if it were un-blocked
   T t[W];
-#pragma unroll
-  for (int e = 0; e < W; ++e)
-    t[e] = op_adjoint_f<T>(op, g[e].cc, g[e].i, g[e].j, g[e].k, [=](i64 row) -> T { return y[row] - y_old[row]; });
+  op_adjoint_n<T, W>(op, SIPB_BLOCK_PLAIN, g, [=](unsigned row) -> T { return y[row] - y_old[row]; }, t);
 #pragma unroll
   for (int e = 0; e < W; ++e) d[0] += (double)t[e] * (double)t[e];
 }

@@ -7,6 +7,11 @@
 // order:   (A*x)[r]  = left fold over the stored columns of row r in ascending column index,
 //          (A'*v)[c] = left fold over the stored rows   of column c in ascending row index,
 // each product rounded separately (no FMA), starting from zero.
+//
+// The kernels are bandwidth bound only if the index arithmetic stays cheap (ncu, round 1: the first
+// generic per-element version spent ~120 instructions per row, mostly 64-bit IMAD and divisions, and
+// ran at 30 % of HBM peak).  Therefore: 32-bit indices, W rows / columns per thread with one
+// division per group and carries for the rest, and the operator-kind switch hoisted to the group.
 #pragma once
 #include "common.cuh"
 #include "../../include/sipb200.h"
@@ -19,6 +24,7 @@ struct OpDev {
   int nblk;          // row blocks: 1, or ndim for TV
   int axis[3];       // storage axis differenced by each block, in row order
   unsigned n[3];     // model grid (n[2] == 1 in 2-D)
+  unsigned rs[4];    // first row of each block (32-bit mirror of row_start)
   i64 npts;          // n0*n1*n2
   i64 rows;          // rows of the operator
   i64 cols;          // npts, or 2*npts for Minkowski block modes
@@ -27,66 +33,253 @@ struct OpDev {
   double a_xz;       // fl(ih[1]*ih[0]) for D_xz
 };
 
-// strides of the storage axes
-__device__ __forceinline__ i64 op_stride(const OpDev& op, int a) {
-  return a == 0 ? 1 : (a == 1 ? (i64)op.n[0] : (i64)op.n[0] * op.n[1]);
+__device__ __forceinline__ unsigned op_stride32(const OpDev& op, int a) {
+  return a == 0 ? 1u : (a == 1 ? op.n[0] : op.n[0] * op.n[1]);
 }
 
-// ---- forward: add the terms of row r (acting on one N-block of x) to acc, in column order -----
+template <typename T, int W>
+__device__ __forceinline__ void load_any(const T* p, T (&v)[W]) {
+  if constexpr (W == Vec<T>::W) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
+      vload<T>(p, v);
+      return;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) v[e] = p[e];
+}
+
+// ---- forward, one row (generic; used for block-straddling groups and tiny grids) ---------------
 template <typename T>
-__device__ __forceinline__ T op_fwd_terms(const OpDev& op, i64 r, const T* __restrict__ x, T acc) {
+__device__ __forceinline__ T op_fwd_terms1(const OpDev& op, unsigned r, const T* __restrict__ x, T acc) {
   switch (op.kind) {
     case SIPB_OP_IDENTITY:
       return acc + x[r];
     case SIPB_OP_DXZ: {
       const unsigned w = op.n[0] - 1u;
-      const unsigned q = (unsigned)r;
-      const unsigned j = q / w, i = q - j * w;
-      const i64 c = (i64)i + (i64)op.n[0] * j;
+      const unsigned j = r / w, i = r - j * w;
+      const unsigned c = i + op.n[0] * j;
       const T a = (T)op.a_xz;
       acc = acc + a * x[c];
-      acc = acc + (-a) * x[c + 1];
+      acc = acc + (-a) * x[c + 1u];
       acc = acc + (-a) * x[c + op.n[0]];
-      acc = acc + a * x[c + op.n[0] + 1];
+      acc = acc + a * x[c + op.n[0] + 1u];
       return acc;
     }
     default: {
       int b = 0;
       if (op.nblk > 1) {
-        b = (r >= op.row_start[1]) ? 1 : 0;
-        if (op.nblk > 2 && r >= op.row_start[2]) b = 2;
+        b = (r >= op.rs[1]) ? 1 : 0;
+        if (op.nblk > 2 && r >= op.rs[2]) b = 2;
       }
       const int a = op.axis[b];
-      const unsigned q = (unsigned)(r - op.row_start[b]);
-      i64 c;
-      if (a == 0) {
-        c = (i64)q + (i64)(q / (op.n[0] - 1u));
-      } else if (a == 1) {
-        const unsigned plane = op.n[0] * (op.n[1] - 1u);
-        c = (i64)q + (i64)op.n[0] * (q / plane);
-      } else {
-        c = (i64)q;
-      }
+      const unsigned q = r - op.rs[b];
+      unsigned c;
+      if (a == 0) c = q + q / (op.n[0] - 1u);
+      else if (a == 1) c = q + op.n[0] * (q / (op.n[0] * (op.n[1] - 1u)));
+      else c = q;
       const T ih = (T)op.ih[a];
       acc = acc + (-ih) * x[c];
-      acc = acc + ih * x[c + op_stride(op, a)];
+      acc = acc + ih * x[c + op_stride32(op, a)];
       return acc;
     }
   }
 }
 
-template <typename T>
-__device__ __forceinline__ T op_forward(const OpDev& op, i64 r, const T* __restrict__ x) {
-  T acc = (T)0;
+// ---- forward, W consecutive rows r0..r0+W-1 acting on one N-block of x; terms are ADDED to acc ----
+template <typename T, int W>
+__device__ __forceinline__ void op_fwd_terms(const OpDev& op, unsigned r0, const T* __restrict__ x, T (&acc)[W]) {
+  if (op.kind == SIPB_OP_IDENTITY) {
+    T xv[W];
+    load_any<T, W>(x + r0, xv);
+#pragma unroll
+    for (int e = 0; e < W; ++e) acc[e] = acc[e] + xv[e];
+    return;
+  }
+  if (op.kind != SIPB_OP_DXZ && W > 1) {
+    int b = 0;
+    if (op.nblk > 1) {
+      b = (r0 >= op.rs[1]) ? 1 : 0;
+      if (op.nblk > 2 && r0 >= op.rs[2]) b = 2;
+    }
+    const unsigned bend = (b + 1 < op.nblk) ? op.rs[b + 1] : (unsigned)op.rows;
+    const int a = op.axis[b];
+    const unsigned q0 = r0 - op.rs[b];
+    if (r0 + W <= bend) {       // whole group inside one block: one division, then carries
+      const T ih = (T)op.ih[a];
+      const T nih = -ih;
+      if (a == 2 || (a == 1 && op.n[2] == 1u)) {     // slowest axis: rows and columns coincide
+        const unsigned st = op_stride32(op, a);
+        T x0[W], x1[W];
+        load_any<T, W>(x + q0, x0);
+        load_any<T, W>(x + q0 + st, x1);
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          acc[e] = acc[e] + nih * x0[e];
+          acc[e] = acc[e] + ih * x1[e];
+        }
+        return;
+      }
+      if (a == 1) {
+        const unsigned plane = op.n[0] * (op.n[1] - 1u);
+        if (plane >= (unsigned)W) {
+          const unsigned k0 = q0 / plane;
+          const unsigned rem0 = q0 - k0 * plane;
+          const unsigned st = op.n[0];
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            const unsigned k = k0 + ((rem0 + e >= plane) ? 1u : 0u);
+            const unsigned c = q0 + e + st * k;
+            acc[e] = acc[e] + nih * x[c];
+            acc[e] = acc[e] + ih * x[c + st];
+          }
+          return;
+        }
+      } else {   // a == 0
+        const unsigned w = op.n[0] - 1u;
+        if (w >= (unsigned)W) {
+          const unsigned jk0 = q0 / w;
+          const unsigned i0 = q0 - jk0 * w;
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            const unsigned jk = jk0 + ((i0 + e >= w) ? 1u : 0u);
+            const unsigned c = q0 + e + jk;
+            acc[e] = acc[e] + nih * x[c];
+            acc[e] = acc[e] + ih * x[c + 1u];
+          }
+          return;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) acc[e] = op_fwd_terms1<T>(op, r0 + e, x, acc[e]);
+}
+
+template <typename T, int W>
+__device__ __forceinline__ void op_forward_n(const OpDev& op, unsigned r0, const T* __restrict__ x, T (&s)[W]) {
+#pragma unroll
+  for (int e = 0; e < W; ++e) s[e] = (T)0;
   switch (op.mode) {
-    case SIPB_BLOCK_RIGHT: return op_fwd_terms<T>(op, r, x + op.npts, acc);
+    case SIPB_BLOCK_RIGHT:
+      op_fwd_terms<T, W>(op, r0, x + op.npts, s);
+      break;
     case SIPB_BLOCK_BOTH:
-      acc = op_fwd_terms<T>(op, r, x, acc);
-      return op_fwd_terms<T>(op, r, x + op.npts, acc);
-    default: return op_fwd_terms<T>(op, r, x, acc);
+      op_fwd_terms<T, W>(op, r0, x, s);
+      op_fwd_terms<T, W>(op, r0, x + op.npts, s);
+      break;
+    default:
+      op_fwd_terms<T, W>(op, r0, x, s);
   }
 }
 
-// The adjoint (A' v)[c] is evaluated by op_adjoint_f in kernels.cuh (generic over the value functor).
+template <typename T>
+__device__ __forceinline__ T op_forward(const OpDev& op, i64 r, const T* __restrict__ x) {
+  T s[1];
+  op_forward_n<T, 1>(op, (unsigned)r, x, s);
+  return s[0];
+}
+
+// ---- grid-point coordinates with carry ---------------------------------------------------------
+struct GridIdx {
+  unsigned cc;       // index inside one N-block
+  unsigned i, j, k;
+  bool upper;        // second Minkowski half
+};
+__device__ __forceinline__ GridIdx grid_decode(i64 c, i64 npts, const unsigned (&n)[3]) {
+  GridIdx g;
+  g.upper = c >= npts;
+  g.cc = (unsigned)(g.upper ? c - npts : c);
+  const unsigned t = g.cc / n[0];
+  g.i = g.cc - t * n[0];
+  g.k = t / n[1];
+  g.j = t - g.k * n[1];
+  return g;
+}
+__device__ __forceinline__ void grid_next(GridIdx& g, unsigned npts, const unsigned (&n)[3]) {
+  g.cc += 1u;
+  if (g.cc == npts) {          // crossed into the second Minkowski half
+    g.cc = 0u; g.i = 0u; g.j = 0u; g.k = 0u; g.upper = true;
+    return;
+  }
+  if (++g.i == n[0]) {
+    g.i = 0u;
+    if (++g.j == n[1]) { g.j = 0u; ++g.k; }
+  }
+}
+
+__device__ __forceinline__ bool op_touches_half(int mode, bool upper) {
+  return mode == SIPB_BLOCK_PLAIN || mode == SIPB_BLOCK_BOTH || (mode == SIPB_BLOCK_LEFT && !upper) ||
+         (mode == SIPB_BLOCK_RIGHT && upper);
+}
+
+// ---- adjoint: t[e] = (A' v)[g[e]] for W grid points; val(row) supplies v[row] ---------------------
+template <typename T, int W, typename F>
+__device__ __forceinline__ void op_adjoint_n(const OpDev& op, int mode, const GridIdx (&g)[W], F val, T (&t)[W]) {
+#pragma unroll
+  for (int e = 0; e < W; ++e) t[e] = (T)0;
+  switch (op.kind) {
+    case SIPB_OP_IDENTITY:
+#pragma unroll
+      for (int e = 0; e < W; ++e)
+        if (op_touches_half(mode, g[e].upper)) t[e] = t[e] + val(g[e].cc);
+      return;
+    case SIPB_OP_DXZ: {
+      const unsigned w = op.n[0] - 1u;
+      const T a = (T)op.a_xz;
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        if (!op_touches_half(mode, g[e].upper)) continue;
+        const unsigned i = g[e].i, j = g[e].j;
+        const bool il = i >= 1u, ih_ = i < op.n[0] - 1u, jl = j >= 1u, jh = j < op.n[1] - 1u;
+        const unsigned q = i + w * j;   // row (i,j)
+        T acc = (T)0;
+        if (il && jl) acc = acc + a * val(q - 1u - w);
+        if (ih_ && jl) acc = acc + (-a) * val(q - w);
+        if (il && jh) acc = acc + (-a) * val(q - 1u);
+        if (ih_ && jh) acc = acc + a * val(q);
+        t[e] = acc;
+      }
+      return;
+    }
+    default: {
+      for (int b = 0; b < op.nblk; ++b) {
+        const int a = op.axis[b];
+        const T ih = (T)op.ih[a];
+        const T nih = -ih;
+        const unsigned base = op.rs[b];
+        if (a == 0) {
+          const unsigned na = op.n[0];
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            if (!op_touches_half(mode, g[e].upper)) continue;
+            const unsigned q = base + g[e].cc - (g[e].j + op.n[1] * g[e].k);   // i + (n0-1)*(j + n1*k)
+            if (g[e].i >= 1u) t[e] = t[e] + ih * val(q - 1u);
+            if (g[e].i < na - 1u) t[e] = t[e] + nih * val(q);
+          }
+        } else if (a == 1) {
+          const unsigned na = op.n[1], st = op.n[0];
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            if (!op_touches_half(mode, g[e].upper)) continue;
+            const unsigned q = base + g[e].cc - st * g[e].k;                   // i + n0*(j + (n1-1)*k)
+            if (g[e].j >= 1u) t[e] = t[e] + ih * val(q - st);
+            if (g[e].j < na - 1u) t[e] = t[e] + nih * val(q);
+          }
+        } else {
+          const unsigned na = op.n[2], st = op.n[0] * op.n[1];
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            if (!op_touches_half(mode, g[e].upper)) continue;
+            const unsigned q = base + g[e].cc;
+            if (g[e].k >= 1u) t[e] = t[e] + ih * val(q - st);
+            if (g[e].k < na - 1u) t[e] = t[e] + nih * val(q);
+          }
+        }
+      }
+      return;
+    }
+  }
+}
 
 }  // namespace sipb

@@ -404,6 +404,7 @@ static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int
   }
   for (int a = 0; a < ndim; ++a)
     SIPB_REQUIRE(n[a] >= 2, SIPB_E_INVALID, "every grid dimension must be at least 2");
+  for (int b = 0; b < 4; ++b) op.rs[b] = (unsigned)op.row_start[b];
   *out = op;
   return SIPB_OK;
 }
@@ -903,6 +904,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
 
   int last_cg = 1;
   int iters_done = 0;
+  const bool fuse_rdual = p <= kRdualSets;
   const int it_limit = o->fixed_iterations > 0 ? std::min(o->fixed_iterations, maxit) : maxit;
   for (int i = 1; i <= it_limit; ++i) {
     // ---------------- rhs (rhs_compose.jl) ---------------------------------------------------
@@ -916,9 +918,16 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         ra.sets[s].op = sets[s]->op;
         ra.sets[s].y = sets[s]->y.p;
         ra.sets[s].l = sets[s]->l.p;
+        ra.sets[s].y_old = sets[s]->y_old.p;
         ra.sets[s].rho = rho[s];
       }
-      LAUNCH(c, KC_RHS, k_rhs<T>, c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), ra);
+      // from the second iteration on the gather also yields the dual residual of iteration i-1
+      if (fuse_rdual && i >= 2)
+        LAUNCH(c, KC_RHS, (k_rhs<T, true>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), ra, c->rs,
+               c->d_scal + kSlotGlobal + 8);
+      else
+        LAUNCH(c, KC_RHS, (k_rhs<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), ra, c->rs,
+               (double*)nullptr);
     }
     phase_end(1);
     // ---------------- x-minimisation (argmin_x.jl + cg.jl) -----------------------------------
@@ -970,8 +979,9 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
           if (rc) return rc;
         }
       }
-      LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
-             (const T*)S.y_old.p, c->rs, c->d_scal + base + 3);
+      if (!fuse_rdual)
+        LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
+               (const T*)S.y_old.p, c->rs, c->d_scal + base + 3);
     }
     LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
            (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
@@ -981,11 +991,13 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       for (int s = 0; s < p; ++s) {
         const int base = s * kSlotPerSet;
         const T rp = (T)std::sqrt(c->h_scal[base + 0]);            // update_y_l.jl:81
-        const T rd = rho[s] * (T)std::sqrt(c->h_scal[base + 3]);   // :84
         LG(log->r_pri, i - 1, s, p_log) = (double)rp;
-        LG(log->r_dual, i - 1, s, p_log) = (double)rd;
         rp_tot = rp_tot + rp;
-        rd_tot = rd_tot + rd;
+        if (!fuse_rdual) {
+          const T rd = rho[s] * (T)std::sqrt(c->h_scal[base + 3]);   // :84
+          LG(log->r_dual, i - 1, s, p_log) = (double)rd;
+          rd_tot = rd_tot + rd;
+        }
         if (feas_it && s < pp) {                                   // :90-94
           const T num = (T)std::sqrt(c->h_scal[base + 1]);
           const T den = (T)std::sqrt(c->h_scal[base + 2]);
@@ -993,7 +1005,18 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         }
       }
       if (feas_it) counter += 1;                                   // :103-105
-      log->r_dual_total[i - 1] = (double)rd_tot;                   // PARSDMM.jl:134
+      if (!fuse_rdual) {
+        log->r_dual_total[i - 1] = (double)rd_tot;                 // PARSDMM.jl:134
+      } else if (i >= 2) {
+        // r_dual of iteration i-1 arrived with this iteration's rhs kernel (it is log-only: no rule reads it)
+        T tot = 0;
+        for (int s = 0; s < p; ++s) {
+          const T rd = (T)LG(log->rho, i - 2, s, p_log) * (T)std::sqrt(c->h_scal[kSlotGlobal + 8 + s]);
+          LG(log->r_dual, i - 2, s, p_log) = (double)rd;
+          tot = tot + rd;
+        }
+        log->r_dual_total[i - 2] = (double)tot;
+      }
       log->r_pri_total[i - 1] = (double)rp_tot;                    // :138
       const double* g = c->h_scal + kSlotGlobal;
       const T nxm = (T)std::sqrt(g[0]);
@@ -1075,6 +1098,23 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       }
     }
     phase_end(6);
+  }
+  if (fuse_rdual && iters_done >= 1) {
+    // dual residual of the last iteration (stand-alone pass)
+    for (int s = 0; s < p; ++s) {
+      SetT<T>& S = *sets[s];
+      LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
+             (const T*)S.y_old.p, c->rs, c->d_scal + s * kSlotPerSet + 3);
+    }
+    int rc = ctx_sync_scalars(c);
+    if (rc) return rc;
+    T tot = 0;
+    for (int s = 0; s < p; ++s) {
+      const T rd = (T)LG(log->rho, iters_done - 1, s, p_log) * (T)std::sqrt(c->h_scal[s * kSlotPerSet + 3]);
+      LG(log->r_dual, iters_done - 1, s, p_log) = (double)rd;
+      tot = tot + rd;
+    }
+    log->r_dual_total[iters_done - 1] = (double)tot;
   }
   SIPB_CUDA_CHECK(cudaEventRecord(ev1, c->stream));
 

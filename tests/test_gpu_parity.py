@@ -225,6 +225,10 @@ def check_parity(o, s, TF, iters_exact=True):
         assert np.allclose(ls.gamma, lo.gamma, rtol=50 * tol)
         assert np.allclose(ls.obj, lo.obj, rtol=50 * tol)
         assert np.allclose(ls.r_pri, lo.r_pri, rtol=1e-2, atol=1e-6 * np.abs(lo.r_pri).max())
+        assert np.allclose(ls.r_dual, lo.r_dual, rtol=1e-2, atol=1e-5 * np.abs(lo.r_dual).max())
+        assert np.allclose(ls.r_dual_total, lo.r_dual_total, rtol=1e-2, atol=1e-5 * np.abs(lo.r_dual_total).max())
+        assert np.allclose(ls.r_pri_total, lo.r_pri_total, rtol=1e-2, atol=1e-6 * np.abs(lo.r_pri_total).max())
+        assert np.allclose(ls.evol_x[1:], lo.evol_x[1:], rtol=1e-2, atol=1e-9)
         for a, b, yb in zip(l2, ll, yy):
             # multipliers of inactive sets are pure rounding noise: absolute floor relative to ||y||
             floor = 1e4 * np.finfo(TF).eps * np.linalg.norm(yb.astype(np.float64))
