@@ -106,3 +106,29 @@ class OracleAPI:
         self.proj = projectors
         self.parsdmm = parsdmm
         self.types = sip_types
+
+
+def build_minkowski(api, n=(32, 28), TF=np.float32, options=None):
+    """BASELINE config 5 (examples/GeneralizedMinkowski/example_2D_Minkowski_projection.jl:61-137):
+    m ≈ x1 + x2 with  c1: vector bounds (water layer) + D_z >= 0;  c2: bounds + TV-l1(0.15);  sum: bounds."""
+    d = (25.0, 6.0)
+    m = synthetic_model(n, TF)
+    cg = api.compgrid(d, n)
+    lo = np.full(n, 1500.0, dtype=TF)
+    hi = np.full(n, 4500.0, dtype=TF)
+    hi[:, : max(n[1] // 8, 1)] = 1500.0
+    mode = ("matrix", "")
+    c1 = [api.set_definitions("bounds", "identity", lo.ravel(order="F"), hi.ravel(order="F"), mode),
+          api.set_definitions("bounds", "D_z", 0.0, 1e6, mode)]
+    c2 = [api.set_definitions("bounds", "identity", -1500.0, 1500.0, mode),
+          api.set_definitions("l1", "TV", 0.0, 0.15 * tv_l1(n, d, TF, m), mode)]
+    cs = [api.set_definitions("bounds", "identity", 1500.0, 4500.0, mode)]
+    P1, T1, S1 = api.setup_constraints(c1, cg, TF)
+    P2, T2, S2 = api.setup_constraints(c2, cg, TF)
+    P3, T3, S3 = api.setup_constraints(cs, cg, TF)
+    opt = options if options is not None else api.PARSDMM_options()
+    opt.FL = TF
+    opt.Minkowski = True
+    opt.feas_tol, opt.obj_tol, opt.evol_rel_tol = 1e-3, 1e-3, 1e-5
+    TD_OP, set_Prop, AtA, l, y = api.PARSDMM_precompute_distribute_Minkowski(T1, T2, T3, S1, S2, S3, cg, opt)
+    return dict(cg=cg, opt=opt, P_sub=list(P1) + list(P2) + list(P3), TD_OP=TD_OP, set_Prop=set_Prop, AtA=AtA, l=l, y=y, m=m)
