@@ -26,4 +26,4 @@ are summation-order-unpinned in the reference (OpenBLAS); ``REDUCTION_MODE`` sel
 "f64acc" (accumulate in float64, round once to TF — the correctly rounded member of that family,
 default) or "native" (NumPy's own TF pairwise reduction).
 """
-from . import sip_types, operators, projectors, setup, parsdmm  # noqa: F401
+from . import sip_types, operators, projectors, setup, parsdmm, multilevel  # noqa: F401

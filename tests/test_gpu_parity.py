@@ -363,3 +363,35 @@ def test_parsdmm_config5_minkowski(sip, orc, TF):
         assert len(ls.obj) < 200        # stopped by the reference's rules, same iteration as the oracle
     tot = xs[: m.size] + xs[m.size:]
     assert tot.min() >= 1500 - 50 and tot.max() <= 4500 + 50
+
+
+@pytest.mark.parametrize("which", ["config4_bounds", "tv_l1"])
+def test_parsdmm_multilevel(sip, orc, which):
+    """PARSDMM_multi_level (config 4, examples/test_scaling_3D.jl:144-145): 3 levels, coarsening 2, warm
+    starts of x, l, y through nearest-neighbour resampling and carried rho."""
+    from oracle import multilevel as om
+    TF = np.float32
+    spec = pr.spec_config4((32, 24, 16), TF) if which == "config4_bounds" else pr.spec_config2((32, 24, 16), TF)
+    res = []
+    for api in (orc, sip):
+        cg = api.compgrid(tuple(spec["d"]), tuple(spec["n"]))
+        cons = [api.set_definitions(st, op, lo, hi, ("tensor", "")) for (st, op, lo, hi) in spec["sets"]]
+        opt = api.PARSDMM_options()
+        opt.FL = TF
+        opt.evol_rel_tol = 10 * np.finfo(TF).eps
+        opt.maxit = 40
+        if which == "config4_bounds":
+            opt.rho_ini = [1.0, 1000.0, 1000.0, 1000.0, 1.0]
+        if api is orc:
+            lv = om.setup_multi_level_PARSDMM(spec["m"], 3, 2, cg, cons, opt, orc.types)
+            res.append(om.PARSDMM_multi_level(spec["m"].copy(), *lv[:5], opt))
+        else:
+            lv = sip.setup_multi_level_PARSDMM(spec["m"], 3, 2, cg, cons, opt)
+            res.append(sip.PARSDMM_multi_level(spec["m"].copy(), *lv[:5], opt))
+        assert [float(v) for v in opt.rho_ini] == ([1.0, 1000.0, 1000.0, 1000.0, 1.0] if which == "config4_bounds" else [10.0])
+    (xo, lo, ll, yy), (xs, ls, l2, y2) = res
+    assert [len(g.obj) for g in lo.levels] == ls.timing["level_iterations"]
+    assert np.array_equal(ls.cg_it, lo.cg_it)
+    assert relerr(xs, xo) < TOL[TF]
+    for a, b in zip(y2, yy):
+        assert relerr(a, b) < 100 * TOL[TF]

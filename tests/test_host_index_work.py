@@ -182,3 +182,71 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
+
+
+# ---- multilevel index work ----------------------------------------------------------------------------
+def test_nearest_neighbour_tables_and_resampling(sip):
+    """Interpolations.jl BSpline(Constant()) at range(1, stop=n_src, length=n_dst): nearest neighbour with
+    half-way positions rounded up; product tables == oracle tables == the float formula away from ties."""
+    from oracle import multilevel as om
+    for ns, nd in [(400, 200), (200, 400), (199, 399), (399, 199), (200, 100), (99, 199), (201, 100), (7, 3), (3, 7), (5, 5)]:
+        a = om.nn_index(ns, nd)
+        assert np.array_equal(a, sip.multilevel._nearest_table(ns, nd))
+        pos = 1 + np.arange(nd) * (ns - 1) / (nd - 1)
+        tie = np.isclose(pos % 1.0, 0.5)
+        assert np.array_equal(a[~tie], np.round(pos[~tie]).astype(int) - 1)
+        assert np.array_equal(a[tie], np.floor(pos[tie] + 0.5).astype(int) - 1)
+        assert a[0] == 0 and a[-1] == ns - 1
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal(6 * 5 * 4).astype(np.float32)
+    for dst in ((12, 10, 8), (3, 3, 2), (6, 5, 4)):
+        assert np.array_equal(sip.resample_nn(v, (6, 5, 4), dst), om.resample(v, (6, 5, 4), dst))
+    assert np.array_equal(sip.resample_nn(v, (6, 5, 4), (6, 5, 4)), v)
+
+
+def test_multilevel_setup_matches_oracle(sip):
+    """setup_multi_level_PARSDMM + constraint2coarse: grids, spacings, rescaled constraints, operators."""
+    from oracle import multilevel as om
+    TF = np.float32
+    spec = pr.spec_config2((16, 12, 8), TF)
+    out = []
+    for api, setup in ((orc, lambda m, cg, cons, opt: om.setup_multi_level_PARSDMM(m, 3, 2, cg, cons, opt, orc.types)),
+                       (sip, lambda m, cg, cons, opt: sip.setup_multi_level_PARSDMM(m, 3, 2, cg, cons, opt))):
+        cg = api.compgrid(tuple(spec["d"]), tuple(spec["n"]))
+        cons = [api.set_definitions(st, op, lo, hi, ("tensor", "")) for (st, op, lo, hi) in spec["sets"]]
+        opt = api.PARSDMM_options()
+        out.append(setup(spec["m"], cg, cons, opt))
+    (TDo, AtAo, Po, SPo, CGo, Co), (TDs, AtAs, Ps, SPs, CGs, Cs) = out
+    assert [tuple(g.n) for g in CGo] == [tuple(g.n) for g in CGs] == [(16, 12, 8), (8, 6, 4), (4, 3, 2)]
+    for go, gs in zip(CGo, CGs):
+        assert np.allclose(go.d, gs.d, rtol=0, atol=0)
+    for co, cs in zip(Co, Cs):
+        assert co.set_type == cs.set_type and np.array_equal(np.asarray(co.max), np.asarray(cs.max))
+    assert Cs[1].max == np.float32(np.float32(spec["sets"][1][3]) / 8 / 8)      # l1 radius / cf^3 per level
+    for lev in range(3):
+        for Ao, As in zip(TDo[lev], TDs[lev]):
+            assert same_csc(As.tosparse(), Ao)
+        for Ro, Rs in zip(AtAo[lev], AtAs[lev]):
+            assert np.array_equal(Ro, Rs)
+
+
+def test_interpolate_y_l_matches_oracle(sip):
+    from oracle import multilevel as om
+    TF = np.float64
+    rng = np.random.default_rng(1)
+    for n, sets, mode in (((12, 10, 8), pr.spec_config3((12, 10, 8), TF)["sets"], "tensor"),
+                          ((14, 10), pr.spec_config1((14, 10), TF)["sets"], "matrix")):
+        res = []
+        for api, interp, setup in ((orc, om.interpolate_y_l, lambda m, cg, cons, opt: om.setup_multi_level_PARSDMM(m, 2, 2, cg, cons, opt, orc.types)),
+                                   (sip, sip.interpolate_y_l, lambda m, cg, cons, opt: sip.setup_multi_level_PARSDMM(m, 2, 2, cg, cons, opt))):
+            cg = api.compgrid((1.0,) * len(n), n)
+            cons = [api.set_definitions(st, op, lo, hi, (mode, "")) for (st, op, lo, hi) in sets]
+            TD, AtA, P, SP, CG, C = setup(np.zeros(int(np.prod(n)), dtype=TF), cg, cons, api.PARSDMM_options())
+            r = np.random.default_rng(5)
+            l = [r.standard_normal(A.shape[0]) for A in TD[1]]
+            y = [r.standard_normal(A.shape[0]) for A in TD[1]]
+            l, y = interp(l, y, SP, CG, len(n) == 3, 0)
+            assert [v.size for v in l] == [A.shape[0] for A in TD[0]]
+            res.append((l, y))
+        for a, b in zip(res[0][0] + res[0][1], res[1][0] + res[1][1]):
+            assert np.array_equal(a, b)
