@@ -150,6 +150,13 @@ int sipb_ctx_num_sms(sipb_ctx* ctx, int* out);
  *      (torch.distributed / MPI / Julia Distributed). ------------------------------------------ */
 int sipb_comm_unique_id(void* out128);
 int sipb_comm_init(sipb_ctx* ctx, int rank, int world, const void* uid128);
+int sipb_comm_info(sipb_ctx* ctx, int* rank, int* world);
+/* planes [k0,k1) of the slowest grid axis owned by `rank`; after sipb_comm_init with world > 1 every
+ * 3-D problem of the ctx is a slab problem: sipb_problem_create still takes the GLOBAL grid, while
+ * sipb_problem_set_ata takes the rank's rows [n1*n2*k0, n1*n2*k1) of each diagonal and sipb_solve takes /
+ * returns the rank's slab of m and x, and of every l[i], y[i] (per row block: the planes [k0,k1), for a
+ * D_z block the planes [k0, min(k1, n3-1))). */
+int sipb_slab_range(int64_t n_last, int rank, int world, int64_t* k0, int64_t* k1);
 
 /* ---- problem set-up: replaces the device-relevant part of PARSDMM_precompute_distribute.jl:6-77
  *      and the allocation / Q assembly of PARSDMM_initialize.jl:117-230 ---------------------- */

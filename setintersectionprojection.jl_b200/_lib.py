@@ -74,6 +74,8 @@ SYMBOLS = [
     ("sipb_ctx_num_sms", _I, [_VP, _PI]),
     ("sipb_comm_unique_id", _I, [_VP]),
     ("sipb_comm_init", _I, [_VP, _I, _I, _VP]),
+    ("sipb_comm_info", _I, [_VP, _PI, _PI]),
+    ("sipb_slab_range", _I, [_I64, _I, _I, _PI64, _PI64]),
     ("sipb_problem_create", _I, [_VP, _I, _I, _PI64, _PD, _I, _I, C.POINTER(_VP)]),
     ("sipb_problem_add_set", _I, [_VP, C.POINTER(SetDesc)]),
     ("sipb_problem_set_ata", _I, [_VP, _I, _VP, _I64, _PI64, _I]),

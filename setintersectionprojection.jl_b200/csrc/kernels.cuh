@@ -339,7 +339,7 @@ __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W
     const T* __restrict__ y = S.y;
     const T* __restrict__ l = S.l;
     T tv[W];
-    op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](unsigned row) -> T { return rho * y[row] + l[row]; }, tv);
+    op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](int row) -> T { return rho * y[row] + l[row]; }, tv);
 #pragma unroll
     for (int e = 0; e < W; ++e) acc[e] = acc[e] + tv[e];
     if (RDUAL) {
@@ -347,7 +347,7 @@ __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W
       // same gather: y_old still holds y^{k-1} until the next y/l update overwrites it
       const T* __restrict__ yo = S.y_old;
       T td[W];
-      op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](unsigned row) -> T { return y[row] - yo[row]; }, td);
+      op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](int row) -> T { return y[row] - yo[row]; }, td);
       double sq = 0.0;
 #pragma unroll
       for (int e = 0; e < W; ++e) sq += (double)td[e] * (double)td[e];
@@ -653,7 +653,7 @@ __global__ void __launch_bounds__(kThreads) k_op_adjoint(const __grid_constant__
     GridIdx g[1];
     g[0] = grid_decode(c, op.npts, op.n);
     T tv[1];
-    op_adjoint_n<T, 1>(op, op.mode, g, [=](unsigned row) -> T { return v[row]; }, tv);
+    op_adjoint_n<T, 1>(op, op.mode, g, [=](int row) -> T { return v[row]; }, tv);
     t[c] = tv[0];
   }
 }
@@ -707,7 +707,7 @@ __device__ __forceinline__ void rdual_cols(const OpDev& op, const T* __restrict_
   for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], 0xffffffffu, op.n); }
   // the dual residual runs over one N-block only: evaluate the operator as if it were un-blocked
   T t[W];
-  op_adjoint_n<T, W>(op, SIPB_BLOCK_PLAIN, g, [=](unsigned row) -> T { return y[row] - y_old[row]; }, t);
+  op_adjoint_n<T, W>(op, SIPB_BLOCK_PLAIN, g, [=](int row) -> T { return y[row] - y_old[row]; }, t);
 #pragma unroll
   for (int e = 0; e < W; ++e) d[0] += (double)t[e] * (double)t[e];
 }
@@ -786,6 +786,7 @@ __global__ void __launch_bounds__(kThreads) k_cds_axpy(i64 N, T* __restrict__ A,
 // reductions are deterministic).
 // =============================================================================================
 struct L1State {
+  double C, S;       // count and sum of the entries above theta (adjacent: one 2-double all-reduce with slabs)
   double theta;      // current iterate
   double tau;
   double S1;         // sum |v|
@@ -795,38 +796,58 @@ struct L1State {
   int passes;
 };
 
+// Newton step theta <- (S - tau)/C with the restart / fix-point logic
+__device__ __forceinline__ void l1_newton_step(L1State* st, double C, double S) {
+  const double theta = st->theta;
+  st->passes += 1;
+  if (C == 0.0) {            // theta at/above max|v|: restart from the left end
+    st->theta = 0.0;
+    st->on_left = 1;
+    if (theta == 0.0) st->done = 1;   // all-zero vector
+  } else {
+    double tn = (S - st->tau) / C;
+    if (tn < 0.0) tn = 0.0;
+    if (st->on_left && tn <= theta) {
+      st->done = 1;          // fix point: theta is the exact root
+    } else {
+      st->theta = tn;
+      st->on_left = 1;
+    }
+  }
+  if (st->passes >= 200) st->done = 1;
+}
+
+// fused != 0: the last block performs the Newton step (single GPU); otherwise it only publishes the
+// rank-local (C, S) and k_l1_step runs after the all-reduce.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict__ v, RedScratch rs, L1State* st) {
+__global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict__ v, RedScratch rs, L1State* st,
+                                                      int fused) {
   if (st->done) return;
   const double theta = st->theta;
   double d[2] = {0.0, 0.0};
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
-    const double a = (double)t_abs<T>(v[r]);
-    if (a > theta) {
-      d[0] += 1.0;
-      d[1] += a;
+  constexpr int VW = Vec<T>::W;
+  const i64 nvec = M / VW;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+    T t[VW];
+    vload<T>(v + iv * VW, t);
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      const double a = (double)t_abs<T>(t[e]);
+      if (a > theta) { d[0] += 1.0; d[1] += a; }
     }
+  }
+  for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const double a = (double)t_abs<T>(v[r]);
+    if (a > theta) { d[0] += 1.0; d[1] += a; }
   }
   if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
-    const double C = d[0], S = d[1];
-    st->passes += 1;
-    if (C == 0.0) {            // theta at/above max|v|: restart from the left end
-      st->theta = 0.0;
-      st->on_left = 1;
-      // f(0) = S1 - tau > 0 is known; next pass from theta = 0
-      if (theta == 0.0) st->done = 1;   // all-zero vector
-    } else {
-      double tn = (S - st->tau) / C;
-      if (tn < 0.0) tn = 0.0;
-      if (st->on_left && tn <= theta) {
-        st->done = 1;          // fix point: theta is the exact root
-      } else {
-        st->theta = tn;
-        st->on_left = 1;
-      }
-    }
-    if (st->passes >= 200) st->done = 1;
+    if (fused) l1_newton_step(st, d[0], d[1]);
+    else { st->C = d[0]; st->S = d[1]; }
   }
+}
+__global__ void k_l1_step(L1State* st) {
+  if (st->done) return;
+  l1_newton_step(st, st->C, st->S);
 }
 
 // =============================================================================================
@@ -841,43 +862,53 @@ struct SelState {
   int key_bits;
 };
 
+// choose the digit bucket that contains the k_rem-th largest key among the current prefix bucket
+__device__ __forceinline__ void radix_pick(SelState* st) {
+  const int shift = st->shift;
+  if (shift < 0) return;
+  unsigned long long k = st->k_rem, cum = 0;
+  int bin = 0;
+  for (int b = 255; b >= 0; --b) {
+    const unsigned long long c = st->hist[b];
+    if (cum + c >= k) {
+      bin = b;
+      break;
+    }
+    cum += c;
+  }
+  st->k_rem = k - cum;
+  st->count_eq = st->hist[bin];
+  st->prefix = (st->prefix << 8) | (unsigned long long)bin;
+  st->shift = shift - 8;
+  for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
+}
+
+// fused != 0: the last block also picks the digit (single GPU); with slabs the histogram is all-reduced
+// first and k_radix_pick runs afterwards.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_radix_hist(i64 M, const T* __restrict__ v, SelState* st,
-                                                         unsigned int* counter) {
+                                                         unsigned int* counter, int fused) {
   __shared__ unsigned int sh[256];
   const int shift = st->shift;
   if (shift < 0) return;
   const unsigned long long prefix = st->prefix;
   const int hi_shift = shift + 8;
+  const bool all_match = hi_shift >= st->key_bits;
   for (int t = threadIdx.x; t < 256; t += blockDim.x) sh[t] = 0u;
   __syncthreads();
   for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
     const unsigned long long key = mag_key<T>(v[r]);
-    const bool match = (hi_shift >= st->key_bits) ? true : ((key >> hi_shift) == prefix);
+    const bool match = all_match ? true : ((key >> hi_shift) == prefix);
     if (match) atomicAdd(&sh[(unsigned)((key >> shift) & 0xffull)], 1u);
   }
   __syncthreads();
   for (int t = threadIdx.x; t < 256; t += blockDim.x)
     if (sh[t]) atomicAdd(&st->hist[t], (unsigned long long)sh[t]);
-  if (last_block_ticket(counter) && threadIdx.x == 0) {
-    // pick the digit bucket that contains the k_rem-th largest key
-    unsigned long long k = st->k_rem, cum = 0;
-    int bin = 0;
-    for (int b = 255; b >= 0; --b) {
-      const unsigned long long c = st->hist[b];
-      if (cum + c >= k) {
-        bin = b;
-        break;
-      }
-      cum += c;
-    }
-    st->k_rem = k - cum;
-    st->count_eq = st->hist[bin];
-    st->prefix = (prefix << 8) | (unsigned long long)bin;
-    st->shift = shift - 8;
-    for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
+  if (fused) {
+    if (last_block_ticket(counter) && threadIdx.x == 0) radix_pick(st);
   }
 }
+__global__ void k_radix_pick(SelState* st) { radix_pick(st); }
 
 // fill helper
 template <typename T>

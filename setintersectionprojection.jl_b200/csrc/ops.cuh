@@ -25,6 +25,8 @@ struct OpDev {
   int axis[3];       // storage axis differenced by each block, in row order
   unsigned n[3];     // model grid (n[2] == 1 in 2-D)
   unsigned rs[4];    // first row of each block (32-bit mirror of row_start)
+  unsigned kofs;     // slabs: global index of the first owned plane of the slowest axis (0 otherwise)
+  unsigned nlast;    // slabs: GLOBAL extent of the slowest axis (== n[2] otherwise)
   i64 npts;          // n0*n1*n2
   i64 rows;          // rows of the operator
   i64 cols;          // npts, or 2*npts for Minkowski block modes
@@ -214,6 +216,7 @@ __device__ __forceinline__ bool op_touches_half(int mode, bool upper) {
 }
 
 // ---- adjoint: t[e] = (A' v)[g[e]] for W grid points; val(row) supplies v[row] ---------------------
+// `val` takes a SIGNED row index (slab halo rows are addressed with negative indices).
 template <typename T, int W, typename F>
 __device__ __forceinline__ void op_adjoint_n(const OpDev& op, int mode, const GridIdx (&g)[W], F val, T (&t)[W]) {
 #pragma unroll
@@ -267,13 +270,16 @@ __device__ __forceinline__ void op_adjoint_n(const OpDev& op, int mode, const Gr
             if (g[e].j < na - 1u) t[e] = t[e] + nih * val(q);
           }
         } else {
-          const unsigned na = op.n[2], st = op.n[0] * op.n[1];
+          // slowest axis: with slabs the row of plane k-1 of the first owned plane lives in the halo plane
+          // stored in front of the block (negative index), boundary tests use GLOBAL plane numbers
+          const unsigned na = op.nlast, st = op.n[0] * op.n[1];
 #pragma unroll
           for (int e = 0; e < W; ++e) {
             if (!op_touches_half(mode, g[e].upper)) continue;
-            const unsigned q = base + g[e].cc;
-            if (g[e].k >= 1u) t[e] = t[e] + ih * val(q - st);
-            if (g[e].k < na - 1u) t[e] = t[e] + nih * val(q);
+            const int q = (int)(base + g[e].cc);
+            const unsigned kg = g[e].k + op.kofs;
+            if (kg >= 1u) t[e] = t[e] + ih * val(q - (int)st);
+            if (kg < na - 1u) t[e] = t[e] + nih * val(q);
           }
         }
       }

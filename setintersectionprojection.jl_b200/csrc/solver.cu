@@ -15,6 +15,9 @@
 #include <memory>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
+
 #include "kernels.cuh"
 
 namespace sipb {
@@ -28,6 +31,52 @@ void set_error(const std::string& msg) { g_err = msg; }
       ::sipb::set_error(msg);           \
       return (code);                    \
     }                                   \
+  } while (0)
+
+// NCCL is bound lazily with dlopen/dlsym instead of a link-time dependency: a process that has already
+// imported torch keeps using torch's bundled libnccl (same soname), and single-GPU users never load it.
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclSend) Send = nullptr;
+  decltype(&ncclRecv) Recv = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+#define SIPB_NCCL_SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(h, "nccl" #name))
+      SIPB_NCCL_SYM(GetUniqueId); SIPB_NCCL_SYM(CommInitRank); SIPB_NCCL_SYM(CommDestroy); SIPB_NCCL_SYM(AllReduce);
+      SIPB_NCCL_SYM(AllGather); SIPB_NCCL_SYM(Send); SIPB_NCCL_SYM(Recv); SIPB_NCCL_SYM(GroupStart);
+      SIPB_NCCL_SYM(GroupEnd); SIPB_NCCL_SYM(GetErrorString);
+#undef SIPB_NCCL_SYM
+      api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.AllGather && api.Send &&
+               api.Recv && api.GroupStart && api.GroupEnd && api.GetErrorString;
+    }
+  }
+  return &api;
+}
+#define NCCL(fn) (nccl_api()->fn)
+
+#define SIPB_NCCL_CHECK(expr)                                                              \
+  do {                                                                                     \
+    ncclResult_t _r = (expr);                                                              \
+    if (_r != ncclSuccess) {                                                               \
+      ::sipb::set_error(std::string(#expr) + ": " + NCCL(GetErrorString)(_r) + " (" + __FILE__ + \
+                        ":" + std::to_string(__LINE__) + ")");                            \
+      return SIPB_E_NCCL;                                                                  \
+    }                                                                                      \
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -47,22 +96,30 @@ static const char* kClassNames[SIPB_N_KERNEL_CLASSES] = {
 
 template <typename T>
 struct DevBuf {
-  T* p = nullptr;
+  T* p = nullptr;       // first owned element (256-byte aligned)
+  T* base = nullptr;    // allocation start (p - front)
   size_t n = 0;
   DevBuf() {}
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
+    if (base) cudaFree(base);
+    p = base = nullptr;
     n = 0;
   }
-  cudaError_t alloc(size_t count) {
+  // `front` / `back` extra elements before / after the owned range (halo planes of a slab)
+  cudaError_t alloc(size_t count, size_t front = 0, size_t back = 0) {
     release();
     n = count;
-    if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    if (count + front + back == 0) return cudaSuccess;
+    const size_t align = 256 / sizeof(T);
+    const size_t fpad = (front + align - 1) / align * align;
+    cudaError_t e = cudaMalloc(&base, (fpad + count + back) * sizeof(T));
+    if (e != cudaSuccess) { base = nullptr; return e; }
+    p = base + fpad;
+    if (front + back) e = cudaMemset(base, 0, (fpad + count + back) * sizeof(T));
+    return e;
   }
 };
 
@@ -88,6 +145,23 @@ struct sipb_ctx {
   unsigned long long* d_tie_counts = nullptr;
   unsigned int* d_counter2 = nullptr;
   int rank = 0, world = 1;
+  ncclComm_t comm = nullptr;
+  unsigned long long* d_gather = nullptr;   // [world][4] tie counts (all-gather target)
+  unsigned long long* d_gather_local = nullptr;   // [4] this rank's tie totals per row block
+  int64_t nccl_calls = 0;
+  // sum-all-reduce of `count` doubles in place on the stream (no-op on a single GPU)
+  int allreduce(double* d, size_t count) {
+    if (world == 1) return SIPB_OK;
+    nccl_calls++;
+    SIPB_NCCL_CHECK(NCCL(AllReduce)(d, d, count, ncclDouble, ncclSum, comm, stream));
+    return SIPB_OK;
+  }
+  int allreduce_u64(unsigned long long* d, size_t count) {
+    if (world == 1) return SIPB_OK;
+    nccl_calls++;
+    SIPB_NCCL_CHECK(NCCL(AllReduce)(d, d, count, ncclUint64, ncclSum, comm, stream));
+    return SIPB_OK;
+  }
   // launch accounting
   bool profile = false;
   int64_t launches[SIPB_N_KERNEL_CLASSES];
@@ -150,8 +224,14 @@ constexpr int kSlotGlobal = kMaxSets * kSlotPerSet;   // 256
     (ctx)->post_launch();                                         \
   } while (0)
 
+// Copies the scalar slots to the host.  With slabs the slots hold per-rank partial sums: one batched
+// Float64 all-reduce makes them global first; the slots are then cleared so that stale entries never
+// accumulate across iterations.
 static int ctx_sync_scalars(sipb_ctx* c) {
+  int rc = c->allreduce(c->d_scal, kScalSlots);
+  if (rc) return rc;
   SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, kScalSlots * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (c->world > 1) SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_scal, 0, kScalSlots * sizeof(double), c->stream));
   SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   return SIPB_OK;
 }
@@ -251,15 +331,35 @@ __global__ void __launch_bounds__(kThreads) k_tie_count_p(i64 M, const T* __rest
     counts[blockIdx.x] = t;
   }
 }
+// totals[b] = number of threshold ties in row block b of this rank (slabs)
+__global__ void k_tie_totals(const unsigned long long* counts, int nblk, int g, int stride, unsigned long long* totals) {
+  for (int b = 0; b < 4; ++b) {       // launched with a single thread
+    unsigned long long t = 0;
+    if (b < nblk)
+      for (int i = 0; i < g; ++i) t += counts[b * stride + i];
+    totals[b] = t;
+  }
+}
+
+// `gather` (slabs): all-gathered totals [world][4]; the global index order of the reference's vector is
+// row-block major, planes (= ranks) ascending inside a block, so the ties that precede this rank's
+// block `blk` are all ties of earlier blocks plus those of lower ranks in the same block.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_tie_zero_p(i64 M, T* __restrict__ v, const ProjParams<T>* pp, i64 chunk,
-                                                         const unsigned long long* __restrict__ counts) {
+                                                         const unsigned long long* __restrict__ counts,
+                                                         const unsigned long long* __restrict__ gather, int rank,
+                                                         int world, int blk) {
   if (!pp->need_ties) return;
   const unsigned long long key = pp->key_thr, quota = pp->quota;
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_warp[32];
   if (threadIdx.x == 0) {
     unsigned long long b = 0;
+    if (gather) {
+      for (int bb = 0; bb < blk; ++bb)
+        for (int r = 0; r < world; ++r) b += gather[r * 4 + bb];
+      for (int r = 0; r < rank; ++r) b += gather[r * 4 + blk];
+    }
     for (unsigned i = 0; i < blockIdx.x; ++i) b += counts[i];
     s_base = b;
   }
@@ -355,17 +455,35 @@ static int64_t op_rows_host(int ndim, const int64_t* n, int op_kind) {
   }
 }
 
+// Slab geometry of a 3-D problem partitioned along its slowest axis (one process per GPU).
+struct SlabGeom {
+  bool on = false;
+  i64 k0 = 0, k1 = 0;     // owned planes [k0,k1) of the slowest axis
+  i64 nlast = 0;          // global extent of the slowest axis
+  i64 plane = 0;          // n0*n1
+  bool has_lo = false, has_hi = false;
+  i64 nloc() const { return k1 - k0; }
+  i64 nz_rows() const { return std::min(k1, nlast - 1) - k0; }   // owned row planes of a D_z block
+};
+
+// `n` is the GLOBAL grid; with an active slab the descriptor addresses the rank's local planes.
 template <typename T>
-static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int block_mode, OpDev* out) {
+static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int block_mode, OpDev* out,
+                   const SlabGeom* sg = nullptr) {
   SIPB_REQUIRE(ndim == 2 || ndim == 3, SIPB_E_INVALID, "ndim must be 2 or 3");
+  for (int a = 0; a < ndim; ++a)
+    SIPB_REQUIRE(n[a] >= 2, SIPB_E_INVALID, "every grid dimension must be at least 2");
+  const bool slab = sg && sg->on;
   OpDev op;
   memset(&op, 0, sizeof(op));
   op.kind = op_kind;
   op.mode = block_mode;
   op.n[0] = (unsigned)n[0];
   op.n[1] = (unsigned)n[1];
-  op.n[2] = (ndim == 3) ? (unsigned)n[2] : 1u;
-  op.npts = (i64)n[0] * n[1] * ((ndim == 3) ? n[2] : 1);
+  op.n[2] = (ndim == 3) ? (unsigned)(slab ? sg->nloc() : n[2]) : 1u;
+  op.kofs = slab ? (unsigned)sg->k0 : 0u;
+  op.nlast = (ndim == 3) ? (unsigned)n[2] : 1u;
+  op.npts = (i64)op.n[0] * op.n[1] * op.n[2];
   op.cols = (block_mode == SIPB_BLOCK_PLAIN) ? op.npts : 2 * op.npts;
   for (int a = 0; a < 3; ++a) {
     // (-1 or 1) ./ h evaluated in TF: get_discrete_Grad.jl:22-23,58-60 with h = TF(comp_grid.d[a])
@@ -373,15 +491,16 @@ static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int
     op.ih[a] = (double)((T)1 / hh);
   }
   op.a_xz = (double)((T)op.ih[1] * (T)op.ih[0]);
-  const int64_t rows = op_rows_host(ndim, n, op_kind);
-  SIPB_REQUIRE(rows >= 0, SIPB_E_UNSUPPORTED, "operator kind not available for this grid dimensionality");
-  SIPB_REQUIRE(rows < (int64_t)4294967295ll && op.npts < (int64_t)4294967295ll, SIPB_E_UNSUPPORTED,
-               "operator with more than 2^32-1 rows");
-  op.rows = rows;
+  SIPB_REQUIRE(op_rows_host(ndim, n, op_kind) >= 0, SIPB_E_UNSUPPORTED,
+               "operator kind not available for this grid dimensionality");
   const int last_axis = ndim - 1;
   auto blk_rows = [&](int a) -> i64 {
     i64 r = 1;
-    for (int q = 0; q < 3; ++q) r *= (i64)(q == a ? op.n[q] - 1 : op.n[q]);
+    for (int q = 0; q < 3; ++q) {
+      i64 ext = op.n[q];
+      if (q == a) ext = (slab && a == 2) ? sg->nz_rows() : ext - 1;
+      r *= ext;
+    }
     return r;
   };
   switch (op_kind) {
@@ -397,16 +516,24 @@ static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int
     default: SIPB_REQUIRE(false, SIPB_E_UNSUPPORTED, "unknown operator kind");
   }
   op.row_start[0] = 0;
-  if (op_kind != SIPB_OP_IDENTITY && op_kind != SIPB_OP_DXZ) {
+  if (op_kind == SIPB_OP_IDENTITY) op.row_start[1] = op.npts;
+  else if (op_kind == SIPB_OP_DXZ) op.row_start[1] = (i64)(op.n[0] - 1) * (op.n[1] - 1);
+  else
     for (int b = 0; b < op.nblk; ++b) op.row_start[b + 1] = op.row_start[b] + blk_rows(op.axis[b]);
-  } else {
-    op.row_start[1] = rows;
-  }
-  for (int a = 0; a < ndim; ++a)
-    SIPB_REQUIRE(n[a] >= 2, SIPB_E_INVALID, "every grid dimension must be at least 2");
+  op.rows = op.row_start[op.nblk];
+  for (int b = op.nblk + 1; b < 4; ++b) op.row_start[b] = op.rows;
+  SIPB_REQUIRE(op.rows < (int64_t)2147483647ll && op.cols < (int64_t)2147483647ll, SIPB_E_UNSUPPORTED,
+               "operator with more than 2^31-1 rows or columns per GPU");
   for (int b = 0; b < 4; ++b) op.rs[b] = (unsigned)op.row_start[b];
   *out = op;
   return SIPB_OK;
+}
+
+static inline bool op_has_slow_axis_block(const OpDev& op) {
+  if (op.kind == SIPB_OP_IDENTITY || op.kind == SIPB_OP_DXZ) return false;
+  for (int b = 0; b < op.nblk; ++b)
+    if (op.axis[b] == 2) return true;
+  return false;
 }
 
 // =============================================================================================
@@ -433,7 +560,8 @@ template <typename T>
 struct SetT {
   sipb_set_desc desc;
   OpDev op;
-  i64 M = 0;
+  i64 M = 0;       // rows held by this rank
+  i64 Mglob = 0;   // rows of the global operator
   DevBuf<T> y, l, y_old, s, s0, y0, l0, lhat0;   // s only for reduction-type projectors
   DevBuf<T> lo_vec, hi_vec;
   DevBuf<T> ata;              // [nd][ld]
@@ -443,6 +571,7 @@ struct SetT {
   bool has_ata = false;
   DevBuf<ProjParams<T>> pp_y, pp_f;   // dynamic projector parameters: y-update / feasibility
   DevBuf<double> warm;        // [2] warm-start thresholds (y-update, feasibility)
+  bool z_halo = false;        // slabs: y, l, y_old have a halo plane in front (D_z block)
 };
 
 template <typename T>
@@ -458,13 +587,73 @@ struct Problem : sipb_problem {
   DevBuf<T> Q, x, x_old, rhs, r, pvec, Ap, m, tmp;
   i64 maxM = 0;
   bool m_resident = false;
+  SlabGeom sg;                // active when the ctx has a communicator with world > 1
+  i64 Nglob;                  // global number of unknowns (== N on a single GPU)
+  int create_error = SIPB_OK;
 
   Problem(sipb_ctx* c, int dt, int nd_, const int64_t* n_, const double* h_, bool mk, bool fo) {
     ctx = c; dtype = dt; ndim = nd_; minkowski = mk; feas_only = fo;
     for (int a = 0; a < 3; ++a) { n[a] = (a < nd_) ? n_[a] : 1; h[a] = (a < nd_) ? h_[a] : 1.0; }
     npts = n[0] * n[1] * n[2];
+    Nglob = mk ? 2 * npts : npts;
+    if (c->world > 1) {
+      // slabs along the slowest axis of a 3-D grid; Minkowski sets couple the halves through the
+      // offsets +-N and stay on one GPU
+      if (nd_ != 3 || mk) {
+        create_error = SIPB_E_UNSUPPORTED;
+      } else {
+        sg.on = true;
+        sg.nlast = n[2];
+        sg.plane = n[0] * n[1];
+        sg.k0 = n[2] * c->rank / c->world;
+        sg.k1 = n[2] * (c->rank + 1) / c->world;
+        sg.has_lo = c->rank > 0;
+        sg.has_hi = c->rank < c->world - 1;
+        if (sg.nloc() < 1) create_error = SIPB_E_INVALID;
+        npts = sg.plane * sg.nloc();
+      }
+    }
     N = mk ? 2 * npts : npts;
     ld = (N + 63) / 64 * 64;
+  }
+
+  ncclDataType_t nccl_type() const { return sizeof(T) == 4 ? ncclFloat : ncclDouble; }
+
+  // Halo exchange of one plane per direction for a vector whose owned part starts at `v` and spans
+  // `planes` planes.  up: my last plane -> lower halo (v - plane) of rank+1;
+  // down: my first plane -> upper halo (v + planes*plane) of rank-1.  Planes are contiguous: no packing.
+  int exchange(T* v, i64 planes, bool up, bool down) {
+    if (!sg.on) return SIPB_OK;
+    sipb_ctx* c = ctx;
+    const size_t cnt = (size_t)sg.plane;
+    c->nccl_calls++;
+    SIPB_NCCL_CHECK(NCCL(GroupStart)());
+    if (up) {
+      if (sg.has_hi) SIPB_NCCL_CHECK(NCCL(Send)(v + (planes - 1) * sg.plane, cnt, nccl_type(), c->rank + 1, c->comm, c->stream));
+      if (sg.has_lo) SIPB_NCCL_CHECK(NCCL(Recv)(v - sg.plane, cnt, nccl_type(), c->rank - 1, c->comm, c->stream));
+    }
+    if (down) {
+      if (sg.has_lo) SIPB_NCCL_CHECK(NCCL(Send)(v, cnt, nccl_type(), c->rank - 1, c->comm, c->stream));
+      if (sg.has_hi) SIPB_NCCL_CHECK(NCCL(Recv)(v + planes * sg.plane, cnt, nccl_type(), c->rank + 1, c->comm, c->stream));
+    }
+    SIPB_NCCL_CHECK(NCCL(GroupEnd)());
+    return SIPB_OK;
+  }
+  // lower halos of y and l for every set with a D_z block (needed by the rhs / dual-residual gathers);
+  // the y_old halo is the previous y halo (local copy, no transfer)
+  int exchange_yl_halos(bool shift_y_old) {
+    if (!sg.on) return SIPB_OK;
+    for (auto& S : sets) {
+      if (!S->z_halo) continue;
+      if (shift_y_old && sg.has_lo)
+        SIPB_CUDA_CHECK(cudaMemcpyAsync(S->y_old.p - sg.plane, S->y.p - sg.plane, sg.plane * sizeof(T),
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+      int rc = exchange(S->y.p, sg.nz_rows(), true, false);
+      if (rc) return rc;
+      rc = exchange(S->l.p, sg.nz_rows(), true, false);
+      if (rc) return rc;
+    }
+    return SIPB_OK;
   }
 
   int add_set(const sipb_set_desc* d) override {
@@ -478,12 +667,16 @@ struct Problem : sipb_problem {
     if (d->set_kind == SIPB_SET_L1) SIPB_REQUIRE(d->max > 0.0, SIPB_E_INVALID, "Radius of L1 ball is negative");
     auto S = std::make_unique<SetT<T>>();
     S->desc = *d;
-    int rc = make_op<T>(ndim, n, h, d->op_kind, d->block_mode, &S->op);
+    int rc = make_op<T>(ndim, n, h, d->op_kind, d->block_mode, &S->op, &sg);
     if (rc) return rc;
     S->M = S->op.rows;
+    S->Mglob = op_rows_host(ndim, n, d->op_kind);
+    S->z_halo = sg.on && op_has_slow_axis_block(S->op);
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M); };
-    A(S->y); A(S->l); A(S->y_old); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
+    // slabs: y, l, y_old of a set with a D_z block carry the neighbour's last row plane in front
+    auto AH = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M, S->z_halo ? (size_t)sg.plane : 0, 0); };
+    AH(S->y); AH(S->l); AH(S->y_old); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
     if (!proj_is_elementwise(d->set_kind)) A(S->s);
     if (e == cudaSuccess) e = S->pp_y.alloc(1);
     if (e == cudaSuccess) e = S->pp_f.alloc(1);
@@ -555,10 +748,14 @@ struct Problem : sipb_problem {
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf<T>& b, size_t cnt) { if (e == cudaSuccess) e = b.alloc(cnt); };
     A(Q, (size_t)ld * q_offs.size());
-    const size_t halo = 0;
-    A(x, (size_t)N + halo); A(x_old, (size_t)N); A(rhs, (size_t)N); A(r, (size_t)N); A(pvec, (size_t)N);
-    A(Ap, (size_t)N); A(m, (size_t)N); A(tmp, (size_t)std::max<i64>(maxM, N));
+    const size_t halo = sg.on ? (size_t)sg.plane : 0;      // one plane on each side (max |offset| of Q)
+    auto AH = [&](DevBuf<T>& b, size_t cnt) { if (e == cudaSuccess) e = b.alloc(cnt, halo, halo); };
+    AH(x, (size_t)N); A(x_old, (size_t)N); A(rhs, (size_t)N); A(r, (size_t)N); AH(pvec, (size_t)N);
+    A(Ap, (size_t)N); AH(m, (size_t)N); A(tmp, (size_t)std::max<i64>(maxM, N));
     SIPB_CUDA_CHECK(e);
+    if (sg.on)
+      for (int64_t o : q_offs)
+        SIPB_REQUIRE(std::llabs((long long)o) <= sg.plane, SIPB_E_UNSUPPORTED, "CDS offset wider than one halo plane");
     finalized = true;
     return SIPB_OK;
   }
@@ -574,7 +771,7 @@ struct Problem : sipb_problem {
     SpmvArgs<T> a;
     a.R = Q.p; a.ld = ld; a.nd = (int)q_offs.size();
     for (int j = 0; j < a.nd; ++j) a.off[j] = q_offs[j];
-    a.N = N; a.row0 = 0; a.Nglob = N; a.x = xin; a.y = yout;
+    a.N = N; a.row0 = sg.on ? sg.plane * sg.k0 : 0; a.Nglob = Nglob; a.x = xin; a.y = yout;
     return a;
   }
 
@@ -598,14 +795,25 @@ struct Problem : sipb_problem {
   int projector_params(SetT<T>& S, T* v, int stat_slot, ProjParams<T>* pp, double* warm, bool allow_tie_zero) {
     sipb_ctx* c = ctx;
     const int kind = S.desc.set_kind;
-    const i64 M = S.M;
+    const i64 M = S.M;               // rank-local rows
+    const i64 Mg = S.Mglob;          // rows of the global operator
+    const int fused = sg.on ? 0 : 1; // single GPU: the reducing kernel also performs the scalar step
     double* stats = c->d_scal + stat_slot;
+    int rc = c->allreduce(stats, 3);
+    if (rc) return rc;
     if (kind == SIPB_SET_L1) {
-      LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)M, warm, c->d_l1, pp);
+      LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)Mg, warm, c->d_l1, pp);
       int launched = 0;
       for (;;) {
-        const int batch = (launched == 0) ? 6 : 8;
-        for (int b = 0; b < batch; ++b) LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for(M), M, v, c->rs, c->d_l1);
+        const int batch = (launched == 0) ? (sg.on ? 4 : 6) : 8;
+        for (int b = 0; b < batch; ++b) {
+          LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for((M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused);
+          if (!fused) {
+            rc = c->allreduce(&c->d_l1->C, 2);
+            if (rc) return rc;
+            LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1);
+          }
+        }
         launched += batch;
         SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_l1, c->d_l1, sizeof(L1State), cudaMemcpyDeviceToHost, c->stream));
         SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -613,18 +821,45 @@ struct Problem : sipb_problem {
       }
       LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
     } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {
-      LAUNCH1(c, KC_PARAMS, k_l2_params<T>, stats, kind, S.desc.min, S.desc.max, (double)M, pp);
+      LAUNCH1(c, KC_PARAMS, k_l2_params<T>, stats, kind, S.desc.min, S.desc.max, (double)Mg, pp);
     } else if (kind == SIPB_SET_CARDINALITY) {
-      LAUNCH1(c, KC_PARAMS, k_sel_begin<T>, (long long)S.desc.k, (long long)M, c->d_sel, pp);
+      LAUNCH1(c, KC_PARAMS, k_sel_begin<T>, (long long)S.desc.k, (long long)Mg, c->d_sel, pp);
       const int npass = (int)sizeof(T);
-      for (int q = 0; q < npass; ++q)
-        LAUNCH(c, KC_RADIX_HIST, k_radix_hist<T>, c->grid_for(M), M, v, c->d_sel, c->d_counter2);
+      for (int q = 0; q < npass; ++q) {
+        LAUNCH(c, KC_RADIX_HIST, k_radix_hist<T>, c->grid_for(M), M, v, c->d_sel, c->d_counter2, fused);
+        if (!fused) {
+          rc = c->allreduce_u64(c->d_sel->hist, 256);
+          if (rc) return rc;
+          LAUNCH1(c, KC_PARAMS, k_radix_pick, c->d_sel);
+        }
+      }
       LAUNCH1(c, KC_PARAMS, k_sel_end<T>, c->d_sel, pp);
       if (allow_tie_zero) {
-        const int g = c->max_grid();
-        const i64 chunk = ((M + g - 1) / g + kThreads - 1) / kThreads * kThreads;
-        LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, M, v, pp, chunk, c->d_tie_counts);
-        LAUNCH(c, KC_TIES, k_tie_zero_p<T>, g, M, v, pp, chunk, c->d_tie_counts);
+        if (!sg.on) {
+          const int g = c->max_grid();
+          const i64 chunk = ((M + g - 1) / g + kThreads - 1) / kThreads * kThreads;
+          LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, M, v, pp, chunk, c->d_tie_counts);
+          LAUNCH(c, KC_TIES, k_tie_zero_p<T>, g, M, v, pp, chunk, c->d_tie_counts, (const unsigned long long*)nullptr,
+                 0, 1, 0);
+        } else {
+          // index-ordered ties across slabs: per row block tie totals are all-gathered (4 x world counters)
+          const int g = c->max_grid() / 4;
+          const int nb = S.op.kind == SIPB_OP_IDENTITY ? 1 : S.op.nblk;
+          for (int b = 0; b < nb; ++b) {
+            const i64 Mb = S.op.row_start[b + 1] - S.op.row_start[b];
+            const i64 chunk = ((std::max<i64>(Mb, 1) + g - 1) / g + kThreads - 1) / kThreads * kThreads;
+            LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, Mb, v + S.op.row_start[b], pp, chunk, c->d_tie_counts + (size_t)b * g);
+          }
+          LAUNCH1(c, KC_TIES, k_tie_totals, c->d_tie_counts, nb, g, g, c->d_gather_local);
+          c->nccl_calls++;
+          SIPB_NCCL_CHECK(NCCL(AllGather)(c->d_gather_local, c->d_gather, 4, ncclUint64, c->comm, c->stream));
+          for (int b = 0; b < nb; ++b) {
+            const i64 Mb = S.op.row_start[b + 1] - S.op.row_start[b];
+            const i64 chunk = ((std::max<i64>(Mb, 1) + g - 1) / g + kThreads - 1) / kThreads * kThreads;
+            LAUNCH(c, KC_TIES, k_tie_zero_p<T>, g, Mb, v + S.op.row_start[b], pp, chunk, c->d_tie_counts + (size_t)b * g,
+                   (const unsigned long long*)c->d_gather, c->rank, c->world, b);
+          }
+        }
       }
     }
     return SIPB_OK;
@@ -657,10 +892,13 @@ struct Problem : sipb_problem {
   }
 
   // device CG on Q (cg.jl:44-128).  parsdmm_it > 0 selects the argmin_x tolerance rule.
+  // Slabs: the halos of `xv` must be valid on entry; they are valid again on exit.  Every rank launches
+  // the same sequence (the control scalars are all-reduced, hence identical), so the NCCL calls match.
   int run_cg(const T* b, T* xv, T* x_old_out, int parsdmm_it, double tol, int max_iter, int predicted,
              int* iters, double* relres, int* flag) {
     sipb_ctx* c = ctx;
     CgState* h = c->h_cg;
+    int rc;
     // only the control fields are (re)written; tol_prev persists on the device between calls
     h->maxit = max_iter;
     h->parsdmm_it = parsdmm_it;
@@ -671,16 +909,18 @@ struct Problem : sipb_problem {
       SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol, &h->tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
     LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g, spmv_args(xv, nullptr), b, r.p, pvec.p, x_old_out, c->rs, c->d_cg);
+    if ((rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
     LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg);
     int launched = 0;
     int batch = std::max(1, predicted);
     for (;;) {
-      if (launched > 0 || batch > 0) {
-        for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
-          LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args(pvec.p, Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done);
-          LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pvec.p, Ap.p, c->rs, c->d_cg);
-          LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pvec.p, c->rs, c->d_cg);
-        }
+      for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
+        if ((rc = exchange(pvec.p, sg.nloc(), true, true))) return rc;     // halo planes of p
+        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args(pvec.p, Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done);
+        if ((rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;
+        LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pvec.p, Ap.p, c->rs, c->d_cg);
+        if ((rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;
+        LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pvec.p, c->rs, c->d_cg);
       }
       SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
       SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -688,6 +928,7 @@ struct Problem : sipb_problem {
       batch = std::max(2, launched / 2);
     }
     if (h->flag == -9) SIPB_CUDA_CHECK(cudaMemsetAsync(xv, 0, N * sizeof(T), c->stream));   // cg.jl:47
+    if ((rc = exchange(xv, sg.nloc(), true, true))) return rc;              // halo planes of the new x
     *iters = h->iter;
     *relres = h->relres;
     *flag = h->flag;
@@ -805,6 +1046,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     log->h2d_bytes += npts * sizeof(T);
     if (minkowski) SIPB_CUDA_CHECK(cudaMemsetAsync(m.p + npts, 0, npts * sizeof(T), c->stream));
     m_resident = true;
+    { int rc = exchange(m.p, sg.nloc(), false, true); if (rc) return rc; }   // slabs: upper halo plane of m
   }
   cudaEvent_t ev0, ev1;
   SIPB_CUDA_CHECK(cudaEventCreate(&ev0));
@@ -883,6 +1125,14 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->warm.p, 0, 2 * sizeof(double), c->stream));
   }
   SIPB_CUDA_CHECK(cudaMemsetAsync(x_old.p, 0, N * sizeof(T), c->stream));
+  if (sg.on) {      // halo planes of the start vectors
+    int rc = exchange(x.p, sg.nloc(), true, true);
+    if (rc) return rc;
+    for (auto& S : sets)
+      if (S->z_halo) SIPB_CUDA_CHECK(cudaMemsetAsync(S->y_old.p - sg.plane, 0, sg.plane * sizeof(T), c->stream));
+    rc = exchange_yl_halos(false);
+    if (rc) return rc;
+  }
 
   // Q = sum rho_i AtA_i, accumulated set by set, diagonal by diagonal (:223-229)
   SIPB_CUDA_CHECK(cudaMemsetAsync(Q.p, 0, (size_t)ld * q_offs.size() * sizeof(T), c->stream));
@@ -983,6 +1233,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
                (const T*)S.y_old.p, c->rs, c->d_scal + base + 3);
     }
+    { int rc = exchange_yl_halos(true); if (rc) return rc; }   // slabs: halo planes for the next rhs gather
     LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
            (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
     { int rc = ctx_sync_scalars(c); if (rc) return rc; }
@@ -1207,6 +1458,9 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_l1); cudaFreeHost(c->h_l1);
   cudaFree(c->d_sel); cudaFree(c->d_tie_counts);
+  if (c->d_gather) cudaFree(c->d_gather);
+  if (c->d_gather_local) cudaFree(c->d_gather_local);
+  if (c->comm) NCCL(CommDestroy)(c->comm);
   cudaStreamDestroy(c->stream);
   delete c;
   return SIPB_OK;
@@ -1219,17 +1473,48 @@ int sipb_ctx_num_sms(sipb_ctx* c, int* out) {
 }
 
 int sipb_comm_unique_id(void* out128) {
-  (void)out128;
-  set_error("multi-GPU slabs are not built into this library yet");
-  return SIPB_E_UNSUPPORTED;
+  SIPB_REQUIRE(out128, SIPB_E_INVALID, "null argument");
+  static_assert(NCCL_UNIQUE_ID_BYTES == 128, "unique id size");
+  SIPB_REQUIRE(nccl_api()->ok, SIPB_E_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId id;
+  SIPB_NCCL_CHECK(NCCL(GetUniqueId)(&id));
+  memcpy(out128, &id, sizeof(id));
+  return SIPB_OK;
 }
 int sipb_comm_init(sipb_ctx* ctx, int rank, int world, const void* uid128) {
-  (void)uid128;
   SIPB_REQUIRE(ctx, SIPB_E_INVALID, "null ctx");
+  SIPB_REQUIRE(world >= 1 && rank >= 0 && rank < world, SIPB_E_INVALID, "bad rank / world");
+  SIPB_REQUIRE(ctx->comm == nullptr, SIPB_E_STATE, "communicator already initialised");
   if (world == 1) { ctx->rank = 0; ctx->world = 1; return SIPB_OK; }
-  (void)rank;
-  set_error("multi-GPU slabs are not built into this library yet");
-  return SIPB_E_UNSUPPORTED;
+  SIPB_REQUIRE(uid128, SIPB_E_INVALID, "null unique id");
+  SIPB_REQUIRE(nccl_api()->ok, SIPB_E_NCCL, "libnccl.so.2 could not be loaded");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, uid128, sizeof(id));
+  SIPB_NCCL_CHECK(NCCL(CommInitRank)(&ctx->comm, world, id, rank));
+  ctx->rank = rank;
+  ctx->world = world;
+  SIPB_CUDA_CHECK(cudaMalloc(&ctx->d_gather, sizeof(unsigned long long) * 4 * world));
+  SIPB_CUDA_CHECK(cudaMalloc(&ctx->d_gather_local, sizeof(unsigned long long) * 4));
+  // warm the communicator up (first collective builds the channels)
+  int rc = ctx->allreduce(ctx->d_scal, kScalSlots);
+  if (rc) return rc;
+  SIPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_scal, 0, kScalSlots * sizeof(double), ctx->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return SIPB_OK;
+}
+int sipb_comm_info(sipb_ctx* ctx, int* rank, int* world) {
+  SIPB_REQUIRE(ctx && rank && world, SIPB_E_INVALID, "null argument");
+  *rank = ctx->rank;
+  *world = ctx->world;
+  return SIPB_OK;
+}
+/* plane range [k0,k1) of the slowest axis owned by `rank` (contiguous, sizes differ by at most one) */
+int sipb_slab_range(int64_t n_last, int rank, int world, int64_t* k0, int64_t* k1) {
+  SIPB_REQUIRE(k0 && k1 && world >= 1 && rank >= 0 && rank < world, SIPB_E_INVALID, "bad argument");
+  *k0 = n_last * rank / world;
+  *k1 = n_last * (rank + 1) / world;
+  return SIPB_OK;
 }
 
 int sipb_problem_create(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const double* h, int minkowski,
@@ -1239,8 +1524,25 @@ int sipb_problem_create(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, co
   SIPB_REQUIRE(ndim == 2 || ndim == 3, SIPB_E_INVALID, "ndim must be 2 or 3");
   for (int a = 0; a < ndim; ++a) SIPB_REQUIRE(n[a] >= 2, SIPB_E_INVALID, "grid dimensions must be >= 2");
   SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
-  if (dtype == SIPB_F32) *out = new Problem<float>(ctx, dtype, ndim, n, h, minkowski != 0, feasibility_only != 0);
-  else *out = new Problem<double>(ctx, dtype, ndim, n, h, minkowski != 0, feasibility_only != 0);
+  sipb_problem* pb = nullptr;
+  int err = SIPB_OK;
+  if (dtype == SIPB_F32) {
+    auto* q = new Problem<float>(ctx, dtype, ndim, n, h, minkowski != 0, feasibility_only != 0);
+    err = q->create_error;
+    pb = q;
+  } else {
+    auto* q = new Problem<double>(ctx, dtype, ndim, n, h, minkowski != 0, feasibility_only != 0);
+    err = q->create_error;
+    pb = q;
+  }
+  if (err) {
+    delete pb;
+    set_error(err == SIPB_E_UNSUPPORTED
+                  ? "multi-GPU slabs need a 3-D, non-Minkowski problem (2-D and Minkowski problems stay on one GPU)"
+                  : "the slowest grid axis has fewer planes than there are ranks");
+    return err;
+  }
+  *out = pb;
   return SIPB_OK;
 }
 int sipb_problem_add_set(sipb_problem* pb, const sipb_set_desc* d) {
@@ -1364,6 +1666,7 @@ static int project_impl(sipb_ctx* c, const sipb_set_desc* d, int64_t M, void* v,
   SetT<T> S;
   S.desc = *d;
   S.M = M;
+  S.Mglob = M;
   SIPB_CUDA_CHECK(S.s.alloc((size_t)M));
   SIPB_CUDA_CHECK(S.pp_f.alloc(1));
   SIPB_CUDA_CHECK(S.warm.alloc(2));

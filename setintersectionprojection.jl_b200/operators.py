@@ -166,26 +166,35 @@ class TDOperator:
         return A
 
     # -- A'A in CDS form ---------------------------------------------------------------------------
-    def ata_cds(self):
+    def ata_cds(self, zrange=None):
         """(R, offsets) == mat2CDS(A'*A): R is [cols x nd] Fortran-ordered, offsets ascending int64.
+        `zrange=(k0,k1)` (3-D, un-blocked operators) returns only the rows of the planes [k0,k1) of the
+        slowest axis — the slab a rank uploads in multi-GPU runs.
 
         For difference operators every off-diagonal entry of A'A is a single product (-1/h)(1/h) and the
         main diagonal is the left fold, in row order (z block, y block, x block), of the squares — the
         accumulation order of a sparse A'*A."""
         base = TDOperator(self.kind, self.n, self.h, self.TF) if self.block_mode != _lib.BLOCK_PLAIN else self
-        R, offs = base._ata_cds_plain()
+        if zrange is not None and (self.block_mode != _lib.BLOCK_PLAIN or self.ndim != 3 or self.kind == "D_xz"):
+            raise ValueError("row slabs exist only for un-blocked 3-D operators")
+        R, offs = base._ata_cds_plain(zrange)
         if self.block_mode == _lib.BLOCK_PLAIN:
             return R, offs
         return _minkowski_cds(R, offs, self.block_mode)
 
-    def _ata_cds_plain(self):
-        TF, N, n = self.TF, self.npts, self.n
+    def _ata_cds_plain(self, zrange=None):
+        TF, n = self.TF, self.n
+        lo, hi = 0, self.npts
+        if zrange is not None:
+            plane = n[0] * n[1]
+            lo, hi = plane * int(zrange[0]), plane * int(zrange[1])
+        N = hi - lo
         if self.kind == "identity":
             return np.ones((N, 1), dtype=TF, order="F"), np.zeros(1, dtype=np.int64)
         if self.kind == "D_xz":
             A = self.tosparse()
             return mat2CDS(sp.csc_matrix(A.T) @ A)
-        idx = np.arange(N, dtype=np.int64)
+        idx = np.arange(lo, hi, dtype=np.int64)
         coords = [idx % n[0], (idx // n[0]) % n[1]] + ([idx // (n[0] * n[1])] if self.ndim == 3 else [])
         strides = [1, n[0], n[0] * n[1]]
         diag = np.zeros(N, dtype=TF)

@@ -12,12 +12,15 @@ import copy
 import numpy as np
 
 from . import _lib
+from . import distributed as dd
 from .operators import TDOperator
 
 
 class CDSList(list):
-    """Vector{Array{TF,2}} of CDS matrices; carries the cached device problem built from it."""
+    """Vector{Array{TF,2}} of CDS matrices; carries the cached device problem built from it.
+    `slab` = (k0, k1) when the matrices hold only this rank's rows (multi-GPU slabs)."""
     _device = None
+    slab = None
 
 
 def _require_device_operators(TD_OP):
@@ -46,13 +49,22 @@ def PARSDMM_precompute_distribute(TD_OP, set_Prop, comp_grid, options):
         set_Prop.tag.append(("distance squared", "identity", "matrix", ""))
     p = len(TD_OP)
     AtA = CDSList()
+    zrange = None
+    if dd.active() and TD_OP[0].ndim == 3:
+        # "distribute": every rank builds and later uploads only the rows of its own z-slab
+        zrange = dd.slab_range(TD_OP[0].n[2])
+        AtA.slab = zrange
     for i in range(p):
-        R, offs = TD_OP[i].ata_cds()          # == mat2CDS(TD_OP[i]'*TD_OP[i]) (identity when AtA_diag)
+        R, offs = TD_OP[i].ata_cds(zrange)    # == mat2CDS(TD_OP[i]'*TD_OP[i]) (identity when AtA_diag)
         AtA.append(R)
         set_Prop.AtA_offsets[i] = offs
     set_Prop.AtA_offsets = set_Prop.AtA_offsets[:p]
-    y = [np.zeros(TD_OP[i].rows, dtype=TF) for i in range(p)]
-    l = [np.zeros(TD_OP[i].rows, dtype=TF) for i in range(p)]
+    if zrange is None:
+        rows = [TD_OP[i].rows for i in range(p)]
+    else:
+        rows = [sum(b - a for a, b in dd.local_td_slices(TD_OP[i], *zrange)) for i in range(p)]
+    y = [np.zeros(r, dtype=TF) for r in rows]
+    l = [np.zeros(r, dtype=TF) for r in rows]
     return TD_OP, AtA, l, y
 
 

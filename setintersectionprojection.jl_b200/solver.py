@@ -12,6 +12,7 @@ import weakref
 import numpy as np
 
 from . import _lib
+from . import distributed as dd
 from .constraints import Projector
 from .operators import TDOperator
 from .types import convert_options, log_type_PARSDMM
@@ -39,6 +40,7 @@ def _problem_key(TF, TD_OP, P_sub, set_Prop, options):
                       float(P.max) if np.ndim(P.max) == 0 else None, P.k,
                       None if P.min_vec is None else P.min_vec.ctypes.data))
     items.append(tuple(bool(v) for v in set_Prop.ncvx))
+    items.append((dd.rank(), dd.world()) if dd.active() else None)
     return tuple(items)
 
 
@@ -59,6 +61,13 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
         if not isinstance(P, Projector):
             raise NotImplementedError("P_sub entries must be the Projector functors returned by setup_constraints")
     op0 = TD_OP[0]
+    slab = None
+    if dd.active():
+        if op0.ndim != 3 or options.Minkowski:
+            raise NotImplementedError("multi-GPU slabs need a 3-D, non-Minkowski problem")
+        slab = dd.slab_range(op0.n[2])
+        if getattr(AtA, "slab", None) not in (None, slab):
+            raise ValueError("AtA was built for another slab than this rank's")
     n = (C.c_int64 * 3)(*(list(op0.n) + [1] * (3 - op0.ndim)))
     h = (C.c_double * 3)(*([float(v) for v in op0.h] + [1.0] * (3 - op0.ndim)))
     handle = C.c_void_p()
@@ -66,13 +75,21 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
                                        int(bool(options.feasibility_only)), C.byref(handle)))
     try:
         for i in range(p):
+            keep = None
             if i < pp:
                 d = P_sub[i].descriptor(TD_OP[i].op_kind, TD_OP[i].block_mode, set_Prop.ncvx[i])
+                if slab is not None and P_sub[i].min_vec is not None:      # vector bounds: this rank's rows only
+                    keep = (dd.scatter_td(P_sub[i].min_vec, TD_OP[i], *slab), dd.scatter_td(P_sub[i].max_vec, TD_OP[i], *slab))
+                    d.min_vec, d.max_vec = keep[0].ctypes.data, keep[1].ctypes.data
             else:
                 d = _lib.SetDesc()
                 d.set_kind, d.op_kind, d.block_mode, d.ncvx = _lib.SET_DISTANCE, TD_OP[i].op_kind, TD_OP[i].block_mode, 0
             _lib.check(lib.sipb_problem_add_set(handle, C.byref(d)))
-            R = np.asfortranarray(AtA[i], dtype=TF)
+            R = AtA[i]
+            if slab is not None and getattr(AtA, "slab", None) is None:       # global CDS given: keep this rank's rows
+                plane = op0.n[0] * op0.n[1]
+                R = R[plane * slab[0]: plane * slab[1], :]
+            R = np.asfortranarray(R, dtype=TF)
             offs = np.ascontiguousarray(set_Prop.AtA_offsets[i], dtype=np.int64)
             if R.shape[1] != offs.size:
                 raise ValueError("AtA[%d] has %d diagonals but %d offsets" % (i, R.shape[1], offs.size))
@@ -86,15 +103,27 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
     except Exception:
         lib.sipb_problem_destroy(handle)
         raise
-    N = op0.npts * (2 if options.Minkowski else 1)
-    return _DeviceProblem(handle, _problem_key(TF, TD_OP, P_sub, set_Prop, options), p, pp, N,
-                          [A.rows for A in TD_OP], qo)
+    if slab is None:
+        N = op0.npts * (2 if options.Minkowski else 1)
+        rows = [A.rows for A in TD_OP]
+    else:
+        N = op0.n[0] * op0.n[1] * (slab[1] - slab[0])
+        rows = [sum(b - a for a, b in dd.local_td_slices(A, *slab)) for A in TD_OP]
+    dev = _DeviceProblem(handle, _problem_key(TF, TD_OP, P_sub, set_Prop, options), p, pp, N, rows, qo)
+    dev.slab = slab
+    dev.N_global = op0.npts * (2 if options.Minkowski else 1)
+    dev.rows_global = [A.rows for A in TD_OP]
+    return dev
 
 
 def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
-            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False):
+            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False, gather_result=True):
     """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
-    Returns (x, log_PARSDMM, l, y)."""
+    Returns (x, log_PARSDMM, l, y).
+
+    Multi-GPU slabs (after `distributed.init`, 3-D problems): every rank passes the same global `m`
+    (or its own slab of it) and receives the global `x` (host-side gather) unless `gather_result=False`;
+    `l`, `y` are this rank's slabs (see `distributed.gather_td`)."""
     if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
         raise TypeError("m must be a Float32/Float64 vector")
     TF = m.dtype.type
@@ -113,6 +142,16 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
             pass
     p, pp, N = dev.p, dev.pp, dev.N
     m = np.ascontiguousarray(m)
+    slab = getattr(dev, "slab", None)
+    if slab is not None:
+        op0 = TD_OP[0]
+        if m.size == dev.N_global:
+            m = dd.scatter_model(m, op0.n, *slab)
+        if x is not None and np.size(x) == dev.N_global:
+            x = dd.scatter_model(np.ascontiguousarray(x, dtype=TF), op0.n, *slab)
+        if l is not None and len(l) and all(np.size(l[i]) == dev.rows_global[i] for i in range(p)):
+            l = [dd.scatter_td(np.ascontiguousarray(l[i], dtype=TF), TD_OP[i], *slab) for i in range(p)]
+            y = [dd.scatter_td(np.ascontiguousarray(y[i], dtype=TF), TD_OP[i], *slab) for i in range(p)]
     if options.Minkowski:
         if m.size * 2 != N:
             raise ValueError("Minkowski problems need length(m) == N/2")
@@ -194,4 +233,6 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
     if x is not None and isinstance(x, np.ndarray) and x.size == x_out.size and x is not x_out:
         x[:] = x_out                                                                       # in-place like the reference
         x_out = x
+    if slab is not None and gather_result and not resident_io:
+        x_out = dd.gather_model(x_out)
     return x_out, log, l, y
