@@ -14,8 +14,11 @@ l1 ball ∩ lateral slope bounds (examples/test_scaling_3D.jl-style).  value = P
 * --impl reference: the reference's CPU algorithm (oracle port; Julia is not installable here) on the
   host cores, same workload/metric, each step a bounded sample (a few PARSDMM iterations).
 
-Multi-GPU (N>1, torchrun): one process per GPU; until slab decomposition lands every rank projects its
-own independent model ("replicas", weak scaling); time = max over ranks.
+Multi-GPU (N>1, torchrun): one process per GPU, the volume is slab-partitioned along its slowest axis
+(NCCL halo planes + Float64 all-reduces inside the C library).  Default is weak scaling: the grid is
+n x n x (n*N), i.e. one n^3 slab per GPU, and `value` counts slab-iterations per second (N x the PARSDMM
+iterations/s of the N-times larger problem; equal to iterations/s at N=1).  `--scaling strong` keeps the
+n^3 grid fixed.  Time = max over ranks of the CUDA-event time.
 """
 from __future__ import annotations
 
@@ -37,12 +40,9 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
-def workload(n, TF=np.float32, seed=1234):
+def workload(n, TF=np.float32, nz=None):
     import problems as pr
-    spec = pr.spec_config2((n, n, n), TF)
-    if seed != 1234:
-        spec["m"] = pr.synthetic_model((n, n, n), TF, seed)
-    return spec
+    return pr.spec_config2((n, n, nz or n), TF)
 
 
 def tweak_options(o):
@@ -170,7 +170,7 @@ def run_device(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("cpu:gloo,cuda:nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
         if dist is not None:
@@ -178,13 +178,18 @@ def run_device(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     n = args.n
-    N = n ** 3
-    spec = workload(n, seed=1234 + rank)
+    nz = n * world if (world > 1 and args.scaling == "weak") else n
+    N = n * n * nz
+    units = world if (world > 1 and args.scaling == "weak") else 1       # slabs of n^3 per PARSDMM iteration
+    if world > 1:
+        from sip_b200 import distributed as dd
+        dd.init(rank, world, local_rank)
+    spec = workload(n, nz=nz)
     opt = tweak_options(sip.PARSDMM_options())
     sb = pr.build(sip, spec, opt)
     m = spec["m"]
     call = lambda **kw: sip.PARSDMM(m, sb["AtA"], sb["TD_OP"], sb["set_Prop"], sb["P_sub"], sb["cg"], sb["opt"],   # noqa: E731
-                                    return_ly=False, **kw)
+                                    return_ly=False, gather_result=False, **kw)
     # first call uploads the operators (the "distribute" of PARSDMM_precompute_distribute)
     x, log, _, _ = call()
     iters_per_step = len(log.obj)
@@ -225,15 +230,17 @@ def run_device(args, rank, world, local_rank):
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_s_max, wall_e2e_max, wall_res_max = [float(v) for v in tm.tolist()]
     its_all, e2e_its_all, launches_all = [float(v) for v in cnt.tolist()]
+    # every rank counted the same global iterations: work units = iterations x slabs
+    its_all, e2e_its_all = its_all / world * units, e2e_its_all / world * units
 
     # ---- roofline of the dominant kernel from one profiled solve (CUDA events around every launch) --
     roof = None
     kernels = {}
+    _, lgp, _, _ = call(resident_io=True, profile_kernels=True)      # every rank: the solve contains collectives
     if rank == 0:
-        _, lgp, _, _ = call(resident_io=True, profile_kernels=True)
         kernels = lgp.timing["kernels"]
         nd = len(sb["AtA"]._device.q_offsets)
-        alg = (nd + 2) * N * 4
+        alg = (nd + 2) * (N // world) * 4           # per GPU
         cnt_k, ms_k = kernels.get("cds_spmv_dot", (0, 0.0))
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -265,13 +272,17 @@ def run_device(args, rank, world, local_rank):
     line = {
         "metric": "parsdmm_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "3D %d^3 Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1], "
-                               "test_scaling_3D-style)" % n, "grid": [n, n, n],
+        "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "3D %dx%dx%d Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1], "
+                               "test_scaling_3D-style)" % (n, n, nz), "grid": [n, n, nz],
+                   "value_units": "PARSDMM iterations/s" if units == 1 else
+                                  "slab-iterations/s = %d x PARSDMM iterations/s (one %d^3 slab per GPU)" % (units, n),
                    "step": "one full PARSDMM projection to the reference's stopping rules",
                    "parsdmm_iterations_per_step": iters_per_step, "time_to_tolerance_ms": 1e3 * dev_s_max / args.steps,
                    "cache": "working set %.1f GB (Q + AtA + 9 vectors per set) >> 126 MB L2, no flush needed" % (N * 4 * 105 / 1e9),
-                   "parallelism": "single GPU" if world == 1 else "replicas x%d (independent models per GPU)" % world},
+                   "parallelism": "single GPU" if world == 1 else
+                                  "z-slabs over %d GPUs: NCCL send/recv halo planes + Float64 all-reduce, %s scaling" % (world, args.scaling)},
         "e2e": {"value": e2e_its_all / wall_e2e_max, "unit": "iterations/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * wall_e2e_max / args.steps},
         "gpu_launches": int(launches_all),
@@ -295,6 +306,8 @@ def main():
     ap.add_argument("--n", type=int, default=200, help="grid width (BASELINE configs[1] uses 200)")
     ap.add_argument("--cpu-iters", type=int, default=4, help="PARSDMM iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = n x n x (n*N) grid (one n^3 slab per GPU), strong = fixed n^3 grid")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
