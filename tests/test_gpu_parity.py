@@ -395,3 +395,51 @@ def test_parsdmm_multilevel(sip, orc, which):
     assert relerr(xs, xo) < TOL[TF]
     for a, b in zip(y2, yy):
         assert relerr(a, b) < 100 * TOL[TF]
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE-size checks through size-independent properties (the oracle would need minutes here)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_config2_properties(sip):
+    """configs[1] at its full size (200^3 Float32): operator adjointness and linearity, projector
+    idempotence / feasibility, and every constraint set satisfied by the PARSDMM result to
+    1.5*feas_tol (the reference's own acceptance test, test_PARSDMM.jl:86-89)."""
+    TF = np.float32
+    n = (200, 200, 200)
+    spec = pr.spec_config2(n, TF)
+    opt = sip.PARSDMM_options()
+    opt.evol_rel_tol = 10 * float(np.finfo(TF).eps)
+    sb = pr.build(sip, spec, opt)
+    rng = np.random.default_rng(0)
+    N = int(np.prod(n))
+    TV = sb["TD_OP"][1]
+    x1, x2 = rng.standard_normal(N).astype(TF), rng.standard_normal(N).astype(TF)
+    v = rng.standard_normal(TV.rows).astype(TF)
+    Ax1, Ax2 = TV @ x1, TV @ x2
+    # <A x, v> == <x, A' v>
+    lhs = float(np.dot(Ax1.astype(np.float64), v.astype(np.float64)))
+    rhs = float(np.dot(x1.astype(np.float64), (TV.T @ v).astype(np.float64)))
+    assert abs(lhs - rhs) <= 1e-5 * (abs(lhs) + abs(rhs) + 1.0)
+    # linearity
+    comb = TV @ (TF(2.0) * x1 - TF(0.5) * x2)
+    assert relerr(comb, TF(2.0) * Ax1 - TF(0.5) * Ax2) < 1e-5
+    # the CDS form of A'A applied by the SpMV kernel agrees with A'(A x)
+    R, off = sb["AtA"][1], sb["set_Prop"].AtA_offsets[1]
+    assert relerr(sip.CDS_MVp(N, R.shape[1], R, off, x1, np.zeros(N, dtype=TF)), TV.T @ Ax1) < 1e-5
+    # projectors: idempotent, inside the set
+    P_l1 = sb["P_sub"][1]
+    assert np.array_equal(P_l1(Ax1.copy()), Ax1)                    # inside the ball: untouched
+    big = (Ax1 * TF(100.0 * float(P_l1.max) / float(np.abs(Ax1.astype(np.float64)).sum()))).astype(TF)
+    y = P_l1(big.copy())
+    assert abs(float(np.abs(y.astype(np.float64)).sum()) - float(P_l1.max)) <= 1e-5 * float(P_l1.max)
+    assert relerr(P_l1(y.copy()), y) < 1e-6
+    # the projection itself
+    x, log, _, _ = sip.PARSDMM(spec["m"].copy(), sb["AtA"], sb["TD_OP"], sb["set_Prop"], sb["P_sub"], sb["cg"], sb["opt"],
+                               return_ly=False)
+    assert 5 < len(log.obj) < opt.maxit and log.cg_it[0] == 0
+    for i in range(len(sb["P_sub"])):
+        s = sb["TD_OP"][i] @ x
+        ps = sb["P_sub"][i](s.copy())
+        feas = np.linalg.norm(ps.astype(np.float64) - s) / np.linalg.norm(s.astype(np.float64))
+        assert feas <= 1.5 * float(opt.feas_tol), (i, feas)
+    assert abs(log.obj[-1] - 0.5 * np.linalg.norm(x.astype(np.float64) - spec["m"]) ** 2) <= 1e-3 * log.obj[-1]
