@@ -323,34 +323,41 @@ struct RhsArgs {
   SetRef<T> sets[kMaxSets];
 };
 
-// W consecutive columns per thread: the gathers of the W columns are independent, which gives the
-// memory system W x (rows per column) loads in flight per thread; rhs is written with 16-byte stores.
-template <typename T, int W, bool RDUAL>
-__device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W], double* d) {
-  GridIdx g[W];
-  g[0] = grid_decode(c0, a.npts, a.n);
+// G consecutive columns per thread (two 16-byte vectors of Float32): the gathers of a group are
+// independent, which puts G x (rows per column) loads in flight per thread and hides the DRAM latency that
+// bounded the per-column version (ncu round 1: long-scoreboard stalls on the first FMUL/FADD after each
+// gather); rhs is written with 16-byte stores.  Groups that wrap a grid line fall back to single points.
+template <typename T, int G, bool RDUAL>
+__device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[G], double* d) {
+  GridIdx g0 = grid_decode(c0, a.npts, a.n);
+  const bool line = (G == 1) || (g0.i + (unsigned)G <= a.n[0] && (g0.upper || c0 + G <= a.npts));
 #pragma unroll
-  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], (unsigned)a.npts, a.n); }
-#pragma unroll
-  for (int e = 0; e < W; ++e) acc[e] = (T)0;
+  for (int e = 0; e < G; ++e) acc[e] = (T)0;
   for (int s = 0; s < a.nsets; ++s) {
     const SetRef<T>& S = a.sets[s];
-    const T rho = S.rho;
-    const T* __restrict__ y = S.y;
-    const T* __restrict__ l = S.l;
-    T tv[W];
-    op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](int row) -> T { return rho * y[row] + l[row]; }, tv);
+    const FetchAxpy<T> fv{S.rho, S.y, S.l};
+    const FetchDiff<T> fd{S.y, S.y_old};
+    T tv[G], td[G];
+    if (line) {
+      op_adjoint_line<T, G>(S.op, S.op.mode, g0, fv, tv);
+      if (RDUAL) op_adjoint_line<T, G>(S.op, S.op.mode, g0, fd, td);
+    } else {
+      GridIdx g = g0;
 #pragma unroll
-    for (int e = 0; e < W; ++e) acc[e] = acc[e] + tv[e];
+      for (int e = 0; e < G; ++e) {
+        tv[e] = op_adjoint_pt<T>(S.op, S.op.mode, g, fv);
+        if (RDUAL) td[e] = op_adjoint_pt<T>(S.op, S.op.mode, g, fd);
+        grid_next(g, (unsigned)a.npts, a.n);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < G; ++e) acc[e] = acc[e] + tv[e];
     if (RDUAL) {
       // dual residual of the PREVIOUS iteration, ||A'(y - y_old)||^2 (update_y_l.jl:82-84), rides on the
       // same gather: y_old still holds y^{k-1} until the next y/l update overwrites it
-      const T* __restrict__ yo = S.y_old;
-      T td[W];
-      op_adjoint_n<T, W>(S.op, S.op.mode, g, [=](int row) -> T { return y[row] - yo[row]; }, td);
       double sq = 0.0;
 #pragma unroll
-      for (int e = 0; e < W; ++e) sq += (double)td[e] * (double)td[e];
+      for (int e = 0; e < G; ++e) sq += (double)td[e] * (double)td[e];
 #pragma unroll
       for (int q = 0; q < kRdualSets; ++q) d[q] += (q == s) ? sq : 0.0;
     }
@@ -359,18 +366,25 @@ __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[W
 
 // RDUAL: additionally reduce, per set s < kRdualSets, ||A_s'(y_s - y_old_s)||^2 -> out[s]
 template <typename T, bool RDUAL>
-__global__ void __launch_bounds__(kThreads) k_rhs(const __grid_constant__ RhsArgs<T> a, RedScratch rs, double* out) {
+__global__ void __launch_bounds__(kThreads, 4) k_rhs(const __grid_constant__ RhsArgs<T> a, RedScratch rs, double* out) {
   constexpr int VW = Vec<T>::W;
   double d[kRdualSets];
 #pragma unroll
   for (int q = 0; q < kRdualSets; ++q) d[q] = 0.0;
-  const i64 nvec = a.ncols / VW;
-  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
-    T acc[VW];
-    rhs_cols<T, VW, RDUAL>(a, iv * VW, acc, d);
-    vstore<T>(a.rhs + iv * VW, acc);
+  constexpr int G = 2 * VW;
+  const i64 ngrp = a.ncols / G;
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < ngrp; iv += (i64)gridDim.x * blockDim.x) {
+    T acc[G];
+    rhs_cols<T, G, RDUAL>(a, iv * G, acc, d);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      T part[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) part[e] = acc[h * VW + e];
+      vstore<T>(a.rhs + iv * G + h * VW, part);
+    }
   }
-  for (i64 c = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; c < a.ncols; c += (i64)gridDim.x * blockDim.x) {
+  for (i64 c = ngrp * G + (i64)blockIdx.x * blockDim.x + threadIdx.x; c < a.ncols; c += (i64)gridDim.x * blockDim.x) {
     T acc[1];
     rhs_cols<T, 1, RDUAL>(a, c, acc, d);
     a.rhs[c] = acc[0];
@@ -607,7 +621,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
 
 // out: [0..2] as d[0..2] (MODE 2 writes only [0]); ADAPT sums go to out[4..9]
 template <typename T, int MODE, bool ADAPT>
-__global__ void __launch_bounds__(kThreads) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
+__global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
   constexpr int VW = Vec<T>::W;
   constexpr int NR = ADAPT ? 9 : 3;
   ProjDev<T> P = a.P;
@@ -650,11 +664,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) k_op_adjoint(const __grid_constant__ OpDev op, const T* __restrict__ v,
                                                          T* __restrict__ t) {
   for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < op.cols; c += (i64)gridDim.x * blockDim.x) {
-    GridIdx g[1];
-    g[0] = grid_decode(c, op.npts, op.n);
-    T tv[1];
-    op_adjoint_n<T, 1>(op, op.mode, g, [=](int row) -> T { return v[row]; }, tv);
-    t[c] = tv[0];
+    const GridIdx g = grid_decode(c, op.npts, op.n);
+    t[c] = op_adjoint_pt<T>(op, op.mode, g, FetchPlain<T>{v});
   }
 }
 
@@ -701,13 +712,19 @@ __global__ void __launch_bounds__(kThreads) k_feas(i64 M, T* __restrict__ s, con
 template <typename T, int W>
 __device__ __forceinline__ void rdual_cols(const OpDev& op, const T* __restrict__ y, const T* __restrict__ y_old,
                                            i64 c0, double* d) {
-  GridIdx g[W];
-  g[0] = grid_decode(c0, op.npts, op.n);
-#pragma unroll
-  for (int e = 1; e < W; ++e) { g[e] = g[e - 1]; grid_next(g[e], 0xffffffffu, op.n); }
   // the dual residual runs over one N-block only: evaluate the operator as if it were un-blocked
+  GridIdx g = grid_decode(c0, op.npts, op.n);
+  const FetchDiff<T> fd{y, y_old};
   T t[W];
-  op_adjoint_n<T, W>(op, SIPB_BLOCK_PLAIN, g, [=](int row) -> T { return y[row] - y_old[row]; }, t);
+  if (W == 1 || g.i + (unsigned)W <= op.n[0]) {
+    op_adjoint_line<T, W>(op, SIPB_BLOCK_PLAIN, g, fd, t);
+  } else {
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      t[e] = op_adjoint_pt<T>(op, SIPB_BLOCK_PLAIN, g, fd);
+      grid_next(g, 0xffffffffu, op.n);
+    }
+  }
 #pragma unroll
   for (int e = 0; e < W; ++e) d[0] += (double)t[e] * (double)t[e];
 }

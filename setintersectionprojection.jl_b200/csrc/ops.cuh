@@ -41,9 +41,16 @@ __device__ __forceinline__ unsigned op_stride32(const OpDev& op, int a) {
 
 template <typename T, int W>
 __device__ __forceinline__ void load_any(const T* p, T (&v)[W]) {
-  if constexpr (W == Vec<T>::W) {
+  constexpr int VW = Vec<T>::W;
+  if constexpr (W >= VW && W % VW == 0) {
     if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0) {
-      vload<T>(p, v);
+#pragma unroll
+      for (int h = 0; h < W / VW; ++h) {
+        T t[VW];
+        vload<T>(p + h * VW, t);
+#pragma unroll
+        for (int e = 0; e < VW; ++e) v[h * VW + e] = t[e];
+      }
       return;
     }
   }
@@ -286,6 +293,145 @@ __device__ __forceinline__ void op_adjoint_n(const OpDev& op, int mode, const Gr
       return;
     }
   }
+}
+
+// ---- value fetchers for the adjoint gathers (W consecutive rows, signed start index) -----------------
+template <typename T>
+struct FetchPlain {          // v[row]
+  const T* __restrict__ v;
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[W]) const { load_any<T, W>(v + row0, out); }
+};
+template <typename T>
+struct FetchAxpy {           // rho*y[row] + l[row]      (rhs_compose.jl:28)
+  T rho;
+  const T* __restrict__ y;
+  const T* __restrict__ l;
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[W]) const {
+    T a[W], b[W];
+    load_any<T, W>(y + row0, a);
+    load_any<T, W>(l + row0, b);
+#pragma unroll
+    for (int e = 0; e < W; ++e) out[e] = rho * a[e] + b[e];
+  }
+};
+template <typename T>
+struct FetchDiff {           // y[row] - y_old[row]      (update_y_l.jl:82)
+  const T* __restrict__ y;
+  const T* __restrict__ yo;
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[W]) const {
+    T a[W], b[W];
+    load_any<T, W>(y + row0, a);
+    load_any<T, W>(yo + row0, b);
+#pragma unroll
+    for (int e = 0; e < W; ++e) out[e] = a[e] - b[e];
+  }
+};
+
+// ---- adjoint for a group of W consecutive grid points that stay inside one grid line (caller checks
+//      g0.i + W <= n0 and a single Minkowski half): the rows the group needs are consecutive too, so they
+//      are fetched with (at most) two wide loads per block instead of 2W scalar gathers. -------------------
+template <typename T, int W, typename F>
+__device__ __forceinline__ void op_adjoint_line(const OpDev& op, int mode, const GridIdx& g0, const F& f, T (&t)[W]) {
+  auto scalar_val = [&](int row) -> T {
+    T v[1];
+    f.template get<1>(row, v);
+    return v[0];
+  };
+#pragma unroll
+  for (int e = 0; e < W; ++e) t[e] = (T)0;
+  if (!op_touches_half(mode, g0.upper)) return;
+  const unsigned cc0 = g0.cc, i0 = g0.i, j = g0.j, k = g0.k;
+  if (op.kind == SIPB_OP_IDENTITY) {
+    T v[W];
+    f.template get<W>((int)cc0, v);
+#pragma unroll
+    for (int e = 0; e < W; ++e) t[e] = t[e] + v[e];
+    return;
+  }
+  if (op.kind == SIPB_OP_DXZ) {
+    const unsigned w = op.n[0] - 1u;
+    const T a = (T)op.a_xz;
+    const bool jl = j >= 1u, jh = j < op.n[1] - 1u;
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      const unsigned i = i0 + e;
+      const bool il = i >= 1u, ih_ = i < op.n[0] - 1u;
+      const int q = (int)(i + w * j);
+      T acc = (T)0;
+      if (il && jl) acc = acc + a * scalar_val(q - 1 - (int)w);
+      if (ih_ && jl) acc = acc + (-a) * scalar_val(q - (int)w);
+      if (il && jh) acc = acc + (-a) * scalar_val(q - 1);
+      if (ih_ && jh) acc = acc + a * scalar_val(q);
+      t[e] = acc;
+    }
+    return;
+  }
+  for (int b = 0; b < op.nblk; ++b) {
+    const int a = op.axis[b];
+    const T ih = (T)op.ih[a];
+    const T nih = -ih;
+    const int base = (int)op.rs[b];
+    if (a == 0) {
+      const int q0 = base + (int)(cc0 - (j + op.n[1] * k));       // row of (i0, j, k)
+      if (i0 + (unsigned)W == op.n[0]) {                          // group ends the line: the row of i = n0-1 does
+#pragma unroll                                                    // not exist -> element-wise (one group per line)
+        for (int e = 0; e < W; ++e) {
+          const int q = q0 + e;
+          if (i0 + e >= 1u) t[e] = t[e] + ih * scalar_val(q - 1);
+          if (i0 + e < op.n[0] - 1u) t[e] = t[e] + nih * scalar_val(q);
+        }
+      } else {
+        T v[W];
+        f.template get<W>(q0, v);
+        T prev = (i0 >= 1u) ? scalar_val(q0 - 1) : (T)0;
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          if (i0 + e >= 1u) t[e] = t[e] + ih * prev;
+          t[e] = t[e] + nih * v[e];            // i < n0-1 holds for the whole group here
+          prev = v[e];
+        }
+      }
+    } else if (a == 1) {
+      const int st = (int)op.n[0];
+      const int q0 = base + (int)(cc0 - op.n[0] * k);             // row of (i0, j, k)
+      if (j >= 1u) {
+        T v[W];
+        f.template get<W>(q0 - st, v);
+#pragma unroll
+        for (int e = 0; e < W; ++e) t[e] = t[e] + ih * v[e];
+      }
+      if (j < op.n[1] - 1u) {
+        T v[W];
+        f.template get<W>(q0, v);
+#pragma unroll
+        for (int e = 0; e < W; ++e) t[e] = t[e] + nih * v[e];
+      }
+    } else {
+      const int st = (int)(op.n[0] * op.n[1]);
+      const int q0 = base + (int)cc0;
+      const unsigned kg = k + op.kofs;
+      if (kg >= 1u) {
+        T v[W];
+        f.template get<W>(q0 - st, v);
+#pragma unroll
+        for (int e = 0; e < W; ++e) t[e] = t[e] + ih * v[e];
+      }
+      if (kg < op.nlast - 1u) {
+        T v[W];
+        f.template get<W>(q0, v);
+#pragma unroll
+        for (int e = 0; e < W; ++e) t[e] = t[e] + nih * v[e];
+      }
+    }
+  }
+}
+
+// single grid point (line wraps, tails)
+template <typename T, typename F>
+__device__ __forceinline__ T op_adjoint_pt(const OpDev& op, int mode, const GridIdx& g, const F& f) {
+  T t[1];
+  op_adjoint_line<T, 1>(op, mode, g, f, t);
+  return t[0];
 }
 
 }  // namespace sipb

@@ -1173,10 +1173,10 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       }
       // from the second iteration on the gather also yields the dual residual of iteration i-1
       if (fuse_rdual && i >= 2)
-        LAUNCH(c, KC_RHS, (k_rhs<T, true>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), ra, c->rs,
+        LAUNCH(c, KC_RHS, (k_rhs<T, true>), c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W)), ra, c->rs,
                c->d_scal + kSlotGlobal + 8);
       else
-        LAUNCH(c, KC_RHS, (k_rhs<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), ra, c->rs,
+        LAUNCH(c, KC_RHS, (k_rhs<T, false>), c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W)), ra, c->rs,
                (double*)nullptr);
     }
     phase_end(1);
