@@ -151,6 +151,9 @@ int sipb_ctx_num_sms(sipb_ctx* ctx, int* out);
 int sipb_comm_unique_id(void* out128);
 int sipb_comm_init(sipb_ctx* ctx, int rank, int world, const void* uid128);
 int sipb_comm_info(sipb_ctx* ctx, int* rank, int* world);
+/* 1 when the CG's reductions and halo planes go through CUDA-IPC peer memory (NVLink loads/stores fused into
+ * the kernels) instead of NCCL; set SIPB_P2P=0 before sipb_comm_init to force the NCCL path. */
+int sipb_comm_peer_path(sipb_ctx* ctx, int* active);
 /* planes [k0,k1) of the slowest grid axis owned by `rank`; after sipb_comm_init with world > 1 every
  * 3-D problem of the ctx is a slab problem: sipb_problem_create still takes the GLOBAL grid, while
  * sipb_problem_set_ata takes the rank's rows [n1*n2*k0, n1*n2*k1) of each diagonal and sipb_solve takes /

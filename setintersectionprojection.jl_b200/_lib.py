@@ -75,6 +75,7 @@ SYMBOLS = [
     ("sipb_comm_unique_id", _I, [_VP]),
     ("sipb_comm_init", _I, [_VP, _I, _I, _VP]),
     ("sipb_comm_info", _I, [_VP, _PI, _PI]),
+    ("sipb_comm_peer_path", _I, [_VP, _PI]),
     ("sipb_slab_range", _I, [_I64, _I, _I, _PI64, _PI64]),
     ("sipb_problem_create", _I, [_VP, _I, _I, _PI64, _PD, _I, _I, C.POINTER(_VP)]),
     ("sipb_problem_add_set", _I, [_VP, C.POINTER(SetDesc)]),

@@ -98,12 +98,14 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[32]) {
   }
 }
 
-// Returns true (in every thread) for the last block of the grid to arrive.
-__device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
+// Returns true (in every thread) for the last block of the grid to arrive.  `sys`: the block's global
+// writes must become visible to PEER GPUs before the last block signals them (system-scope fence).
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, bool sys = false) {
   __shared__ int s_last;
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (sys) __threadfence_system();
+    else __threadfence();
     unsigned int t = atomicAdd(counter, 1u);
     s_last = (t == gridDim.x - 1);
     if (s_last) *counter = 0u;   // all blocks have arrived; safe to reset for the next kernel
@@ -116,14 +118,14 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter) {
 // fixed order.  On return `v[0..NV)` holds the grid totals in thread 0 of the LAST block only;
 // the function returns true in every thread of that block.
 template <int NV>
-__device__ __forceinline__ bool grid_sum(double (&v)[NV], const RedScratch& rs) {
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], const RedScratch& rs, bool sys = false) {
   __shared__ double sm[NV][32];
   block_sum<NV>(v, sm);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) rs.partials[i * kMaxBlocks + blockIdx.x] = v[i];
   }
-  const bool last = last_block_ticket(rs.counter);
+  const bool last = last_block_ticket(rs.counter, sys);
   if (last) {
     __threadfence();
 #pragma unroll
@@ -136,6 +138,119 @@ __device__ __forceinline__ bool grid_sum(double (&v)[NV], const RedScratch& rs) 
     block_sum<NV>(v, sm);
   }
   return last;
+}
+
+// ---------------------------------------------------------------------------------------------
+// peer-memory collectives for slabs (one process per GPU, buffers mapped with CUDA IPC over NVLink)
+//
+// The CG has three tiny reductions and one halo per iteration; with NCCL each costs a kernel launch and
+// ~10-15 us of latency on the critical path.  Here the reducing kernel's last block stores its partial sums
+// straight into every peer's mailbox (NVLink peer stores + system fence + flag) and the consuming kernel
+// sums the W partials in rank order (bit-identical on all ranks); the SpMV reads the neighbours' boundary
+// plane of p through mapped peer pointers after waiting on a version flag the neighbour's p-update kernel
+// publishes.  Two mailbox buffers suffice: a rank can only be one reduction ahead of its slowest peer.
+// Every spin is bounded (kSpinLimit cycles); on time-out an error flag is raised and the kernel finishes.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+constexpr int kMailK = 4;
+constexpr long long kSpinLimit = 6000000000ll;   // ~3 s at 1.9 GHz
+
+struct PeerMail {
+  double val[2][kMaxRanks][kMailK];
+  unsigned long long flag[2][kMaxRanks];
+  unsigned long long pver[2];        // [0]: version of the lower neighbour's p, [1]: of the upper neighbour's
+};
+
+struct CommDev {
+  int on;                            // peer path active
+  int rank, world;
+  int has_lo, has_hi;
+  int* err;                          // device flag: a bounded spin timed out
+  unsigned long long* seq;           // device counter: mailbox reductions produced by this rank
+  unsigned long long* pv;            // device counter: version of this rank's p vector
+  PeerMail* mail[kMaxRanks];         // mail[q]: rank q's mailbox (peer mapped; mail[rank] is local)
+};
+
+__device__ __forceinline__ unsigned long long ld_vol(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ double ld_vol(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+
+// Called by every thread of ONE block (the last block of the reducing kernel); v valid in thread 0.
+template <int K>
+__device__ __forceinline__ void mail_publish(const CommDev& cd, const double (&v)[K]) {
+  static_assert(K <= kMailK, "mailbox slot too small");
+  __shared__ double sh[K];
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) sh[i] = v[i];
+    s_seq = *cd.seq + 1ull;
+  }
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int buf = (int)(seq & 1ull);
+  if ((int)threadIdx.x < cd.world) {
+    PeerMail* pm = cd.mail[threadIdx.x];
+#pragma unroll
+    for (int i = 0; i < K; ++i) *reinterpret_cast<volatile double*>(&pm->val[buf][cd.rank][i]) = sh[i];
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&pm->flag[buf][cd.rank]) = seq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *cd.seq = seq;
+}
+
+// Called by every thread of a block of the consuming kernel: sums the W partials in rank order.
+template <int K>
+__device__ __forceinline__ void mail_collect(const CommDev& cd, double (&out)[K]) {
+  __shared__ double sh[K];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = *cd.seq;
+    const int buf = (int)(seq & 1ull);
+    const PeerMail* me = cd.mail[cd.rank];
+    double acc[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) acc[i] = 0.0;
+    const long long t0 = clock64();
+    for (int q = 0; q < cd.world; ++q) {
+      while (ld_vol(&me->flag[buf][q]) != seq) {
+        if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; }
+      }
+      __threadfence_system();
+#pragma unroll
+      for (int i = 0; i < K; ++i) acc[i] += ld_vol(&me->val[buf][q][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) sh[i] = acc[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < K; ++i) out[i] = sh[i];
+}
+
+// thread 0 of the LAST block of a kernel that rewrote p (every block fenced at system scope before its ticket)
+__device__ __forceinline__ void p_publish(const CommDev& cd) {
+  const unsigned long long v = *cd.pv + 1ull;
+  *cd.pv = v;
+  __threadfence_system();
+  if (cd.has_lo) *reinterpret_cast<volatile unsigned long long*>(&cd.mail[cd.rank - 1]->pver[1]) = v;
+  if (cd.has_hi) *reinterpret_cast<volatile unsigned long long*>(&cd.mail[cd.rank + 1]->pver[0]) = v;
+}
+// every thread of a block of the SpMV: wait until both neighbours have published the current version of p
+__device__ __forceinline__ void p_wait(const CommDev& cd) {
+  if (threadIdx.x == 0) {
+    const unsigned long long v = *cd.pv;
+    const PeerMail* me = cd.mail[cd.rank];
+    const long long t0 = clock64();
+    if (cd.has_lo)
+      while (ld_vol(&me->pver[0]) < v) { if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; } }
+    if (cd.has_hi)
+      while (ld_vol(&me->pver[1]) < v) { if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; } }
+    __threadfence_system();
+  }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -35,7 +35,18 @@ struct SpmvArgs {
   i64 Nglob;         // global rows
   const T* x;        // x[r + off] addresses local row r (+halo), same indexing as y
   T* y;
+  const T* x_lo;     // slabs, peer path: the lower / upper neighbour's vector (owned start), read over NVLink
+  const T* x_hi;     //   instead of a local halo copy; null => local halo planes
+  i64 n_lo;          // rows owned by the lower neighbour
 };
+
+// element x[idx] for a local index that may fall into a neighbour's slab
+template <typename T>
+__device__ __forceinline__ T spmv_x(const SpmvArgs<T>& a, i64 idx) {
+  if (idx < 0 && a.x_lo) return __ldcg(a.x_lo + (a.n_lo + idx));
+  if (idx >= a.N && a.x_hi) return __ldcg(a.x_hi + (idx - a.N));
+  return a.x[idx];
+}
 
 // acc[e] for VW consecutive rows starting at r (vector path; r % VW == 0, r + VW <= N)
 template <typename T>
@@ -50,8 +61,10 @@ __device__ __forceinline__ void spmv_rows_vec(const SpmvArgs<T>& a, i64 r, T (&a
     vload_stream<T>(a.R + (i64)j * a.ld + r, rv);
     const i64 o = a.off[j];
     const i64 gc = g + o;
-    if (gc >= 0 && gc + VW <= a.Nglob) {
-      const T* xp = a.x + r + o;
+    const i64 li = r + o;
+    const bool local = (a.x_lo == nullptr && a.x_hi == nullptr) || (li >= 0 && li + VW <= a.N);
+    if (gc >= 0 && gc + VW <= a.Nglob && local) {
+      const T* xp = a.x + li;
       if ((o & (VW - 1)) == 0) {
         vload<T>(xp, xv);
       } else {
@@ -62,7 +75,7 @@ __device__ __forceinline__ void spmv_rows_vec(const SpmvArgs<T>& a, i64 r, T (&a
 #pragma unroll
       for (int e = 0; e < VW; ++e) {
         const i64 ge = gc + e;
-        xv[e] = (ge >= 0 && ge < a.Nglob) ? a.x[r + o + e] : (T)0;
+        xv[e] = (ge >= 0 && ge < a.Nglob) ? spmv_x<T>(a, li + e) : (T)0;
       }
     }
 #pragma unroll
@@ -76,16 +89,19 @@ __device__ __forceinline__ T spmv_row_scalar(const SpmvArgs<T>& a, i64 r) {
   const i64 g = a.row0 + r;
   for (int j = 0; j < a.nd; ++j) {
     const i64 gc = g + a.off[j];
-    if (gc >= 0 && gc < a.Nglob) acc = acc + a.R[(i64)j * a.ld + r] * a.x[r + a.off[j]];
+    if (gc >= 0 && gc < a.Nglob) acc = acc + a.R[(i64)j * a.ld + r] * spmv_x<T>(a, r + a.off[j]);
   }
   return acc;
 }
 
 // y = A x  and (DOT) partial sum of x.*y  -> out_dot[0]
+// cd.on: p's neighbour planes are read through peer pointers (after p_wait) and the partial of p.Ap is
+// published to every rank's mailbox instead of being written to out_dot.
 template <typename T, bool DOT>
 __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs, double* out_dot,
-                                                   const int* __restrict__ done_flag) {
+                                                   const int* __restrict__ done_flag, const __grid_constant__ CommDev cd) {
   if (done_flag && *done_flag) return;
+  if (cd.on) p_wait(cd);
   constexpr int VW = Vec<T>::W;
   double d[1] = {0.0};
   const i64 nvec = a.N / VW;
@@ -108,7 +124,10 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
     if (DOT) d[0] += (double)a.x[r] * (double)acc;
   }
   if (DOT) {
-    if (grid_sum<1>(d, rs) && threadIdx.x == 0) out_dot[0] = d[0];
+    if (grid_sum<1>(d, rs)) {
+      if (cd.on) mail_publish<1>(cd, d);
+      else if (threadIdx.x == 0) out_dot[0] = d[0];
+    }
   }
 }
 
@@ -134,7 +153,7 @@ struct CgState {
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __restrict__ b, T* __restrict__ r,
                                                       T* __restrict__ p, T* __restrict__ x_old, RedScratch rs,
-                                                      CgState* st) {
+                                                      CgState* st, const __grid_constant__ CommDev cd) {
   constexpr int VW = Vec<T>::W;
   double d[2] = {0.0, 0.0};
   const i64 nvec = a.N / VW;
@@ -168,16 +187,27 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
     p[row] = rv;
     if (x_old) x_old[row] = a.x[row];
   }
-  if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
-    st->bb = d[0];
-    st->rr = d[1];
+  if (grid_sum<2>(d, rs, cd.on != 0)) {
+    if (cd.on) {
+      mail_publish<2>(cd, d);
+      if (threadIdx.x == 0) p_publish(cd);      // p = r has been (re)written
+    } else if (threadIdx.x == 0) {
+      st->bb = d[0];
+      st->rr = d[1];
+    }
   }
 }
 
 // scalar epilogue of the init (after the optional all-reduce of bb, rr): tolerance rule of
 // argmin_x.jl:33-37 and the early exits of cg.jl:47,73-76
 template <typename T>
-__global__ void k_cg_init_fin(CgState* st) {
+__global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd) {
+  if (cd.on) {
+    double g[2];
+    mail_collect<2>(cd, g);
+    st->bb = g[0];
+    st->rr = g[1];
+  }
   const T nb = (T)sqrt(st->bb);
   const T nr = (T)sqrt(st->rr);
   st->iter = 0;
@@ -212,11 +242,17 @@ __global__ void k_cg_init_fin(CgState* st) {
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T* __restrict__ r,
                                                     const T* __restrict__ p, const T* __restrict__ Ap,
-                                                    RedScratch rs, CgState* st) {
+                                                    RedScratch rs, CgState* st, const __grid_constant__ CommDev cd) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
+  double pAp = st->pAp;
+  if (cd.on) {
+    double g[1];
+    mail_collect<1>(cd, g);
+    pAp = g[0];
+  }
   const T gamma = (T)st->rr;
-  const T alpha = gamma / (T)st->pAp;
+  const T alpha = gamma / (T)pAp;
   const bool bad = (alpha == (T)INFINITY) || (alpha < (T)0);   // cg.jl:91
   double d[1] = {0.0};
   if (!bad) {
@@ -246,13 +282,17 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
       r[row] = rv;
     }
   }
-  if (grid_sum<1>(d, rs) && threadIdx.x == 0) {
+  if (grid_sum<1>(d, rs)) {
     if (bad) {
-      st->flag = -2;          // "Matrix A in cg has to be positive definite"
-      st->iter = st->iter + 1;
-      st->relres = 0.0;       // resvec[lastIter] never written
-      st->done = 1;
-    } else {
+      if (threadIdx.x == 0) {
+        st->flag = -2;          // "Matrix A in cg has to be positive definite"
+        st->iter = st->iter + 1;
+        st->relres = 0.0;       // resvec[lastIter] never written
+        st->done = 1;
+      }
+    } else if (cd.on) {
+      mail_publish<1>(cd, d);
+    } else if (threadIdx.x == 0) {
       st->rr_new = d[0];
     }
   }
@@ -261,17 +301,23 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
 // convergence test + p = r + beta p          (cg.jl:100-114); the last block advances the state
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ r, T* __restrict__ p,
-                                                   RedScratch rs, CgState* st) {
+                                                   RedScratch rs, CgState* st, const __grid_constant__ CommDev cd) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
+  double rr_new = st->rr_new;
+  if (cd.on) {
+    double g[1];
+    mail_collect<1>(cd, g);
+    rr_new = g[0];
+  }
   const T nb = (T)sqrt(st->bb);
-  const T res = (T)sqrt(st->rr_new) / nb;
+  const T res = (T)sqrt(rr_new) / nb;
   const bool conv = res <= (T)st->tol;
   const int it = st->iter + 1;
   const bool last_it = it >= st->maxit;
   if (!conv && !last_it) {
     const T gamma = (T)st->rr;
-    const T beta = (T)st->rr_new / gamma;
+    const T beta = (T)rr_new / gamma;
     const i64 nvec = N / VW;
     for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
       const i64 row = iv * VW;
@@ -286,7 +332,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
          row += (i64)gridDim.x * blockDim.x)
       p[row] = r[row] + beta * p[row];
   }
-  if (last_block_ticket(rs.counter) && threadIdx.x == 0) {
+  if (last_block_ticket(rs.counter, cd.on != 0) && threadIdx.x == 0) {
     st->iter = it;
     st->relres = (double)res;
     if (conv) {
@@ -296,7 +342,9 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
       st->flag = -1;
       st->done = 1;
     } else {
-      st->rr = st->rr_new;
+      st->rr = rr_new;
+      st->rr_new = rr_new;
+      if (cd.on) p_publish(cd);               // p has been rewritten: release it to the neighbours
     }
   }
 }

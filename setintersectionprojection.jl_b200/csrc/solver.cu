@@ -148,6 +148,28 @@ struct sipb_ctx {
   ncclComm_t comm = nullptr;
   unsigned long long* d_gather = nullptr;   // [world][4] tie counts (all-gather target)
   unsigned long long* d_gather_local = nullptr;   // [4] this rank's tie totals per row block
+  // peer-memory path (CUDA IPC over NVLink): mailboxes + counters; see common.cuh
+  bool p2p = false;
+  PeerMail* d_mail = nullptr;                      // this rank's mailbox (exported)
+  void* peer_mail_base[kMaxRanks] = {nullptr};     // imported mappings (to close)
+  unsigned long long* d_seq_pv = nullptr;          // [0] seq, [1] pv
+  int* d_p2p_err = nullptr;
+  int* h_p2p_err = nullptr;
+  CommDev cd_on;                                   // descriptor with the peer path active
+  CommDev cd_off;
+  std::vector<void*> shared_bufs;                  // exported p vectors: freed at ctx teardown only (see DESIGN)
+  // all-gather `bytes` per rank through a device bounce buffer (set-up only)
+  int allgather_bytes(const void* mine, void* all, size_t bytes) {
+    char* d = nullptr;
+    SIPB_CUDA_CHECK(cudaMalloc(&d, bytes * (size_t)(world + 1)));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(d, mine, bytes, cudaMemcpyHostToDevice, stream));
+    nccl_calls++;
+    SIPB_NCCL_CHECK(NCCL(AllGather)(d, d + bytes, bytes, ncclChar, comm, stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(all, d + bytes, bytes * (size_t)world, cudaMemcpyDeviceToHost, stream));
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    cudaFree(d);
+    return SIPB_OK;
+  }
   int64_t nccl_calls = 0;
   // sum-all-reduce of `count` doubles in place on the stream (no-op on a single GPU)
   int allreduce(double* d, size_t count) {
@@ -588,6 +610,49 @@ struct Problem : sipb_problem {
   i64 maxM = 0;
   bool m_resident = false;
   SlabGeom sg;                // active when the ctx has a communicator with world > 1
+  // peer path: p lives in an IPC-exported allocation; the neighbours' p are mapped here
+  T* p_shared = nullptr;      // owned start of the exported p vector (null => pvec)
+  const T* p_lo = nullptr;    // lower / upper neighbour's p (owned start)
+  const T* p_hi = nullptr;
+  void* p_lo_base = nullptr;
+  void* p_hi_base = nullptr;
+  i64 n_lo = 0;
+  ~Problem() override {
+    if (p_lo_base) cudaIpcCloseMemHandle(p_lo_base);
+    if (p_hi_base) cudaIpcCloseMemHandle(p_hi_base);
+  }
+  T* pv() { return p_shared ? p_shared : pvec.p; }
+  // Export this rank's p vector and import the neighbours' (collective over all ranks).
+  int setup_peer_p() {
+    sipb_ctx* c = ctx;
+    if (!sg.on || !c->p2p) return SIPB_OK;
+    const size_t align = 256 / sizeof(T);
+    const size_t fpad = ((size_t)sg.plane + align - 1) / align * align;
+    void* base = nullptr;
+    const size_t bytes = (fpad + (size_t)N + (size_t)sg.plane) * sizeof(T);
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    int ok = cudaMalloc(&base, bytes) == cudaSuccess && cudaMemset(base, 0, bytes) == cudaSuccess &&
+             cudaIpcGetMemHandle(&mine, base) == cudaSuccess;
+    cudaGetLastError();
+    std::vector<cudaIpcMemHandle_t> all(c->world);
+    int rc = c->allgather_bytes(&mine, all.data(), sizeof(mine));
+    if (rc) return rc;
+    SIPB_REQUIRE(ok, SIPB_E_CUDA, "could not export the p vector for the peer path");
+    c->shared_bufs.push_back(base);
+    p_shared = reinterpret_cast<T*>(base) + fpad;
+    if (sg.has_lo) {
+      SIPB_CUDA_CHECK(cudaIpcOpenMemHandle(&p_lo_base, all[c->rank - 1], cudaIpcMemLazyEnablePeerAccess));
+      p_lo = reinterpret_cast<const T*>(p_lo_base) + fpad;
+      const i64 k0l = n[2] * (c->rank - 1) / c->world, k1l = n[2] * c->rank / c->world;
+      n_lo = sg.plane * (k1l - k0l);
+    }
+    if (sg.has_hi) {
+      SIPB_CUDA_CHECK(cudaIpcOpenMemHandle(&p_hi_base, all[c->rank + 1], cudaIpcMemLazyEnablePeerAccess));
+      p_hi = reinterpret_cast<const T*>(p_hi_base) + fpad;
+    }
+    return SIPB_OK;
+  }
   i64 Nglob;                  // global number of unknowns (== N on a single GPU)
   int create_error = SIPB_OK;
 
@@ -756,6 +821,7 @@ struct Problem : sipb_problem {
     if (sg.on)
       for (int64_t o : q_offs)
         SIPB_REQUIRE(std::llabs((long long)o) <= sg.plane, SIPB_E_UNSUPPORTED, "CDS offset wider than one halo plane");
+    { int rc = setup_peer_p(); if (rc) return rc; }
     finalized = true;
     return SIPB_OK;
   }
@@ -772,6 +838,13 @@ struct Problem : sipb_problem {
     a.R = Q.p; a.ld = ld; a.nd = (int)q_offs.size();
     for (int j = 0; j < a.nd; ++j) a.off[j] = q_offs[j];
     a.N = N; a.row0 = sg.on ? sg.plane * sg.k0 : 0; a.Nglob = Nglob; a.x = xin; a.y = yout;
+    a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
+    return a;
+  }
+  // SpMV on p with the neighbours' planes read through peer pointers
+  SpmvArgs<T> spmv_args_peer(T* yout) {
+    SpmvArgs<T> a = spmv_args(pv(), yout);
+    if (p_shared) { a.x_lo = p_lo; a.x_hi = p_hi; a.n_lo = n_lo; }
     return a;
   }
 
@@ -908,22 +981,27 @@ struct Problem : sipb_problem {
     if (parsdmm_it == 0)
       SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol, &h->tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
-    LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g, spmv_args(xv, nullptr), b, r.p, pvec.p, x_old_out, c->rs, c->d_cg);
-    if ((rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
-    LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg);
+    const bool peer = p_shared != nullptr;            // peer-memory collectives instead of NCCL inside the CG
+    const CommDev& cd = peer ? c->cd_on : c->cd_off;
+    T* pp = pv();
+    LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+    if (!peer && (rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
+    LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg, cd);
     int launched = 0;
     int batch = std::max(1, predicted);
     for (;;) {
       for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
-        if ((rc = exchange(pvec.p, sg.nloc(), true, true))) return rc;     // halo planes of p
-        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args(pvec.p, Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done);
-        if ((rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;
-        LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pvec.p, Ap.p, c->rs, c->d_cg);
-        if ((rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;
-        LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pvec.p, c->rs, c->d_cg);
+        if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
+        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
+        if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;
+        LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
+        if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;
+        LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pp, c->rs, c->d_cg, cd);
       }
       SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+      if (peer) SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_p2p_err, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      if (peer) SIPB_REQUIRE(*c->h_p2p_err == 0, SIPB_E_NCCL, "peer-memory collective timed out (a rank stopped participating)");
       if (h->done || launched >= max_iter) break;
       batch = std::max(2, launched / 2);
     }
@@ -1424,6 +1502,9 @@ int sipb_ctx_create(int device, sipb_ctx** out) {
   auto* c = new sipb_ctx();
   c->device = device;
   c->reset_accounting();
+  memset(&c->cd_off, 0, sizeof(CommDev));
+  memset(&c->cd_on, 0, sizeof(CommDev));
+  c->cd_off.world = 1;
   cudaDeviceProp prop;
   SIPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
@@ -1458,6 +1539,13 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_l1); cudaFreeHost(c->h_l1);
   cudaFree(c->d_sel); cudaFree(c->d_tie_counts);
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (c->peer_mail_base[q]) cudaIpcCloseMemHandle(c->peer_mail_base[q]);
+  for (void* b : c->shared_bufs) cudaFree(b);
+  if (c->d_mail) cudaFree(c->d_mail);
+  if (c->d_seq_pv) cudaFree(c->d_seq_pv);
+  if (c->d_p2p_err) cudaFree(c->d_p2p_err);
+  if (c->h_p2p_err) cudaFreeHost(c->h_p2p_err);
   if (c->d_gather) cudaFree(c->d_gather);
   if (c->d_gather_local) cudaFree(c->d_gather_local);
   if (c->comm) NCCL(CommDestroy)(c->comm);
@@ -1469,6 +1557,61 @@ int sipb_ctx_destroy(sipb_ctx* c) {
 int sipb_ctx_num_sms(sipb_ctx* c, int* out) {
   SIPB_REQUIRE(c && out, SIPB_E_INVALID, "null argument");
   *out = c->num_sms;
+  return SIPB_OK;
+}
+
+// Peer-memory set-up: export this rank's mailbox with CUDA IPC, import everybody else's.  Any failure (no P2P
+// between the devices, IPC unavailable, SIPB_P2P=0) turns the peer path off on ALL ranks (min-reduction of
+// the success flag) and the NCCL path is used instead.
+static int comm_setup_p2p(sipb_ctx* c) {
+  memset(&c->cd_off, 0, sizeof(CommDev));
+  memset(&c->cd_on, 0, sizeof(CommDev));
+  c->cd_off.rank = c->rank;
+  c->cd_off.world = c->world;
+  const char* env = getenv("SIPB_P2P");
+  int ok = (env && env[0] == '0') ? 0 : 1;
+  if (c->world > kMaxRanks) ok = 0;
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    ok = cudaMalloc(&c->d_mail, sizeof(PeerMail)) == cudaSuccess && cudaMemset(c->d_mail, 0, sizeof(PeerMail)) == cudaSuccess &&
+         cudaMalloc(&c->d_seq_pv, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+         cudaMemset(c->d_seq_pv, 0, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+         cudaMalloc(&c->d_p2p_err, sizeof(int)) == cudaSuccess && cudaMemset(c->d_p2p_err, 0, sizeof(int)) == cudaSuccess &&
+         cudaMallocHost(&c->h_p2p_err, sizeof(int)) == cudaSuccess &&
+         cudaIpcGetMemHandle(&mine, c->d_mail) == cudaSuccess;
+    cudaGetLastError();
+  }
+  std::vector<cudaIpcMemHandle_t> all(c->world);
+  int rc = c->allgather_bytes(&mine, all.data(), sizeof(mine));
+  if (rc) return rc;
+  c->cd_on = c->cd_off;
+  if (ok) {
+    for (int q = 0; q < c->world && ok; ++q) {
+      if (q == c->rank) { c->cd_on.mail[q] = c->d_mail; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); break; }
+      c->peer_mail_base[q] = ptr;
+      c->cd_on.mail[q] = reinterpret_cast<PeerMail*>(ptr);
+    }
+  }
+  // agree on the outcome
+  double flag = ok ? 0.0 : 1.0;
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(c->d_scal, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  rc = c->allreduce(c->d_scal, 1);
+  if (rc) return rc;
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(&flag, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_scal, 0, sizeof(double), c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  c->p2p = (flag == 0.0);
+  if (c->p2p) {
+    c->cd_on.on = 1;
+    c->cd_on.has_lo = c->rank > 0;
+    c->cd_on.has_hi = c->rank < c->world - 1;
+    c->cd_on.err = c->d_p2p_err;
+    c->cd_on.seq = c->d_seq_pv;
+    c->cd_on.pv = c->d_seq_pv + 1;
+  }
   return SIPB_OK;
 }
 
@@ -1501,12 +1644,17 @@ int sipb_comm_init(sipb_ctx* ctx, int rank, int world, const void* uid128) {
   if (rc) return rc;
   SIPB_CUDA_CHECK(cudaMemsetAsync(ctx->d_scal, 0, kScalSlots * sizeof(double), ctx->stream));
   SIPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  return SIPB_OK;
+  return comm_setup_p2p(ctx);
 }
 int sipb_comm_info(sipb_ctx* ctx, int* rank, int* world) {
   SIPB_REQUIRE(ctx && rank && world, SIPB_E_INVALID, "null argument");
   *rank = ctx->rank;
   *world = ctx->world;
+  return SIPB_OK;
+}
+int sipb_comm_peer_path(sipb_ctx* ctx, int* active) {
+  SIPB_REQUIRE(ctx && active, SIPB_E_INVALID, "null argument");
+  *active = ctx->p2p ? 1 : 0;
   return SIPB_OK;
 }
 /* plane range [k0,k1) of the slowest axis owned by `rank` (contiguous, sizes differ by at most one) */
@@ -1623,8 +1771,9 @@ static int cds_spmv_impl(sipb_ctx* c, int64_t N, int nd, const void* R, const in
   a.R = dR.p; a.ld = ld; a.nd = nd;
   for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
   a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
+  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
   LAUNCH(c, KC_SPMV, (k_spmv<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), a, c->rs, (double*)nullptr,
-         (const int*)nullptr);
+         (const int*)nullptr, c->cd_off);
   SIPB_CUDA_CHECK(cudaGetLastError());
   SIPB_CUDA_CHECK(cudaMemcpyAsync(y, dy.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
   SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1770,6 +1919,7 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   a.R = dR.p; a.ld = ld; a.nd = nd;
   for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
   a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
+  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
   const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
   cudaEvent_t e0, e1;
   SIPB_CUDA_CHECK(cudaEventCreate(&e0));
@@ -1778,7 +1928,7 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   for (int it = 0; it < warmup + reps; ++it) {
     if (flush_l2) LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), (i64)flush_elems, flush.p, (T)it);
     SIPB_CUDA_CHECK(cudaEventRecord(e0, c->stream));
-    LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, a, c->rs, c->d_scal, (const int*)nullptr);
+    LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, a, c->rs, c->d_scal, (const int*)nullptr, c->cd_off);
     SIPB_CUDA_CHECK(cudaEventRecord(e1, c->stream));
     SIPB_CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;

@@ -44,6 +44,15 @@ def active() -> bool:
     return bool(_state["active"])
 
 
+def peer_path() -> bool:
+    """True when the CG uses the peer-memory (CUDA IPC / NVLink) collectives instead of NCCL."""
+    if not active():
+        return False
+    flag = C.c_int(0)
+    _lib.check(_lib.load().sipb_comm_peer_path(_lib.ctx(_state["device"]), C.byref(flag)))
+    return bool(flag.value)
+
+
 def rank() -> int:
     return int(_state["rank"])
 

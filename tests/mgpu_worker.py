@@ -31,6 +31,8 @@ def main():
     dist.init_process_group("cpu:gloo,cuda:nccl")
     dd.init(rank, world, local)
     orc = pr.OracleAPI() if rank == 0 else None
+    if rank == 0:
+        print("[mgpu %d ranks] peer-memory path: %s" % (world, dd.peer_path()), flush=True)
     cases = [
         ("config2_f32", pr.spec_config2((24, 20, 17), np.float32), dict(maxit=60, evol_rel_tol=10 * np.finfo(np.float32).eps)),
         ("config2_f64", pr.spec_config2((16, 12, 11), np.float64), dict(maxit=80)),
