@@ -201,33 +201,29 @@ __device__ __forceinline__ void mail_publish(const CommDev& cd, const double (&v
   if (threadIdx.x == 0) *cd.seq = seq;
 }
 
-// Called by every thread of a block of the consuming kernel: sums the W partials in rank order.
+// Executed by ONE thread (a one-thread kernel between producer and consumer): sums the W partials in rank
+// order.  A single poller per GPU: an earlier version let thread 0 of every block of the consumer poll the
+// mailbox line, and the ~1200 pollers delayed the peers' NVLink writes to that very line by tens of us.
 template <int K>
-__device__ __forceinline__ void mail_collect(const CommDev& cd, double (&out)[K]) {
-  __shared__ double sh[K];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long seq = *cd.seq;
-    const int buf = (int)(seq & 1ull);
-    const PeerMail* me = cd.mail[cd.rank];
-    double acc[K];
+__device__ __forceinline__ void mail_collect(const CommDev& cd, double* out) {
+  const unsigned long long seq = *cd.seq;
+  const int buf = (int)(seq & 1ull);
+  const PeerMail* me = cd.mail[cd.rank];
+  double acc[K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) acc[i] = 0.0;
-    const long long t0 = clock64();
-    for (int q = 0; q < cd.world; ++q) {
-      while (ld_vol(&me->flag[buf][q]) != seq) {
-        if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; }
-      }
-      __threadfence_system();
-#pragma unroll
-      for (int i = 0; i < K; ++i) acc[i] += ld_vol(&me->val[buf][q][i]);
+  for (int i = 0; i < K; ++i) acc[i] = 0.0;
+  const long long t0 = clock64();
+  for (int q = 0; q < cd.world; ++q) {
+    while (ld_vol(&me->flag[buf][q]) != seq) {
+      __nanosleep(64);
+      if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; }
     }
+    __threadfence_system();
 #pragma unroll
-    for (int i = 0; i < K; ++i) sh[i] = acc[i];
+    for (int i = 0; i < K; ++i) acc[i] += ld_vol(&me->val[buf][q][i]);
   }
-  __syncthreads();
 #pragma unroll
-  for (int i = 0; i < K; ++i) out[i] = sh[i];
+  for (int i = 0; i < K; ++i) out[i] = acc[i];
 }
 
 // thread 0 of the LAST block of a kernel that rewrote p (every block fenced at system scope before its ticket)
@@ -238,16 +234,17 @@ __device__ __forceinline__ void p_publish(const CommDev& cd) {
   if (cd.has_lo) *reinterpret_cast<volatile unsigned long long*>(&cd.mail[cd.rank - 1]->pver[1]) = v;
   if (cd.has_hi) *reinterpret_cast<volatile unsigned long long*>(&cd.mail[cd.rank + 1]->pver[0]) = v;
 }
-// every thread of a block of the SpMV: wait until both neighbours have published the current version of p
-__device__ __forceinline__ void p_wait(const CommDev& cd) {
+// every thread of a block of the SpMV that touches a boundary plane: wait until that neighbour has
+// published the current version of p (only the few blocks that own boundary rows poll)
+__device__ __forceinline__ void p_wait(const CommDev& cd, bool need_lo, bool need_hi) {
   if (threadIdx.x == 0) {
     const unsigned long long v = *cd.pv;
     const PeerMail* me = cd.mail[cd.rank];
     const long long t0 = clock64();
-    if (cd.has_lo)
-      while (ld_vol(&me->pver[0]) < v) { if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; } }
-    if (cd.has_hi)
-      while (ld_vol(&me->pver[1]) < v) { if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; } }
+    if (need_lo && cd.has_lo)
+      while (ld_vol(&me->pver[0]) < v) { __nanosleep(64); if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; } }
+    if (need_hi && cd.has_hi)
+      while (ld_vol(&me->pver[1]) < v) { __nanosleep(64); if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; } }
     __threadfence_system();
   }
   __syncthreads();

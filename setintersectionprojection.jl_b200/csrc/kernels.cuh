@@ -40,6 +40,18 @@ struct SpmvArgs {
   i64 n_lo;          // rows owned by the lower neighbour
 };
 
+// true when the calling block (grid-stride over vector groups of W rows) owns rows within `halo` rows of either
+// end of the local slab — only those rows are read by the neighbours, so only these blocks need
+// system-scope fences / version waits on the peer path
+__device__ __forceinline__ void block_touches_ends(i64 N, i64 halo, int W, bool& lo, bool& hi) {
+  const i64 first = (i64)blockIdx.x * blockDim.x * W;
+  const i64 sweep = (i64)gridDim.x * blockDim.x * W;
+  const i64 nsweeps = first < N ? (N - 1 - first) / sweep : 0;
+  const i64 last = min(N, first + nsweeps * sweep + (i64)blockDim.x * W);
+  lo = first < halo;
+  hi = last > N - halo;
+}
+
 // element x[idx] for a local index that may fall into a neighbour's slab
 template <typename T>
 __device__ __forceinline__ T spmv_x(const SpmvArgs<T>& a, i64 idx) {
@@ -101,10 +113,18 @@ template <typename T, bool DOT>
 __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs, double* out_dot,
                                                    const int* __restrict__ done_flag, const __grid_constant__ CommDev cd) {
   if (done_flag && *done_flag) return;
-  if (cd.on) p_wait(cd);
   constexpr int VW = Vec<T>::W;
   double d[1] = {0.0};
   const i64 nvec = a.N / VW;
+  if (cd.on) {
+    // rows within one plane (= max |offset|) of the slab ends read the neighbours' p: only the blocks that
+    // own such rows wait for the neighbours' version flag
+    i64 halo = 0;
+    for (int j = 0; j < a.nd; ++j) halo = max(halo, a.off[j] < 0 ? -a.off[j] : a.off[j]);
+    bool lo, hi;
+    block_touches_ends(a.N, halo, VW, lo, hi);
+    p_wait(cd, lo, hi);
+  }
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 r = iv * VW;
     T acc[VW];
@@ -187,7 +207,15 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
     p[row] = rv;
     if (x_old) x_old[row] = a.x[row];
   }
-  if (grid_sum<2>(d, rs, cd.on != 0)) {
+  bool sys = false;
+  if (cd.on) {
+    i64 halo = 0;
+    for (int j = 0; j < a.nd; ++j) halo = max(halo, a.off[j] < 0 ? -a.off[j] : a.off[j]);
+    bool lo, hi;
+    block_touches_ends(a.N, halo, VW, lo, hi);
+    sys = lo || hi;            // only boundary rows of p are read by the neighbours
+  }
+  if (grid_sum<2>(d, rs, sys)) {
     if (cd.on) {
       mail_publish<2>(cd, d);
       if (threadIdx.x == 0) p_publish(cd);      // p = r has been (re)written
@@ -198,16 +226,18 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
   }
 }
 
+// one-thread collector of a peer-memory reduction (between the producing and the consuming kernel)
+template <int K>
+__global__ void k_mail_collect(const __grid_constant__ CommDev cd, double* dst, const int* done_flag) {
+  if (done_flag && *done_flag) return;
+  mail_collect<K>(cd, dst);
+}
+
 // scalar epilogue of the init (after the optional all-reduce of bb, rr): tolerance rule of
 // argmin_x.jl:33-37 and the early exits of cg.jl:47,73-76
 template <typename T>
 __global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd) {
-  if (cd.on) {
-    double g[2];
-    mail_collect<2>(cd, g);
-    st->bb = g[0];
-    st->rr = g[1];
-  }
+  if (cd.on) mail_collect<2>(cd, &st->bb);       // bb, rr are adjacent
   const T nb = (T)sqrt(st->bb);
   const T nr = (T)sqrt(st->rr);
   st->iter = 0;
@@ -245,12 +275,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
                                                     RedScratch rs, CgState* st, const __grid_constant__ CommDev cd) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
-  double pAp = st->pAp;
-  if (cd.on) {
-    double g[1];
-    mail_collect<1>(cd, g);
-    pAp = g[0];
-  }
+  const double pAp = st->pAp;       // peer path: made global by k_mail_collect
   const T gamma = (T)st->rr;
   const T alpha = gamma / (T)pAp;
   const bool bad = (alpha == (T)INFINITY) || (alpha < (T)0);   // cg.jl:91
@@ -301,15 +326,11 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
 // convergence test + p = r + beta p          (cg.jl:100-114); the last block advances the state
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ r, T* __restrict__ p,
-                                                   RedScratch rs, CgState* st, const __grid_constant__ CommDev cd) {
+                                                   RedScratch rs, CgState* st, const __grid_constant__ CommDev cd,
+                                                   i64 halo) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
-  double rr_new = st->rr_new;
-  if (cd.on) {
-    double g[1];
-    mail_collect<1>(cd, g);
-    rr_new = g[0];
-  }
+  const double rr_new = st->rr_new;   // peer path: made global by k_mail_collect
   const T nb = (T)sqrt(st->bb);
   const T res = (T)sqrt(rr_new) / nb;
   const bool conv = res <= (T)st->tol;
@@ -332,7 +353,13 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
          row += (i64)gridDim.x * blockDim.x)
       p[row] = r[row] + beta * p[row];
   }
-  if (last_block_ticket(rs.counter, cd.on != 0) && threadIdx.x == 0) {
+  bool sys = false;
+  if (cd.on) {
+    bool lo, hi;
+    block_touches_ends(N, halo, VW, lo, hi);
+    sys = lo || hi;              // only boundary rows of p are read by the neighbours
+  }
+  if (last_block_ticket(rs.counter, sys) && threadIdx.x == 0) {
     st->iter = it;
     st->relres = (double)res;
     if (conv) {

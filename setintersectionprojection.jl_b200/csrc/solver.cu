@@ -993,10 +993,12 @@ struct Problem : sipb_problem {
       for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
         if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
         LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
-        if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;
+        if (peer) LAUNCH1(c, KC_PARAMS, k_mail_collect<1>, cd, &c->d_cg->pAp, (const int*)&c->d_cg->done);
+        else if ((rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;
         LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
-        if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;
-        LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pp, c->rs, c->d_cg, cd);
+        if (peer) LAUNCH1(c, KC_PARAMS, k_mail_collect<1>, cd, &c->d_cg->rr_new, (const int*)&c->d_cg->done);
+        else if ((rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;
+        LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0);
       }
       SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
       if (peer) SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_p2p_err, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
