@@ -913,7 +913,7 @@ __device__ __forceinline__ void l1_newton_step(L1State* st, double C, double S) 
 // rank-local (C, S) and k_l1_step runs after the all-reduce.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict__ v, RedScratch rs, L1State* st,
-                                                      int fused) {
+                                                      int fused, const __grid_constant__ CommDev cd) {
   if (st->done) return;
   const double theta = st->theta;
   double d[2] = {0.0, 0.0};
@@ -932,9 +932,12 @@ __global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict
     const double a = (double)t_abs<T>(v[r]);
     if (a > theta) { d[0] += 1.0; d[1] += a; }
   }
-  if (grid_sum<2>(d, rs) && threadIdx.x == 0) {
-    if (fused) l1_newton_step(st, d[0], d[1]);
-    else { st->C = d[0]; st->S = d[1]; }
+  if (grid_sum<2>(d, rs)) {
+    if (cd.on) mail_publish<2>(cd, d);          // slabs, peer path: partial (C, S) to every rank's mailbox
+    else if (threadIdx.x == 0) {
+      if (fused) l1_newton_step(st, d[0], d[1]);
+      else { st->C = d[0]; st->S = d[1]; }
+    }
   }
 }
 __global__ void k_l1_step(L1State* st) {

@@ -880,10 +880,12 @@ struct Problem : sipb_problem {
       for (;;) {
         const int batch = (launched == 0) ? (sg.on ? 4 : 6) : 8;
         for (int b = 0; b < batch; ++b) {
-          LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for((M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused);
+          const bool peer = sg.on && c->p2p;
+          LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for((M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused,
+                 peer ? c->cd_on : c->cd_off);
           if (!fused) {
-            rc = c->allreduce(&c->d_l1->C, 2);
-            if (rc) return rc;
+            if (peer) LAUNCH1(c, KC_PARAMS, k_mail_collect<2>, c->cd_on, &c->d_l1->C, (const int*)&c->d_l1->done);
+            else if ((rc = c->allreduce(&c->d_l1->C, 2))) return rc;
             LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1);
           }
         }
