@@ -40,8 +40,13 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+WORKLOAD = {"name": "config2"}
+
+
 def workload(n, TF=np.float32, nz=None):
     import problems as pr
+    if WORKLOAD["name"] == "config3":      # BASELINE configs[2]: bounds ∩ TV-l1 ∩ cardinality(TV), k = 5 % of the rows
+        return pr.spec_config3((n, n, nz or n), TF)
     return pr.spec_config2((n, n, nz or n), TF)
 
 
@@ -287,8 +292,10 @@ def run_device(args, rank, world, local_rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dev_s_max / args.steps,
         "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "3D %dx%dx%d Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1], "
-                               "test_scaling_3D-style)" % (n, n, nz), "grid": [n, n, nz],
+        "config": {"workload": ("3D %dx%dx%d Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1], "
+                                "test_scaling_3D-style)" if args.workload == "config2" else
+                                "3D %dx%dx%d Float32 bounds ∩ TV l1 ∩ cardinality of the discrete gradient (BASELINE configs[2])")
+                               % (n, n, nz), "grid": [n, n, nz],
                    "value_units": "PARSDMM iterations/s" if units == 1 else
                                   "slab-iterations/s = %d x PARSDMM iterations/s (one %d^3 slab per GPU)" % (units, n),
                    "step": "one full PARSDMM projection to the reference's stopping rules",
@@ -319,9 +326,12 @@ def main():
     ap.add_argument("--n", type=int, default=200, help="grid width (BASELINE configs[1] uses 200)")
     ap.add_argument("--cpu-iters", type=int, default=4, help="PARSDMM iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
+                    help="config2 = BASELINE configs[1] (default, the bench line); config3 = configs[2] (TV cardinality)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = n x n x (n*N) grid (one n^3 slab per GPU), strong = fixed n^3 grid")
     args = ap.parse_args()
+    WORKLOAD["name"] = args.workload
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":
         run_reference(args, rank, world)
