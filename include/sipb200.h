@@ -99,7 +99,8 @@ typedef struct sipb_options {
   int32_t return_ly;            /* 1: copy l and y back to the host arrays                      */
   int32_t resident_io;          /* 1: benchmark mode — m is taken from the device buffer left by the previous
                                    solve of this problem and x/l/y are not copied back (no H2D/D2H at all)   */
-  int32_t reserved;
+  int32_t warm_resident;        /* 1 (with zero_ini_guess == 0): the start vectors x, l, y already sit in the problem's
+                                   device buffers (put there by sipb_problem_warm_from); nothing is uploaded for them */
 } sipb_options;
 
 #define SIPB_N_PHASES 7         /* TimerOutputs sections of PARSDMM.jl:40,100,105,113,152,163,229 */
@@ -176,6 +177,20 @@ int sipb_problem_finalize(sipb_problem* pb);
 int sipb_problem_num_q_offsets(sipb_problem* pb, int* nd);
 int sipb_problem_q_offsets(sipb_problem* pb, int64_t* out);     /* Q_offsets, reference order */
 int sipb_problem_destroy(sipb_problem* pb);
+
+/* Multilevel warm start on the device: nearest-neighbour resampling of the coarse problem's x, l, y into the
+ * fine problem's device buffers.  Replaces the Interpolations.jl calls of PARSDMM_multi_level.jl:61-67 and
+ * interpolate_y_l.jl:32-91.  Each segment resamples one column-major box: `vec` = -1 for x, or the set index
+ * for l and y (both are resampled); offsets are element offsets inside that vector; the sampling positions
+ * are range(1, stop=n_src, length=n_dst) per axis with half-way positions rounded up. */
+typedef struct sipb_resample_seg {
+  int32_t vec;
+  int32_t reserved;
+  int64_t src_off, dst_off;
+  int64_t src_shape[3];
+  int64_t dst_shape[3];
+} sipb_resample_seg;
+int sipb_problem_warm_from(sipb_problem* fine, sipb_problem* coarse, const sipb_resample_seg* segs, int nseg);
 
 /* ---- the solve: replaces PARSDMM(m,AtA,TD_OP,set_Prop,P_sub,comp_grid,options[,x,l,y])
  *      (PARSDMM.jl:25-258).  m: host TF[N_model]; x: host TF[N] in/out (start guess when

@@ -45,7 +45,12 @@ class Options(C.Structure):
                 ("evol_rel_tol", C.c_double), ("feas_tol", C.c_double), ("obj_tol", C.c_double),
                 ("gamma_ini", C.c_double), ("rho_ini", C.POINTER(C.c_double)),
                 ("fixed_iterations", C.c_int32), ("return_ly", C.c_int32), ("resident_io", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("warm_resident", C.c_int32)]
+
+
+class ResampleSeg(C.Structure):
+    _fields_ = [("vec", C.c_int32), ("reserved", C.c_int32), ("src_off", C.c_int64), ("dst_off", C.c_int64),
+                ("src_shape", C.c_int64 * 3), ("dst_shape", C.c_int64 * 3)]
 
 
 class Log(C.Structure):
@@ -84,6 +89,7 @@ SYMBOLS = [
     ("sipb_problem_num_q_offsets", _I, [_VP, _PI]),
     ("sipb_problem_q_offsets", _I, [_VP, _PI64]),
     ("sipb_problem_destroy", _I, [_VP]),
+    ("sipb_problem_warm_from", _I, [_VP, _VP, C.POINTER(ResampleSeg), _I]),
     ("sipb_solve", _I, [_VP, _VP, _VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(Options), C.POINTER(Log)]),
     ("sipb_cds_spmv", _I, [_VP, _I, _I64, _I, _VP, _PI64, _VP, _VP]),
     ("sipb_cds_cg", _I, [_VP, _I, _I64, _I, _VP, _PI64, _VP, _VP, _D, _I, _PI, _PD, _PI]),

@@ -570,6 +570,7 @@ struct sipb_problem {
   virtual int finalize() = 0;
   virtual int solve(const void* m, void* x, void* const* l, void* const* y, const sipb_options* o, sipb_log* log) = 0;
   virtual int q_offsets(std::vector<int64_t>& out) = 0;
+  virtual int warm_from(sipb_problem* coarse, const sipb_resample_seg* segs, int nseg) = 0;
 };
 
 namespace sipb {
@@ -829,6 +830,45 @@ struct Problem : sipb_problem {
   int q_offsets(std::vector<int64_t>& out) override {
     SIPB_REQUIRE(finalized, SIPB_E_STATE, "problem not finalized");
     out = q_offs;
+    return SIPB_OK;
+  }
+
+  // device-side nearest-neighbour warm start from a coarser problem (PARSDMM_multi_level.jl:61-82)
+  int warm_from(sipb_problem* coarse_, const sipb_resample_seg* segs, int nseg) override {
+    SIPB_REQUIRE(finalized && coarse_ && segs, SIPB_E_STATE, "warm_from needs two finalized problems");
+    SIPB_REQUIRE(coarse_->dtype == dtype && coarse_->ctx == ctx, SIPB_E_INVALID, "problems differ in dtype / context");
+    SIPB_REQUIRE(!sg.on, SIPB_E_UNSUPPORTED, "device warm starts are single-GPU (multilevel levels are small)");
+    Problem<T>* co = static_cast<Problem<T>*>(coarse_);
+    SIPB_REQUIRE(co->finalized && co->sets.size() == sets.size(), SIPB_E_INVALID, "level problems have different sets");
+    sipb_ctx* c = ctx;
+    for (int q = 0; q < nseg; ++q) {
+      const sipb_resample_seg& g = segs[q];
+      i64 ns = 1, nd = 1;
+      for (int a = 0; a < 3; ++a) {
+        SIPB_REQUIRE(g.src_shape[a] >= 1 && g.dst_shape[a] >= 1, SIPB_E_INVALID, "bad resampling shape");
+        ns *= g.src_shape[a];
+        nd *= g.dst_shape[a];
+      }
+      const T* srcs[2];
+      T* dsts[2];
+      int nv = 0;
+      i64 src_len, dst_len;
+      if (g.vec < 0) {
+        srcs[0] = co->x.p; dsts[0] = x.p; nv = 1; src_len = co->N; dst_len = N;
+      } else {
+        SIPB_REQUIRE(g.vec < (int)sets.size(), SIPB_E_INVALID, "set index out of range");
+        srcs[0] = co->sets[g.vec]->l.p; dsts[0] = sets[g.vec]->l.p;
+        srcs[1] = co->sets[g.vec]->y.p; dsts[1] = sets[g.vec]->y.p;
+        nv = 2; src_len = co->sets[g.vec]->M; dst_len = sets[g.vec]->M;
+      }
+      SIPB_REQUIRE(g.src_off >= 0 && g.src_off + ns <= src_len && g.dst_off >= 0 && g.dst_off + nd <= dst_len,
+                   SIPB_E_INVALID, "resampling segment outside its vector");
+      for (int v = 0; v < nv; ++v)
+        LAUNCH(c, KC_OP_APPLY, k_resample_nn<T>, c->grid_for(nd), srcs[v] + g.src_off, dsts[v] + g.dst_off, g.src_shape[0],
+               g.src_shape[1], g.src_shape[2], g.dst_shape[0], g.dst_shape[1], g.dst_shape[2]);
+    }
+    SIPB_CUDA_CHECK(cudaGetLastError());
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return SIPB_OK;
   }
 
@@ -1101,7 +1141,8 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   SIPB_REQUIRE(maxit >= 1, SIPB_E_INVALID, "maxit must be >= 1");
   SIPB_REQUIRE(o->n_rho_ini == 1 || o->n_rho_ini == p, SIPB_E_INVALID, "rho_ini must have 1 or p entries");
   SIPB_REQUIRE(o->rho_update_frequency >= 1, SIPB_E_INVALID, "rho_update_frequency must be >= 1");
-  if (!o->zero_ini_guess) SIPB_REQUIRE(l_h && y_h, SIPB_E_INVALID, "warm start needs l and y");
+  const bool warm_res = o->warm_resident != 0 && !o->zero_ini_guess;
+  if (!o->zero_ini_guess && !warm_res) SIPB_REQUIRE(l_h && y_h, SIPB_E_INVALID, "warm start needs l and y");
   if (o->return_ly) SIPB_REQUIRE(l_h && y_h, SIPB_E_INVALID, "return_ly needs l and y");
   log->p = p; log->pp = pp; log->iters = 0; log->feas_rows = 1; log->stopped_feasible = 0;
   log->h2d_bytes = 0; log->d2h_bytes = 0;
@@ -1188,7 +1229,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       SIPB_CUDA_CHECK(cudaMemsetAsync(S->y.p, 0, S->M * sizeof(T), c->stream));
       SIPB_CUDA_CHECK(cudaMemsetAsync(S->l.p, 0, S->M * sizeof(T), c->stream));
     }
-  } else {
+  } else if (!warm_res) {
     SIPB_CUDA_CHECK(cudaMemcpyAsync(x.p, x_h, N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     log->h2d_bytes += N * sizeof(T);
     for (int i = 0; i < p; ++i) {
@@ -1724,6 +1765,11 @@ int sipb_problem_q_offsets(sipb_problem* pb, int64_t* out) {
   if (rc) return rc;
   for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
   return SIPB_OK;
+}
+int sipb_problem_warm_from(sipb_problem* fine, sipb_problem* coarse, const sipb_resample_seg* segs, int nseg) {
+  SIPB_REQUIRE(fine && coarse && segs && nseg >= 0, SIPB_E_INVALID, "null argument");
+  SIPB_CUDA_CHECK(cudaSetDevice(fine->ctx->device));
+  return fine->warm_from(coarse, segs, nseg);
 }
 int sipb_problem_destroy(sipb_problem* pb) {
   if (pb) {

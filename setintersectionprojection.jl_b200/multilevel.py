@@ -15,9 +15,13 @@ import copy
 
 import numpy as np
 
+import ctypes as C
+
+from . import _lib
+from . import distributed as dd
 from .constraints import setup_constraints
 from .precompute import PARSDMM_precompute_distribute
-from .solver import PARSDMM
+from .solver import PARSDMM, device_problem
 from .types import compgrid
 
 
@@ -109,9 +113,48 @@ def interpolate_y_l(l, y, set_Prop_levels, comp_grid_levels, dim3, i):
     return l, y
 
 
+def _pad3(shape):
+    return tuple(int(v) for v in shape) + (1,) * (3 - len(shape))
+
+
+def warm_start_segments(set_Prop_levels, comp_grid_levels, dim3, i):
+    """The boxes `interpolate_y_l` (and the x up-sampling) resample between level i+1 and level i, as
+    (vector id, src offset, dst offset, src shape, dst shape); vector id -1 is x, otherwise the set index."""
+    coarse, fine = tuple(comp_grid_levels[i + 1].n), tuple(comp_grid_levels[i].n)
+    nax = 3 if dim3 else 2
+    segs = [(-1, 0, 0, coarse[:nax], fine[:nax])]
+    for j in range(len(set_Prop_levels[i].tag)):
+        if set_Prop_levels[i].tag[j][1] in ("TV", "D2D", "D3D"):
+            so = do = 0
+            for axis in range(nax):
+                sc = tuple(v - 1 if a == axis else v for a, v in enumerate(coarse[:nax]))
+                sf = tuple(v - 1 if a == axis else v for a, v in enumerate(fine[:nax]))
+                segs.append((j, so, do, sc, sf))
+                so += int(np.prod(sc))
+                do += int(np.prod(sf))
+        else:
+            src = tuple(set_Prop_levels[i + 1].TD_n[j])
+            shrink = tuple(a - b for a, b in zip(fine, set_Prop_levels[i].TD_n[j]))
+            segs.append((j, 0, 0, src, tuple(a - b for a, b in zip(fine, shrink))))
+    return segs
+
+
+def _device_warm_start(dev_fine, dev_coarse, segs):
+    arr = (_lib.ResampleSeg * len(segs))()
+    for q, (vec, so, do, ss, ds) in enumerate(segs):
+        arr[q].vec, arr[q].src_off, arr[q].dst_off = vec, so, do
+        arr[q].src_shape[:] = _pad3(ss)
+        arr[q].dst_shape[:] = _pad3(ds)
+    _lib.check(_lib.load().sipb_problem_warm_from(dev_fine.handle, dev_coarse.handle, arr, len(segs)))
+
+
 def PARSDMM_multi_level(m, TD_OP_levels, AtA_levels, P_sub_levels, set_Prop_levels, comp_grid_levels, options,
-                        x_ini=None, l_ini=None, y_ini=None):
-    """-> (x, log_PARSDMM, l, y) on the finest grid (PARSDMM_multi_level.jl:8-19,88)."""
+                        x_ini=None, l_ini=None, y_ini=None, *, device_resample=True):
+    """-> (x, log_PARSDMM, l, y) on the finest grid (PARSDMM_multi_level.jl:8-19,88).
+
+    With `device_resample` (default, single GPU) x, l, y never leave the GPU between levels: a resampling
+    kernel writes the warm start straight into the finer problem's device buffers; only the finest level's
+    x, l, y are copied back.  Otherwise the host-side `resample_nn` / `interpolate_y_l` are used."""
     TF = m.dtype.type
     n_levels = len(TD_OP_levels)
     rho_orig = copy.deepcopy(options.rho_ini)
@@ -120,16 +163,27 @@ def PARSDMM_multi_level(m, TD_OP_levels, AtA_levels, P_sub_levels, set_Prop_leve
     m_levels = [m] + [resample_nn(m, fine, comp_grid_levels[k].n) for k in range(1, n_levels)]
     logs = []
     x, l, y = x_ini, l_ini, y_ini
+    on_device = bool(device_resample) and not dd.active() and not options.Minkowski
     try:
         for k in range(n_levels - 1, -1, -1):
+            kw = {}
             if k == n_levels - 1:
                 options.zero_ini_guess = True                                    # coarsest level: zero guess (:53)
+            elif on_device:
+                devs = [device_problem(m.dtype, AtA_levels[q], TD_OP_levels[q], set_Prop_levels[q], P_sub_levels[q],
+                                       comp_grid_levels[q], options) for q in (k, k + 1)]
+                _device_warm_start(devs[0], devs[1], warm_start_segments(set_Prop_levels, comp_grid_levels, dim3, k))
+                options.zero_ini_guess = False                                   # :81
+                x, l, y = None, None, None
+                kw = dict(warm_resident=True)
             else:
                 x = resample_nn(x, comp_grid_levels[k + 1].n, comp_grid_levels[k].n)       # :61-67
                 l, y = interpolate_y_l(l, y, set_Prop_levels, comp_grid_levels, dim3, k)   # :74
                 options.zero_ini_guess = False                                   # :81
+            if on_device and k > 0:
+                kw["return_ly"] = False                                          # l, y stay on the device
             x, log, l, y = PARSDMM(m_levels[k], AtA_levels[k], TD_OP_levels[k], set_Prop_levels[k], P_sub_levels[k],
-                                   comp_grid_levels[k], options, x, l, y)
+                                   comp_grid_levels[k], options, x, l, y, **kw)
             options.rho_ini = [TF(v) for v in log.rho[-1, :]]                    # :57 / :83
             logs.append(log)
     finally:

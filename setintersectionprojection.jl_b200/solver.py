@@ -116,22 +116,9 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
     return dev
 
 
-def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
-            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False, gather_result=True):
-    """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
-    Returns (x, log_PARSDMM, l, y).
-
-    Multi-GPU slabs (after `distributed.init`, 3-D problems): every rank passes the same global `m`
-    (or its own slab of it) and receives the global `x` (host-side gather) unless `gather_result=False`;
-    `l`, `y` are this rank's slabs (see `distributed.gather_td`)."""
-    if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
-        raise TypeError("m must be a Float32/Float64 vector")
-    TF = m.dtype.type
-    if np.iscomplexobj(m) or (x is not None and np.iscomplexobj(x)):
-        raise ValueError("input for PARSDMM is not real")                                  # PARSDMM.jl:50-52
-    if getattr(options, "parallel", False):
-        raise NotImplementedError("options.parallel=true is rejected on the device path (use slab decomposition)")
-    convert_options(options, TF)                                                           # PARSDMM.jl:43
+def device_problem(m_dtype, AtA, TD_OP, set_Prop, P_sub, comp_grid, options):
+    """The cached device problem of (AtA, TD_OP, P_sub, ...) — built and uploaded on first use."""
+    TF = np.dtype(m_dtype).type
     key = _problem_key(TF, TD_OP, P_sub, set_Prop, options)
     dev = getattr(AtA, "_device", None)
     if dev is None or dev.key != key:
@@ -140,6 +127,30 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
             AtA._device = dev
         except AttributeError:
             pass
+    return dev
+
+
+def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
+            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False, gather_result=True,
+            warm_resident=False):
+    """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
+    Returns (x, log_PARSDMM, l, y).
+
+    Multi-GPU slabs (after `distributed.init`, 3-D problems): every rank passes the same global `m`
+    (or its own slab of it) and receives the global `x` (host-side gather) unless `gather_result=False`;
+    `l`, `y` are this rank's slabs (see `distributed.gather_td`).
+
+    `warm_resident=True` (with options.zero_ini_guess == False): the start vectors were already placed in the
+    device buffers by `sipb_problem_warm_from` (multilevel driver); x, l, y are not uploaded."""
+    if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
+        raise TypeError("m must be a Float32/Float64 vector")
+    TF = m.dtype.type
+    if np.iscomplexobj(m) or (x is not None and np.iscomplexobj(x)):
+        raise ValueError("input for PARSDMM is not real")                                  # PARSDMM.jl:50-52
+    if getattr(options, "parallel", False):
+        raise NotImplementedError("options.parallel=true is rejected on the device path (use slab decomposition)")
+    convert_options(options, TF)                                                           # PARSDMM.jl:43
+    dev = device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options)
     p, pp, N = dev.p, dev.pp, dev.N
     m = np.ascontiguousarray(m)
     slab = getattr(dev, "slab", None)
@@ -168,7 +179,9 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
             else:
                 raise ValueError("x has the wrong length")
     have_ly = l is not None and len(l) > 0 and y is not None and len(y) > 0
-    if not zero_guess and not have_ly:
+    if warm_resident and not zero_guess and not return_ly:
+        have_ly, l, y = False, None, None
+    if not zero_guess and not have_ly and not warm_resident:
         # PARSDMM_initialize.jl:120-127 allocates zeros when l / y are empty
         l = [np.zeros(r, dtype=TF) for r in dev.rows]
         y = [np.zeros(r, dtype=TF) for r in dev.rows]
@@ -199,6 +212,7 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
     o.rho_ini = rho_ini.ctypes.data_as(C.POINTER(C.c_double))
     o.fixed_iterations, o.return_ly = int(fixed_iterations), int(bool(return_ly and have_ly))
     o.resident_io = int(bool(resident_io))      # benchmark mode: no H2D/D2H (see include/sipb200.h)
+    o.warm_resident = int(bool(warm_resident and not zero_guess))
 
     arr = {
         "set_feasibility": np.zeros((maxit + 2, max(pp, 1))), "r_dual": np.zeros((maxit, p)),

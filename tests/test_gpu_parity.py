@@ -387,7 +387,10 @@ def test_parsdmm_multilevel(sip, orc, which):
             res.append(om.PARSDMM_multi_level(spec["m"].copy(), *lv[:5], opt))
         else:
             lv = sip.setup_multi_level_PARSDMM(spec["m"], 3, 2, cg, cons, opt)
-            res.append(sip.PARSDMM_multi_level(spec["m"].copy(), *lv[:5], opt))
+            res.append(sip.PARSDMM_multi_level(spec["m"].copy(), *lv[:5], opt))                      # device resampling
+            host = sip.PARSDMM_multi_level(spec["m"].copy(), *lv[:5], opt, device_resample=False)   # host resampling
+            assert np.array_equal(host[0], res[-1][0]) and host[1].timing["level_iterations"] == res[-1][1].timing["level_iterations"]
+            assert all(np.array_equal(a, b) for a, b in zip(host[3], res[-1][3]))
         assert [float(v) for v in opt.rho_ini] == ([1.0, 1000.0, 1000.0, 1000.0, 1.0] if which == "config4_bounds" else [10.0])
     (xo, lo, ll, yy), (xs, ls, l2, y2) = res
     assert [len(g.obj) for g in lo.levels] == ls.timing["level_iterations"]
