@@ -269,8 +269,14 @@ def run_device(args, rank, world, local_rank):
             avg_ms = ms_k / cnt_k
             ach = alg / (avg_ms * 1e-3) / 1e9
             tot_ms = sum(v[1] for v in kernels.values())
+            traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+            tpath = os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")
+            if os.path.exists(tpath) and world == 1 and args.workload == "config2":
+                tj = json.load(open(tpath))
+                if tj.get("grid") == [n, n, nz]:
+                    traffic = tj["dram_bytes_per_launch"]
             roof = {"bound": "hbm", "kernel": "cds_spmv_dot", "achieved": ach, "peak": peak, "peak_source": which,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "algorithmic_bytes_per_launch": alg,
+                    "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
                     "avg_launch_ms": avg_ms, "launches": cnt_k, "share_of_kernel_time": ms_k / tot_ms if tot_ms else None}
 
     if rank != 0:
