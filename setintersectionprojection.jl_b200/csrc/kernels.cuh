@@ -583,33 +583,16 @@ struct YlArgs {
   int do_snapshot;   // overwrite the snapshots (l_hat_0, y_0, s_0, l_0)
 };
 
-// W == k * (16 bytes / sizeof(T)): k aligned 16-byte accesses; otherwise element-wise (tails)
 template <typename T, int W> __device__ __forceinline__ void load_n(const T* p, T (&v)[W]) {
-  constexpr int VW = Vec<T>::W;
-  if constexpr (W >= VW && W % VW == 0) {
-#pragma unroll
-    for (int h = 0; h < W / VW; ++h) {
-      T t[VW];
-      vload<T>(p + h * VW, t);
-#pragma unroll
-      for (int e = 0; e < VW; ++e) v[h * VW + e] = t[e];
-    }
-  } else {
+  if constexpr (W == Vec<T>::W) vload<T>(p, v);
+  else {
 #pragma unroll
     for (int e = 0; e < W; ++e) v[e] = p[e];
   }
 }
 template <typename T, int W> __device__ __forceinline__ void store_n(T* p, const T (&v)[W]) {
-  constexpr int VW = Vec<T>::W;
-  if constexpr (W >= VW && W % VW == 0) {
-#pragma unroll
-    for (int h = 0; h < W / VW; ++h) {
-      T t[VW];
-#pragma unroll
-      for (int e = 0; e < VW; ++e) t[e] = v[h * VW + e];
-      vstore<T>(p + h * VW, t);
-    }
-  } else {
+  if constexpr (W == Vec<T>::W) vstore<T>(p, v);
+  else {
 #pragma unroll
     for (int e = 0; e < W; ++e) p[e] = v[e];
   }
@@ -724,14 +707,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlAr
   double d[NR];
 #pragma unroll
   for (int i = 0; i < NR; ++i) d[i] = 0.0;
-  // rows per thread and grid-stride step: without the snapshot streams there are registers to spare, and two
-  // 16-byte vectors per array double the bytes in flight of this latency-bound kernel
-  constexpr int G = (ADAPT || MODE == 2) ? VW : 2 * VW;
   const i64 M = a.op.rows;
-  const i64 nvec = M / G;
+  const i64 nvec = M / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x)
-    yl_rows<T, MODE, ADAPT, G>(a, P, iv * G, d);
-  for (i64 r = nvec * G + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x)
+    yl_rows<T, MODE, ADAPT, VW>(a, P, iv * VW, d);
+  for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x)
     yl_rows<T, MODE, ADAPT, 1>(a, P, r, d);
   if (grid_sum<NR>(d, rs) && threadIdx.x == 0) {
     out[0] = d[0];

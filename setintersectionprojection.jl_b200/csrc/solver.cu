@@ -1335,14 +1335,13 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       ya.do_snapshot = fuse_adapt ? 1 : 0;
       const int base = s * kSlotPerSet;
       const int g = c->grid_for((S.M + Vec<T>::W - 1) / Vec<T>::W);
-      const int g2 = c->grid_for((S.M + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W));      // kernels with two vectors per thread
       if (proj_is_elementwise(S.desc.set_kind)) {
         ya.want_feas = want_feas ? 1 : 0;
         if (fuse_adapt) LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, true>), g, ya, c->rs, c->d_scal + base);
-        else LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, false>), g2, ya, c->rs, c->d_scal + base);
+        else LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, false>), g, ya, c->rs, c->d_scal + base);
       } else {
         ya.want_feas = 0;
-        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), g2, ya, c->rs, c->d_scal + base + 10);
+        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), g, ya, c->rs, c->d_scal + base + 10);
         int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
         if (rc) return rc;
         ya.dyn = S.pp_y.p;
