@@ -48,6 +48,9 @@ extern "C" {
 #define SIPB_SET_CARDINALITY   5   /* project_cardinality!.jl:3-21 (vector mode) */
 #define SIPB_SET_PROX_L1       6   /* prox_l1!.jl:8-10 (set_type "prox_l1", get_projector.jl:21-27) */
 #define SIPB_SET_DISTANCE      7   /* prox_l2s!.jl:3-6: the 1/2||x-m||^2 term (PARSDMM_initialize.jl:64-71) */
+#define SIPB_SET_BOUNDS_FIBER  8   /* project_bounds!.jl:38-88: per-fiber bounds, max then min, bounds indexed along the fiber */
+#define SIPB_SET_CARD_FIBER    9   /* project_cardinality!.jl:23-113: k largest magnitudes of every fiber (stable ties) */
+#define SIPB_SET_KIND_MAX      9
 
 /* transform-domain operator kinds (get_TD_operator.jl:12-95, get_discrete_Grad.jl) */
 #define SIPB_OP_IDENTITY 0
@@ -76,8 +79,11 @@ typedef struct sipb_set_desc {
   double  min;             /* scalar lower bound / annulus sigma_min                           */
   double  max;             /* scalar upper bound / l1 tau / l2 sigma / prox_l1 rho             */
   int64_t k;               /* cardinality                                                      */
-  const void* min_vec;     /* host TF[M] for SIPB_SET_BOUNDS_VECTOR, else NULL                 */
+  const void* min_vec;     /* host TF[M] for SIPB_SET_BOUNDS_VECTOR, TF[td_n[fiber_axis]] for ..._FIBER, else NULL */
   const void* max_vec;
+  int32_t fiber_axis;      /* fiber modes (app_mode ("fiber","x"|"y"|"z")): 0, 1 or 2 — axis of the transform-domain grid */
+  int32_t reserved;
+  int64_t td_n[3];         /* fiber modes: set_Prop.TD_n[i], the transform-domain grid (third entry 1 in 2-D)  */
 } sipb_set_desc;
 
 /* Mirror of PARSDMM_options (SetIntersectionProjection.jl:110-128) after convert_options!. */

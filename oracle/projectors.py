@@ -132,3 +132,43 @@ def prox_l1(x: np.ndarray, rho) -> np.ndarray:
     thr = TF(TF(1) / TF(rho))          # 1 ./ rho : Int / TF -> TF
     x[:] = np.sign(x) * np.maximum(TF(0.0), np.abs(x) - thr)
     return x
+
+
+def _fiber_axis(ndim: int, direction: str) -> int:
+    """2-D: "x" = columns x[:,i] (axis 0), "z" = rows x[i,:] (axis 1); 3-D: "x","y","z" = axes 0,1,2."""
+    if ndim == 2:
+        return {"x": 0, "z": 1}[direction]
+    return {"x": 0, "y": 1, "z": 2}[direction]
+
+
+def project_bounds_fiber(x: np.ndarray, LB, UB, TD_n, mode) -> np.ndarray:
+    """project_bounds!.jl:38-88 (matrix :38-55, tensor fiber modes :57-88): every fiber along `mode[2]`
+    gets x .= min.(max.(x, LB), UB) — max first — with LB/UB indexed along the fiber."""
+    TF = x.dtype.type
+    if mode[0] != "fiber":
+        raise NotImplementedError("bound constraints per slice of a tensor currently not implemented, yet...")   # :83
+    X = x.reshape(tuple(TD_n), order="F")
+    ax = _fiber_axis(X.ndim, mode[1])
+    shp = [1] * X.ndim
+    shp[ax] = X.shape[ax]
+    lb = np.asarray(LB, dtype=TF).reshape(shp)
+    ub = np.asarray(UB, dtype=TF).reshape(shp)
+    X[...] = np.minimum(np.maximum(X, lb), ub)
+    x[:] = X.ravel(order="F")
+    return x
+
+
+def project_cardinality_fiber(x: np.ndarray, k: int, TD_n, mode) -> np.ndarray:
+    """project_cardinality!.jl:23-62 (matrix) and :64-113 (tensor, fiber modes): in every fiber keep the k
+    largest magnitudes (stable sortperm => lower index inside the fiber wins ties), zero the rest."""
+    TF = x.dtype.type
+    if mode[0] != "fiber":
+        raise NotImplementedError("oracle: slice modes are outside the hot path")
+    X = x.reshape(tuple(TD_n), order="F")
+    ax = _fiber_axis(X.ndim, mode[1])
+    Xm = np.moveaxis(X, ax, 0)                       # fibers are now columns Xm[:, ...]
+    order = np.argsort(-np.abs(Xm), axis=0, kind="stable")
+    drop = order[int(k):]
+    np.put_along_axis(Xm, drop, TF(0.0), axis=0)
+    x[:] = X.ravel(order="F")
+    return x

@@ -24,9 +24,14 @@ def get_projector(constraint, comp_grid, A, TD_n, TF):
     st = constraint.set_type
     if constraint.TD_OP in SPECIAL_OPERATORS:
         raise NotImplementedError("oracle: JOLI transform operators are outside the CDS hot path")
-    if constraint.app_mode[0] not in ("matrix", "tensor"):
-        raise NotImplementedError("oracle: fiber/slice application modes are outside the hot path")
     cmin, cmax = constraint.min, constraint.max
+    if constraint.app_mode[0] not in ("matrix", "tensor"):
+        mode = tuple(constraint.app_mode)
+        if st == "bounds":                                                   # get_projector.jl:16
+            return lambda x: proj.project_bounds_fiber(x, cmin, cmax, TD_n, mode)
+        if st == "cardinality":                                              # get_projector.jl:96
+            return lambda x: proj.project_cardinality_fiber(x, int(cmax), TD_n, mode)
+        raise NotImplementedError("oracle: fiber/slice modes exist for bounds and cardinality only")
     if st == "bounds":
         return lambda x: proj.project_bounds(x, cmin, cmax)                 # :10
     if st == "prox_l1":

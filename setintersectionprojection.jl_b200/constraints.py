@@ -26,8 +26,11 @@ _REJECTED = {
 class Projector:
     """Device projector functor: P(v) mutates v in place and returns it, like the Julia `!` functions."""
 
-    def __init__(self, set_kind: int, TF, lo=0.0, hi=0.0, k=0, lo_vec=None, hi_vec=None, name=""):
+    def __init__(self, set_kind: int, TF, lo=0.0, hi=0.0, k=0, lo_vec=None, hi_vec=None, name="", fiber_axis=0,
+                 td_n=None):
         self.set_kind = set_kind
+        self.fiber_axis = int(fiber_axis)
+        self.td_n = None if td_n is None else tuple(int(v) for v in td_n) + (1,) * (3 - len(td_n))
         self.TF = np.dtype(TF).type
         self.min = lo
         self.max = hi
@@ -44,12 +47,18 @@ class Projector:
         d.k = self.k
         d.min_vec = self.min_vec.ctypes.data if self.min_vec is not None else None
         d.max_vec = self.max_vec.ctypes.data if self.max_vec is not None else None
+        d.fiber_axis = self.fiber_axis
+        if self.td_n is not None:
+            d.td_n[:] = self.td_n
         return d
 
     def __call__(self, v: np.ndarray) -> np.ndarray:
         if not isinstance(v, np.ndarray) or v.dtype != self.TF or not v.flags.c_contiguous:
             raise TypeError("projector expects a contiguous %s vector" % self.TF.__name__)
-        if self.min_vec is not None and self.min_vec.size != v.size:
+        if self.td_n is not None:
+            if int(np.prod(self.td_n)) != v.size:
+                raise ValueError("input has %d entries, the transform-domain grid %s" % (v.size, self.td_n))
+        elif self.min_vec is not None and self.min_vec.size != v.size:
             raise ValueError("vector bounds have %d entries, input has %d" % (self.min_vec.size, v.size))
         d = self.descriptor()
         lib = _lib.load()
@@ -67,9 +76,24 @@ def get_projector(constraint, comp_grid, special_operator_list, A, TD_n, TF) -> 
         raise NotImplementedError(_REJECTED[st] + " and are rejected (no CPU fallback)")
     if constraint.TD_OP in special_operator_list:
         raise NotImplementedError("JOLI transform operators (%s) are outside the device CDS path" % constraint.TD_OP)
-    if constraint.app_mode[0] not in ("matrix", "tensor"):
-        raise NotImplementedError("fiber/slice application modes are not on the device path yet")
     lo, hi = constraint.min, constraint.max
+    if constraint.app_mode[0] not in ("matrix", "tensor"):
+        # fiber application modes (get_projector.jl:12-18,92-98; project_bounds!.jl:38-88,
+        # project_cardinality!.jl:23-113); slice modes are rejected
+        if constraint.app_mode[0] != "fiber" or st not in ("bounds", "cardinality"):
+            raise NotImplementedError("only the fiber application mode of bounds and cardinality is on the device path")
+        if constraint.TD_OP in ("TV", "D2D", "D3D"):
+            raise ValueError("fiber modes need a single-block operator (the TV output is not a grid)")
+        nd = len(TD_n)
+        try:
+            axis = ({"x": 0, "z": 1} if nd == 2 else {"x": 0, "y": 1, "z": 2})[constraint.app_mode[1]]
+        except KeyError:
+            raise ValueError("fiber direction %r is not valid for a %d-D grid" % (constraint.app_mode[1], nd))
+        if st == "bounds":
+            if np.ndim(lo) == 0 or np.size(lo) != TD_n[axis] or np.size(hi) != TD_n[axis]:
+                raise ValueError("fiber bounds need one (min, max) pair per point of the fiber (%d)" % TD_n[axis])
+            return Projector(_lib.SET_BOUNDS_FIBER, TF, lo_vec=lo, hi_vec=hi, name="bounds(fiber)", fiber_axis=axis, td_n=TD_n)
+        return Projector(_lib.SET_CARD_FIBER, TF, k=int(hi), name="cardinality(fiber)", fiber_axis=axis, td_n=TD_n)
     if st == "bounds":
         if np.ndim(lo) == 0:
             return Projector(_lib.SET_BOUNDS_SCALAR, TF, lo, hi, name="bounds")          # :10

@@ -482,6 +482,8 @@ struct ProjDev {
   const T* lo_vec;   // vector bounds
   const T* hi_vec;
   const T* m;        // distance term: the vector being projected
+  unsigned td[3];    // fiber bounds: transform-domain grid
+  int fiber_axis;
   T rho;             // distance term / prox_l1: current rho
   // parameters produced by the reduction passes:
   T theta;           // l1 soft threshold (0 => identity)
@@ -521,6 +523,15 @@ __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
       return t_max<T>(P.lo, t_min<T>(v, P.hi));
     case SIPB_SET_BOUNDS_VECTOR:   // min then max          project_bounds!.jl:21-22
       return t_max<T>(P.lo_vec[r], t_min<T>(v, P.hi_vec[r]));
+    case SIPB_SET_BOUNDS_FIBER: {  // x[:,i] .= min.(max.(x[:,i],LB),UB): max first, bounds follow the fiber coordinate
+      const unsigned q = (unsigned)r;
+      unsigned c = q % P.td[0];
+      if (P.fiber_axis == 1) c = (q / P.td[0]) % P.td[1];
+      else if (P.fiber_axis == 2) c = q / (P.td[0] * P.td[1]);
+      return t_min<T>(t_max<T>(v, P.lo_vec[c]), P.hi_vec[c]);       // project_bounds!.jl:46,50,65-77
+    }
+    case SIPB_SET_CARD_FIBER:      // already projected in place by k_card_fiber_* (pass-through)
+      return v;
     case SIPB_SET_DISTANCE: {      // (x*rho + m) / (rho + 1.0) in Float64   prox_l2s!.jl:4
       const T num = v * P.rho + P.m[r];
       return (T)((double)num / ((double)P.rho + 1.0));
@@ -546,7 +557,8 @@ __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
 }
 
 __host__ __device__ __forceinline__ bool proj_is_elementwise(int kind) {
-  return kind == SIPB_SET_BOUNDS_SCALAR || kind == SIPB_SET_BOUNDS_VECTOR || kind == SIPB_SET_DISTANCE ||
+  return kind == SIPB_SET_BOUNDS_SCALAR || kind == SIPB_SET_BOUNDS_VECTOR || kind == SIPB_SET_BOUNDS_FIBER ||
+         kind == SIPB_SET_DISTANCE ||
          kind == SIPB_SET_PROX_L1;
 }
 
@@ -1019,6 +1031,88 @@ __global__ void __launch_bounds__(kThreads) k_resample_nn(const T* __restrict__ 
     const i64 i = q % nd0, t = q / nd0, j = t % nd1, kk = t / nd1;
     const i64 si = nn_src_index(i, ns0, nd0), sj = nn_src_index(j, ns1, nd1), sk = nn_src_index(kk, ns2, nd2);
     dst[q] = src[si + ns0 * (sj + ns1 * sk)];
+  }
+}
+
+// =============================================================================================
+// per-fiber cardinality (project_cardinality!.jl:23-113, fiber modes): in every fiber of the
+// transform-domain grid keep the k largest magnitudes (stable sortperm: among equal magnitudes the lower
+// index inside the fiber wins) and zero the rest — a bit-serial radix select, in place.
+// =============================================================================================
+template <typename T> struct KeyBits;
+template <> struct KeyBits<float> { static constexpr int n = 31; };
+template <> struct KeyBits<double> { static constexpr int n = 63; };
+
+// fibers along the fastest axis are contiguous: one warp per fiber, lanes strided over the fiber
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_card_fiber_contig(T* __restrict__ v, i64 nfib, unsigned L, long long k) {
+  const int lane = threadIdx.x & 31;
+  const i64 wpg = (i64)gridDim.x * (blockDim.x >> 5);
+  for (i64 f = (i64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); f < nfib; f += wpg) {
+    T* fib = v + f * (i64)L;
+    if (k >= (long long)L) continue;
+    if (k <= 0) {
+      for (unsigned e = lane; e < L; e += 32) fib[e] = (T)0;
+      continue;
+    }
+    unsigned long long prefix = 0ull;          // decided high bits of the k-th largest key
+    unsigned long long need = (unsigned long long)k;   // rank still to locate among the keys matching the prefix
+    for (int b = KeyBits<T>::n - 1; b >= 0; --b) {
+      unsigned cnt = 0;
+      for (unsigned e = lane; e < L; e += 32) {
+        const unsigned long long key = mag_key<T>(fib[e]);
+        cnt += ((key >> b) == ((prefix << 1) | 1ull)) ? 1u : 0u;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      if ((unsigned long long)cnt >= need) prefix = (prefix << 1) | 1ull;
+      else { need -= cnt; prefix = prefix << 1; }
+    }
+    // prefix = threshold key; `need` = how many of the ties survive (lowest indices first)
+    unsigned long long seen = 0ull;
+    for (unsigned e0 = 0; e0 < L; e0 += 32) {
+      const unsigned e = e0 + lane;
+      const unsigned long long key = e < L ? mag_key<T>(fib[e]) : 0ull;
+      const bool tie = e < L && key == prefix;
+      const unsigned bal = __ballot_sync(0xffffffffu, tie);
+      const unsigned before = __popc(bal & ((1u << lane) - 1u));
+      if (e < L && (key < prefix || (tie && seen + before >= need))) fib[e] = (T)0;
+      seen += __popc(bal);
+    }
+  }
+}
+
+// fibers along a slower axis: one thread per fiber, so that the lanes of a warp (neighbouring fibers) read
+// neighbouring addresses at every step of the walk along the fiber
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_card_fiber_strided(T* __restrict__ v, unsigned d0, unsigned d1, unsigned d2,
+                                                                 int axis, long long k) {
+  const unsigned L = axis == 1 ? d1 : d2;
+  const i64 stride = axis == 1 ? (i64)d0 : (i64)d0 * d1;
+  const i64 nfib = axis == 1 ? (i64)d0 * d2 : (i64)d0 * d1;
+  for (i64 f = (i64)blockIdx.x * blockDim.x + threadIdx.x; f < nfib; f += (i64)gridDim.x * blockDim.x) {
+    T* fib = axis == 1 ? v + (f % d0) + (i64)d0 * d1 * (f / d0) : v + f;
+    if (k >= (long long)L) continue;
+    if (k <= 0) {
+      for (unsigned e = 0; e < L; ++e) fib[e * stride] = (T)0;
+      continue;
+    }
+    unsigned long long prefix = 0ull, need = (unsigned long long)k;
+    for (int b = KeyBits<T>::n - 1; b >= 0; --b) {
+      unsigned cnt = 0;
+      for (unsigned e = 0; e < L; ++e) cnt += ((mag_key<T>(fib[e * stride]) >> b) == ((prefix << 1) | 1ull)) ? 1u : 0u;
+      if ((unsigned long long)cnt >= need) prefix = (prefix << 1) | 1ull;
+      else { need -= cnt; prefix = prefix << 1; }
+    }
+    unsigned long long seen = 0ull;
+    for (unsigned e = 0; e < L; ++e) {
+      const unsigned long long key = mag_key<T>(fib[e * stride]);
+      if (key < prefix) fib[e * stride] = (T)0;
+      else if (key == prefix) {
+        if (seen >= need) fib[e * stride] = (T)0;
+        ++seen;
+      }
+    }
   }
 }
 

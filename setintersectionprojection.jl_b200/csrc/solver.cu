@@ -725,9 +725,16 @@ struct Problem : sipb_problem {
   int add_set(const sipb_set_desc* d) override {
     SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
     SIPB_REQUIRE((int)sets.size() < kMaxSets, SIPB_E_UNSUPPORTED, "too many sets");
-    SIPB_REQUIRE(d->set_kind >= SIPB_SET_BOUNDS_SCALAR && d->set_kind <= SIPB_SET_DISTANCE, SIPB_E_UNSUPPORTED,
-                 "set type is outside the device hot path (rank, nuclear, subspace, histogram and fiber/slice "
-                 "modes are rejected)");
+    SIPB_REQUIRE(d->set_kind >= SIPB_SET_BOUNDS_SCALAR && d->set_kind <= SIPB_SET_KIND_MAX, SIPB_E_UNSUPPORTED,
+                 "set type is outside the device hot path (rank, nuclear, subspace, histogram and slice modes are "
+                 "rejected)");
+    const bool fiber = d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_CARD_FIBER;
+    if (fiber) {
+      SIPB_REQUIRE(!sg.on && !minkowski, SIPB_E_UNSUPPORTED, "fiber modes are single-GPU, non-Minkowski");
+      SIPB_REQUIRE(d->fiber_axis >= 0 && d->fiber_axis < ndim, SIPB_E_INVALID, "fiber axis outside the grid");
+      SIPB_REQUIRE(d->op_kind != SIPB_OP_TV, SIPB_E_INVALID,
+                   "fiber modes need a single-block operator (the TV output is not a grid)");
+    }
     SIPB_REQUIRE(minkowski ? d->block_mode != SIPB_BLOCK_PLAIN : d->block_mode == SIPB_BLOCK_PLAIN, SIPB_E_INVALID,
                  "block_mode inconsistent with the Minkowski flag of the problem");
     if (d->set_kind == SIPB_SET_L1) SIPB_REQUIRE(d->max > 0.0, SIPB_E_INVALID, "Radius of L1 ball is negative");
@@ -751,12 +758,16 @@ struct Problem : sipb_problem {
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->warm.p, 0, 2 * sizeof(double), ctx->stream));
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->pp_y.p, 0, sizeof(ProjParams<T>), ctx->stream));
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->pp_f.p, 0, sizeof(ProjParams<T>), ctx->stream));
-    if (d->set_kind == SIPB_SET_BOUNDS_VECTOR) {
+    if (fiber)
+      SIPB_REQUIRE(d->td_n[0] * d->td_n[1] * d->td_n[2] == S->M && d->td_n[0] >= 1 && d->td_n[1] >= 1 && d->td_n[2] >= 1,
+                   SIPB_E_INVALID, "td_n does not match the rows of the operator");
+    if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER) {
       SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
-      SIPB_CUDA_CHECK(S->lo_vec.alloc((size_t)S->M));
-      SIPB_CUDA_CHECK(S->hi_vec.alloc((size_t)S->M));
-      SIPB_CUDA_CHECK(cudaMemcpyAsync(S->lo_vec.p, d->min_vec, S->M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
-      SIPB_CUDA_CHECK(cudaMemcpyAsync(S->hi_vec.p, d->max_vec, S->M * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+      const size_t nb = d->set_kind == SIPB_SET_BOUNDS_VECTOR ? (size_t)S->M : (size_t)d->td_n[d->fiber_axis];
+      SIPB_CUDA_CHECK(S->lo_vec.alloc(nb));
+      SIPB_CUDA_CHECK(S->hi_vec.alloc(nb));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(S->lo_vec.p, d->min_vec, nb * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(S->hi_vec.p, d->max_vec, nb * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
       SIPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
       S->desc.min_vec = S->desc.max_vec = nullptr;
     }
@@ -897,9 +908,24 @@ struct Problem : sipb_problem {
     P.lo_vec = S.lo_vec.p;
     P.hi_vec = S.hi_vec.p;
     P.m = m.p;
+    for (int a = 0; a < 3; ++a) P.td[a] = (unsigned)std::max<int64_t>(S.desc.td_n[a], 1);
+    P.fiber_axis = S.desc.fiber_axis;
     P.rho = (S.desc.set_kind == SIPB_SET_PROX_L1) ? (T)S.desc.max : rho_dist;
     P.theta = (T)-1; P.scale = (T)1; P.fill = (T)NAN; P.key_thr = 0ull; P.keep_all = 1; P.keep_none = 0;
     return P;
+  }
+
+  // per-fiber cardinality in place (project_cardinality!.jl:23-113)
+  void card_fiber(const sipb_set_desc& d, T* v) {
+    sipb_ctx* c = ctx;
+    const unsigned d0 = (unsigned)d.td_n[0], d1 = (unsigned)d.td_n[1], d2 = (unsigned)d.td_n[2];
+    if (d.fiber_axis == 0) {
+      const i64 nfib = (i64)d1 * d2;
+      LAUNCH(c, KC_TIES, k_card_fiber_contig<T>, c->grid_for(nfib * 32), v, nfib, d0, (long long)d.k);
+    } else {
+      const i64 nfib = d.fiber_axis == 1 ? (i64)d0 * d2 : (i64)d0 * d1;
+      LAUNCH(c, KC_TIES, k_card_fiber_strided<T>, c->grid_for(nfib), v, d0, d1, d2, d.fiber_axis, (long long)d.k);
+    }
   }
 
   // Computes the dynamic parameters of a reduction-type projector for the vector `v` whose stats
@@ -935,6 +961,8 @@ struct Problem : sipb_problem {
         if (c->h_l1->done || launched >= 256) break;
       }
       LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
+    } else if (kind == SIPB_SET_CARD_FIBER) {
+      card_fiber(S.desc, v);            // projects every fiber in place; the apply pass is then a pass-through
     } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {
       LAUNCH1(c, KC_PARAMS, k_l2_params<T>, stats, kind, S.desc.min, S.desc.max, (double)Mg, pp);
     } else if (kind == SIPB_SET_CARDINALITY) {
@@ -994,7 +1022,7 @@ struct Problem : sipb_problem {
     LAUNCH(c, KC_VEC_STATS, k_vec_stats<T>, c->grid_for(M), M, sv, c->rs, c->d_scal + stat_slot);
     T* vec = sv;
     const T* ref = nullptr;
-    if (S.desc.set_kind == SIPB_SET_CARDINALITY) {   // ties are resolved on a scratch copy
+    if (S.desc.set_kind == SIPB_SET_CARDINALITY || S.desc.set_kind == SIPB_SET_CARD_FIBER) {   // in-place work on a scratch copy
       SIPB_CUDA_CHECK(cudaMemcpyAsync(tmp.p, sv, M * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
       vec = tmp.p;
       ref = sv;
@@ -1873,12 +1901,13 @@ static int project_impl(sipb_ctx* c, const sipb_set_desc* d, int64_t M, void* v,
   SIPB_CUDA_CHECK(cudaMemsetAsync(S.warm.p, 0, 2 * sizeof(double), c->stream));
   SIPB_CUDA_CHECK(cudaMemsetAsync(S.pp_f.p, 0, sizeof(ProjParams<T>), c->stream));
   SIPB_CUDA_CHECK(cudaMemcpyAsync(S.s.p, v, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-  if (d->set_kind == SIPB_SET_BOUNDS_VECTOR) {
+  if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER) {
     SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
-    SIPB_CUDA_CHECK(S.lo_vec.alloc((size_t)M));
-    SIPB_CUDA_CHECK(S.hi_vec.alloc((size_t)M));
-    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.lo_vec.p, d->min_vec, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.hi_vec.p, d->max_vec, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    const size_t nb = d->set_kind == SIPB_SET_BOUNDS_VECTOR ? (size_t)M : (size_t)d->td_n[d->fiber_axis];
+    SIPB_CUDA_CHECK(S.lo_vec.alloc(nb));
+    SIPB_CUDA_CHECK(S.hi_vec.alloc(nb));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.lo_vec.p, d->min_vec, nb * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.hi_vec.p, d->max_vec, nb * sizeof(T), cudaMemcpyHostToDevice, c->stream));
   }
   if (d->set_kind == SIPB_SET_DISTANCE) {
     SIPB_REQUIRE(m_vec, SIPB_E_INVALID, "distance prox needs m");
@@ -2021,8 +2050,13 @@ int sipb_cds_cg(sipb_ctx* ctx, int dtype, int64_t N, int nd, const void* R, cons
 }
 int sipb_project(sipb_ctx* ctx, int dtype, const sipb_set_desc* desc, int64_t M, void* v, const void* m_vec) {
   SIPB_REQUIRE(ctx && desc && v, SIPB_E_INVALID, "null argument");
-  SIPB_REQUIRE(desc->set_kind >= SIPB_SET_BOUNDS_SCALAR && desc->set_kind <= SIPB_SET_DISTANCE, SIPB_E_UNSUPPORTED,
+  SIPB_REQUIRE(desc->set_kind >= SIPB_SET_BOUNDS_SCALAR && desc->set_kind <= SIPB_SET_KIND_MAX, SIPB_E_UNSUPPORTED,
                "set type is outside the device hot path");
+  if (desc->set_kind == SIPB_SET_BOUNDS_FIBER || desc->set_kind == SIPB_SET_CARD_FIBER) {
+    SIPB_REQUIRE(desc->fiber_axis >= 0 && desc->fiber_axis < 3 && desc->td_n[0] >= 1 && desc->td_n[1] >= 1 &&
+                     desc->td_n[2] >= 1 && desc->td_n[0] * desc->td_n[1] * desc->td_n[2] == M,
+                 SIPB_E_INVALID, "td_n / fiber_axis do not match the vector");
+  }
   SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
   DISPATCH(dtype, project_impl, ctx, desc, M, v, m_vec);
 }

@@ -38,7 +38,7 @@ def _problem_key(TF, TD_OP, P_sub, set_Prop, options):
     for P in P_sub:
         items.append((P.set_kind, float(P.min) if np.ndim(P.min) == 0 else None,
                       float(P.max) if np.ndim(P.max) == 0 else None, P.k,
-                      None if P.min_vec is None else P.min_vec.ctypes.data))
+                      None if P.min_vec is None else P.min_vec.ctypes.data, P.fiber_axis, P.td_n))
     items.append(tuple(bool(v) for v in set_Prop.ncvx))
     items.append((dd.rank(), dd.world()) if dd.active() else None)
     return tuple(items)

@@ -446,3 +446,73 @@ def test_full_size_config2_properties(sip):
         feas = np.linalg.norm(ps.astype(np.float64) - s) / np.linalg.norm(s.astype(np.float64))
         assert feas <= 1.5 * float(opt.feas_tol), (i, feas)
     assert abs(log.obj[-1] - 0.5 * np.linalg.norm(x.astype(np.float64) - spec["m"]) ** 2) <= 1e-3 * log.obj[-1]
+
+
+# ---------------------------------------------------------------------------------------------
+# fiber application modes: project_bounds!.jl:38-88, project_cardinality!.jl:23-113
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+@pytest.mark.parametrize("n,kind", [((50, 37), "identity"), ((50, 37), "D_x"), ((50, 37), "D_z"), ((23, 17, 11), "identity"),
+                                    ((23, 17, 11), "D_y"), ((23, 17, 11), "D_z")])
+def test_fiber_projectors_match_oracle(sip, orc, TF, n, kind):
+    rng = np.random.default_rng(11)
+    dirs = ("x", "z") if len(n) == 2 else ("x", "y", "z")
+    for direction in dirs:
+        for st in ("cardinality", "bounds"):
+            P = {}
+            for api in (orc, sip):
+                cg = api.compgrid((1.0,) * len(n), n)
+                TD_n = api.get_TD_operator(cg, kind, TF)[3]
+                ax = dirs.index(direction)
+                if st == "bounds":
+                    lo = np.sort(rng.standard_normal(TD_n[ax])) - 0.5 if api is orc else lo
+                    hi = lo + np.abs(rng.standard_normal(TD_n[ax])) if api is orc else hi
+                    cons = [api.set_definitions("bounds", kind, lo.copy(), hi.copy(), ("fiber", direction))]
+                else:
+                    cons = [api.set_definitions("cardinality", kind, 0, 3, ("fiber", direction))]
+                P[api] = api.setup_constraints(cons, cg, TF)[0][0]
+            M = int(np.prod(TD_n))
+            v = np.round(rng.standard_normal(M) * 2, 1).astype(TF)        # rounded: plenty of exact ties
+            got, want = P[sip](v.copy()), P[orc](v.copy())
+            assert np.array_equal(got, want), (kind, direction, st)
+            if st == "cardinality":
+                G = got.reshape(TD_n, order="F")
+                assert np.all(np.count_nonzero(G, axis=dirs.index(direction)) <= 3)
+
+
+def test_fiber_cardinality_counts_like_reference_test(sip):
+    """test_setup_constraints.jl:108-135: exactly k non-zeros per column / row for random data."""
+    n = (50, 100)
+    X = np.random.default_rng(3).standard_normal(n)
+    for direction, k, axis in (("x", 7, 0), ("z", 11, 1)):
+        cons = [sip.set_definitions("cardinality", "identity", 0, k, ("fiber", direction))]
+        P = sip.setup_constraints(cons, sip.compgrid((1.0, 1.0), n), np.float64)[0][0]
+        Y = P(X.ravel(order="F").copy()).reshape(n, order="F")
+        assert np.all(np.count_nonzero(Y, axis=axis) == k)
+
+
+@pytest.mark.parametrize("TF", [np.float64, np.float32])
+def test_parsdmm_with_fiber_sets(sip, orc, TF):
+    """PARSDMM with a per-fiber cardinality set on D_x / D_z (examples/constrained_freq_FWI_simple.jl:286-302)
+    and per-fiber bounds."""
+    n, d = (40, 36), (25.0, 6.0)
+    m = pr.synthetic_model(n, TF)
+    lo = np.linspace(1400.0, 1600.0, n[1])
+    hi = np.linspace(3000.0, 4700.0, n[1])
+    res = []
+    for api in (orc, sip):
+        cg = api.compgrid(d, n)
+        cons = [api.set_definitions("bounds", "identity", lo.copy(), hi.copy(), ("fiber", "z")),
+                api.set_definitions("cardinality", "D_x", 0, 6, ("fiber", "x")),
+                api.set_definitions("cardinality", "D_z", 0, 8, ("fiber", "z"))]
+        opt = api.PARSDMM_options()
+        opt.FL, opt.maxit = TF, 30
+        P_sub, TD_OP, set_Prop = api.setup_constraints(cons, cg, TF)
+        TD_OP, AtA, l, y = api.PARSDMM_precompute_distribute(TD_OP, set_Prop, cg, opt)
+        res.append(api.PARSDMM(m.copy(), AtA, TD_OP, set_Prop, P_sub, cg, opt) + (set_Prop,))
+    (xo, lo_, ll, yy, spo), (xs, ls, l2, y2, sps) = res
+    assert spo.ncvx == sps.ncvx == [False, True, True, False]
+    assert len(ls.obj) == len(lo_.obj) and np.array_equal(ls.cg_it, lo_.cg_it)
+    assert relerr(xs, xo) < TOL[TF]
+    assert np.array_equal(y2[1] != 0, yy[1] != 0) and np.array_equal(y2[2] != 0, yy[2] != 0)     # supports bit exact
+    assert np.allclose(ls.set_feasibility, lo_.set_feasibility, rtol=50 * TOL[TF], atol=1e-12)
