@@ -308,7 +308,10 @@ def run_device(args, rank, world, local_rank):
                    "parsdmm_iterations_per_step": iters_per_step, "time_to_tolerance_ms": 1e3 * dev_s_max / args.steps,
                    "cache": "working set %.1f GB (Q + AtA + 9 vectors per set) >> 126 MB L2, no flush needed" % (N * 4 * 105 / 1e9),
                    "parallelism": "single GPU" if world == 1 else
-                                  "z-slabs over %d GPUs: NCCL send/recv halo planes + Float64 all-reduce, %s scaling" % (world, args.scaling)},
+                                  "z-slabs over %d GPUs (%s), %s scaling" % (
+                                      world, "peer-memory CG reductions + neighbour-plane loads over NVLink (CUDA IPC), NCCL for the "
+                                      "per-iteration halos / batched all-reduce" if dd.peer_path() else
+                                      "NCCL send/recv halo planes + Float64 all-reduce", args.scaling)},
         "e2e": {"value": e2e_its_all / wall_e2e_max, "unit": "iterations/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": 1e3 * wall_e2e_max / args.steps},
         "gpu_launches": int(launches_all),
@@ -329,7 +332,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
-    ap.add_argument("--n", type=int, default=200, help="grid width (BASELINE configs[1] uses 200)")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=200,
+                    help="grid width (BASELINE configs[1] uses 200); use --size under torchrun (its parser claims --n)")
     ap.add_argument("--cpu-iters", type=int, default=4, help="PARSDMM iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],

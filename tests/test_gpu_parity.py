@@ -516,3 +516,61 @@ def test_parsdmm_with_fiber_sets(sip, orc, TF):
     assert relerr(xs, xo) < TOL[TF]
     assert np.array_equal(y2[1] != 0, yy[1] != 0) and np.array_equal(y2[2] != 0, yy[2] != 0)     # supports bit exact
     assert np.allclose(ls.set_feasibility, lo_.set_feasibility, rtol=50 * TOL[TF], atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------
+# feasibility problems and error behaviour of the boundary
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("TF", [np.float64, np.float32])
+def test_parsdmm_feasibility_only(sip, orc, TF):
+    """options.feasibility_only = true drops the distance term (PARSDMM_precompute_distribute.jl:17,
+    PARSDMM.jl:55-56, update_y_l.jl:90): every operator is a constraint set, p == pp."""
+    spec = pr.spec_config1((36, 30), TF)
+    def tw(o):
+        o.feasibility_only = True
+        o.maxit = 60
+    o, s = run_both(sip, orc, spec, tw)
+    assert len(s[4]["TD_OP"]) == len(spec["sets"]) and s[1].rho.shape[1] == len(spec["sets"])
+    check_parity(o, s, TF)
+
+
+def test_boundary_error_behaviour(sip):
+    """Errors surface as exceptions with the library's message, never as silent fallbacks."""
+    import ctypes as C
+    L = sip._lib
+    lib = L.load()
+    spec = pr.spec_config1((16, 16), np.float32)
+    b = pr.build(sip, spec)
+    # wrong length of m
+    with pytest.raises(ValueError):
+        sip.PARSDMM(spec["m"][:-1].copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+    # P_sub / TD_OP mismatch
+    with pytest.raises(ValueError):
+        sip.PARSDMM(spec["m"].copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"][:-1], b["cg"], b["opt"])
+    # complex input (PARSDMM.jl:50-52)
+    with pytest.raises((TypeError, ValueError)):
+        sip.PARSDMM(spec["m"].astype(np.complex64), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+    # C ABI: unsupported set kind and call-order violations return codes + messages
+    pb = C.c_void_p()
+    n = (C.c_int64 * 3)(8, 8, 1)
+    h = (C.c_double * 3)(1.0, 1.0, 1.0)
+    assert lib.sipb_problem_create(L.ctx(), L.SIPB_F32, 2, n, h, 0, 0, C.byref(pb)) == 0
+    d = L.SetDesc()
+    d.set_kind = 42
+    assert lib.sipb_problem_add_set(pb, C.byref(d)) == L.SIPB_E_UNSUPPORTED and b"outside the device hot path" in lib.sipb_last_error()
+    assert lib.sipb_problem_finalize(pb) == L.SIPB_E_INVALID          # no sets
+    d.set_kind, d.op_kind = L.SET_L1, L.OP_TV
+    d.max = -1.0
+    assert lib.sipb_problem_add_set(pb, C.byref(d)) == L.SIPB_E_INVALID and b"Radius of L1 ball" in lib.sipb_last_error()
+    d.max = 1.0
+    assert lib.sipb_problem_add_set(pb, C.byref(d)) == 0
+    assert lib.sipb_problem_finalize(pb) == L.SIPB_E_STATE            # AtA missing
+    lib.sipb_problem_destroy(pb)
+    # a diagonal of AtA missing in Q: CDS_scaled_add!.jl:18-20
+    R = np.ones((16, 1), dtype=np.float32, order="F")
+    with pytest.raises(L.SipbError) as e:
+        sip.CDS_scaled_add(R.copy(order="F"), np.ones((16, 1), dtype=np.float32, order="F"), np.array([0]), np.array([1]), 1.0)
+    assert e.value.code == L.SIPB_E_MISSING_DIAG
+    # 3-D-only operator on a 2-D grid
+    with pytest.raises(ValueError):
+        sip.get_TD_operator(sip.compgrid((1.0, 1.0), (8, 8)), "D_y", np.float32)
