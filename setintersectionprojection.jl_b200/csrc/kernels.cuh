@@ -402,6 +402,24 @@ struct RhsArgs {
 // independent, which puts G x (rows per column) loads in flight per thread and hides the DRAM latency that
 // bounded the per-column version (ncu round 1: long-scoreboard stalls on the first FMUL/FADD after each
 // gather); rhs is written with 16-byte stores.  Groups that wrap a grid line fall back to single points.
+template <typename T, int G, typename F>
+__device__ __forceinline__ void rhs_set(const OpDev& op, const GridIdx& g0, bool line, const F& f, unsigned npts,
+                                        const unsigned (&n)[3], T (&t)[F::NV][G]) {
+  if (line) {
+    op_adjoint_line<T, G>(op, op.mode, g0, f, t);
+  } else {
+    GridIdx g = g0;
+#pragma unroll
+    for (int e = 0; e < G; ++e) {
+      T one[F::NV];
+      op_adjoint_pt<T>(op, op.mode, g, f, one);
+#pragma unroll
+      for (int q = 0; q < F::NV; ++q) t[q][e] = one[q];
+      grid_next(g, npts, n);
+    }
+  }
+}
+
 template <typename T, int G, bool RDUAL>
 __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[G], double* d) {
   GridIdx g0 = grid_decode(c0, a.npts, a.n);
@@ -410,31 +428,23 @@ __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[G
   for (int e = 0; e < G; ++e) acc[e] = (T)0;
   for (int s = 0; s < a.nsets; ++s) {
     const SetRef<T>& S = a.sets[s];
-    const FetchAxpy<T> fv{S.rho, S.y, S.l};
-    const FetchDiff<T> fd{S.y, S.y_old};
-    T tv[G], td[G];
-    if (line) {
-      op_adjoint_line<T, G>(S.op, S.op.mode, g0, fv, tv);
-      if (RDUAL) op_adjoint_line<T, G>(S.op, S.op.mode, g0, fd, td);
-    } else {
-      GridIdx g = g0;
-#pragma unroll
-      for (int e = 0; e < G; ++e) {
-        tv[e] = op_adjoint_pt<T>(S.op, S.op.mode, g, fv);
-        if (RDUAL) td[e] = op_adjoint_pt<T>(S.op, S.op.mode, g, fd);
-        grid_next(g, (unsigned)a.npts, a.n);
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < G; ++e) acc[e] = acc[e] + tv[e];
     if (RDUAL) {
-      // dual residual of the PREVIOUS iteration, ||A'(y - y_old)||^2 (update_y_l.jl:82-84), rides on the
-      // same gather: y_old still holds y^{k-1} until the next y/l update overwrites it
+      // the dual residual of the PREVIOUS iteration, ||A'(y - y_old)||^2 (update_y_l.jl:82-84), rides on the
+      // same gather (y is loaded once for both): y_old still holds y^{k-1} until the next y/l update
+      T t[2][G];
+      rhs_set<T, G>(S.op, g0, line, FetchAxpyDiff<T>{S.rho, S.y, S.l, S.y_old}, (unsigned)a.npts, a.n, t);
       double sq = 0.0;
 #pragma unroll
-      for (int e = 0; e < G; ++e) sq += (double)td[e] * (double)td[e];
+      for (int e = 0; e < G; ++e) {
+        acc[e] = acc[e] + t[0][e];
+        sq += (double)t[1][e] * (double)t[1][e];
+      }
+      if (s < kRdualSets) d[s * kThreads] += sq;     // per-thread slot in shared memory (keeps 16 registers free)
+    } else {
+      T t[1][G];
+      rhs_set<T, G>(S.op, g0, line, FetchAxpy<T>{S.rho, S.y, S.l}, (unsigned)a.npts, a.n, t);
 #pragma unroll
-      for (int q = 0; q < kRdualSets; ++q) d[q] += (q == s) ? sq : 0.0;
+      for (int e = 0; e < G; ++e) acc[e] = acc[e] + t[0][e];
     }
   }
 }
@@ -443,9 +453,12 @@ __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[G
 template <typename T, bool RDUAL>
 __global__ void __launch_bounds__(kThreads, 4) k_rhs(const __grid_constant__ RhsArgs<T> a, RedScratch rs, double* out) {
   constexpr int VW = Vec<T>::W;
-  double d[kRdualSets];
+  __shared__ double dsh[RDUAL ? kRdualSets * kThreads : 1];
+  double* d = dsh + (RDUAL ? threadIdx.x : 0);
+  if (RDUAL) {
 #pragma unroll
-  for (int q = 0; q < kRdualSets; ++q) d[q] = 0.0;
+    for (int q = 0; q < kRdualSets; ++q) d[q * kThreads] = 0.0;
+  }
   constexpr int G = 2 * VW;
   const i64 ngrp = a.ncols / G;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < ngrp; iv += (i64)gridDim.x * blockDim.x) {
@@ -465,9 +478,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_rhs(const __grid_constant__ Rhs
     a.rhs[c] = acc[0];
   }
   if (RDUAL) {
-    if (grid_sum<kRdualSets>(d, rs) && threadIdx.x == 0) {
+    double dr[kRdualSets];
 #pragma unroll
-      for (int q = 0; q < kRdualSets; ++q) out[q] = d[q];
+    for (int q = 0; q < kRdualSets; ++q) dr[q] = d[q * kThreads];
+    if (grid_sum<kRdualSets>(dr, rs) && threadIdx.x == 0) {
+#pragma unroll
+      for (int q = 0; q < kRdualSets; ++q) out[q] = dr[q];
     }
   }
 }
@@ -752,7 +768,9 @@ __global__ void __launch_bounds__(kThreads) k_op_adjoint(const __grid_constant__
                                                          T* __restrict__ t) {
   for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < op.cols; c += (i64)gridDim.x * blockDim.x) {
     const GridIdx g = grid_decode(c, op.npts, op.n);
-    t[c] = op_adjoint_pt<T>(op, op.mode, g, FetchPlain<T>{v});
+    T one[1];
+    op_adjoint_pt<T>(op, op.mode, g, FetchPlain<T>{v}, one);
+    t[c] = one[0];
   }
 }
 
@@ -802,18 +820,20 @@ __device__ __forceinline__ void rdual_cols(const OpDev& op, const T* __restrict_
   // the dual residual runs over one N-block only: evaluate the operator as if it were un-blocked
   GridIdx g = grid_decode(c0, op.npts, op.n);
   const FetchDiff<T> fd{y, y_old};
-  T t[W];
+  T t[1][W];
   if (W == 1 || g.i + (unsigned)W <= op.n[0]) {
     op_adjoint_line<T, W>(op, SIPB_BLOCK_PLAIN, g, fd, t);
   } else {
 #pragma unroll
     for (int e = 0; e < W; ++e) {
-      t[e] = op_adjoint_pt<T>(op, SIPB_BLOCK_PLAIN, g, fd);
+      T one[1];
+      op_adjoint_pt<T>(op, SIPB_BLOCK_PLAIN, g, fd, one);
+      t[0][e] = one[0];
       grid_next(g, 0xffffffffu, op.n);
     }
   }
 #pragma unroll
-  for (int e = 0; e < W; ++e) d[0] += (double)t[e] * (double)t[e];
+  for (int e = 0; e < W; ++e) d[0] += (double)t[0][e] * (double)t[0][e];
 }
 
 template <typename T>

@@ -295,57 +295,87 @@ __device__ __forceinline__ void op_adjoint_n(const OpDev& op, int mode, const Gr
   }
 }
 
-// ---- value fetchers for the adjoint gathers (W consecutive rows, signed start index) -----------------
+// ---- value fetchers for the adjoint gathers: NV values per row, W consecutive rows, signed start index ----
 template <typename T>
 struct FetchPlain {          // v[row]
+  static constexpr int NV = 1;
   const T* __restrict__ v;
-  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[W]) const { load_any<T, W>(v + row0, out); }
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[1][W]) const { load_any<T, W>(v + row0, out[0]); }
 };
 template <typename T>
 struct FetchAxpy {           // rho*y[row] + l[row]      (rhs_compose.jl:28)
+  static constexpr int NV = 1;
   T rho;
   const T* __restrict__ y;
   const T* __restrict__ l;
-  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[W]) const {
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[1][W]) const {
     T a[W], b[W];
     load_any<T, W>(y + row0, a);
     load_any<T, W>(l + row0, b);
 #pragma unroll
-    for (int e = 0; e < W; ++e) out[e] = rho * a[e] + b[e];
+    for (int e = 0; e < W; ++e) out[0][e] = rho * a[e] + b[e];
   }
 };
 template <typename T>
 struct FetchDiff {           // y[row] - y_old[row]      (update_y_l.jl:82)
+  static constexpr int NV = 1;
   const T* __restrict__ y;
   const T* __restrict__ yo;
-  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[W]) const {
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[1][W]) const {
     T a[W], b[W];
     load_any<T, W>(y + row0, a);
     load_any<T, W>(yo + row0, b);
 #pragma unroll
-    for (int e = 0; e < W; ++e) out[e] = a[e] - b[e];
+    for (int e = 0; e < W; ++e) out[0][e] = a[e] - b[e];
+  }
+};
+template <typename T>
+struct FetchAxpyDiff {       // both of the above from ONE load of y (fused rhs + dual residual gather)
+  static constexpr int NV = 2;
+  T rho;
+  const T* __restrict__ y;
+  const T* __restrict__ l;
+  const T* __restrict__ yo;
+  template <int W> __device__ __forceinline__ void get(int row0, T (&out)[2][W]) const {
+    T a[W], b[W], c[W];
+    load_any<T, W>(y + row0, a);
+    load_any<T, W>(l + row0, b);
+    load_any<T, W>(yo + row0, c);
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      out[0][e] = rho * a[e] + b[e];
+      out[1][e] = a[e] - c[e];
+    }
   }
 };
 
 // ---- adjoint for a group of W consecutive grid points that stay inside one grid line (caller checks
 //      g0.i + W <= n0 and a single Minkowski half): the rows the group needs are consecutive too, so they
-//      are fetched with (at most) two wide loads per block instead of 2W scalar gathers. -------------------
+//      are fetched with (at most) two wide loads per block instead of 2W scalar gathers.  F::NV independent
+//      row vectors are pushed through the same index arithmetic at once (t[q][e] = (A' v_q)[g0 + e]). ------
 template <typename T, int W, typename F>
-__device__ __forceinline__ void op_adjoint_line(const OpDev& op, int mode, const GridIdx& g0, const F& f, T (&t)[W]) {
-  auto scalar_val = [&](int row) -> T {
-    T v[1];
+__device__ __forceinline__ void op_adjoint_line(const OpDev& op, int mode, const GridIdx& g0, const F& f,
+                                                T (&t)[F::NV][W]) {
+  constexpr int NV = F::NV;
+  auto scalar_val = [&](int row, T (&v1)[NV]) {
+    T v[NV][1];
     f.template get<1>(row, v);
-    return v[0];
+#pragma unroll
+    for (int q = 0; q < NV; ++q) v1[q] = v[q][0];
   };
 #pragma unroll
-  for (int e = 0; e < W; ++e) t[e] = (T)0;
+  for (int q = 0; q < NV; ++q)
+#pragma unroll
+    for (int e = 0; e < W; ++e) t[q][e] = (T)0;
   if (!op_touches_half(mode, g0.upper)) return;
   const unsigned cc0 = g0.cc, i0 = g0.i, j = g0.j, k = g0.k;
   if (op.kind == SIPB_OP_IDENTITY) {
-    T v[W];
+    T v[NV][W];
     f.template get<W>((int)cc0, v);
 #pragma unroll
-    for (int e = 0; e < W; ++e) t[e] = t[e] + v[e];
+    for (int q = 0; q < NV; ++q)
+#pragma unroll
+      for (int e = 0; e < W; ++e) t[q][e] = t[q][e] + v[q][e];
     return;
   }
   if (op.kind == SIPB_OP_DXZ) {
@@ -356,13 +386,24 @@ __device__ __forceinline__ void op_adjoint_line(const OpDev& op, int mode, const
     for (int e = 0; e < W; ++e) {
       const unsigned i = i0 + e;
       const bool il = i >= 1u, ih_ = i < op.n[0] - 1u;
-      const int q = (int)(i + w * j);
-      T acc = (T)0;
-      if (il && jl) acc = acc + a * scalar_val(q - 1 - (int)w);
-      if (ih_ && jl) acc = acc + (-a) * scalar_val(q - (int)w);
-      if (il && jh) acc = acc + (-a) * scalar_val(q - 1);
-      if (ih_ && jh) acc = acc + a * scalar_val(q);
-      t[e] = acc;
+      const int r = (int)(i + w * j);
+      T acc[NV], v1[NV];
+#pragma unroll
+      for (int q = 0; q < NV; ++q) acc[q] = (T)0;
+      if (il && jl) { scalar_val(r - 1 - (int)w, v1);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = acc[q] + a * v1[q]; }
+      if (ih_ && jl) { scalar_val(r - (int)w, v1);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = acc[q] + (-a) * v1[q]; }
+      if (il && jh) { scalar_val(r - 1, v1);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = acc[q] + (-a) * v1[q]; }
+      if (ih_ && jh) { scalar_val(r, v1);
+#pragma unroll
+        for (int q = 0; q < NV; ++q) acc[q] = acc[q] + a * v1[q]; }
+#pragma unroll
+      for (int q = 0; q < NV; ++q) t[q][e] = acc[q];
     }
     return;
   }
@@ -376,51 +417,64 @@ __device__ __forceinline__ void op_adjoint_line(const OpDev& op, int mode, const
       if (i0 + (unsigned)W == op.n[0]) {                          // group ends the line: the row of i = n0-1 does
 #pragma unroll                                                    // not exist -> element-wise (one group per line)
         for (int e = 0; e < W; ++e) {
-          const int q = q0 + e;
-          if (i0 + e >= 1u) t[e] = t[e] + ih * scalar_val(q - 1);
-          if (i0 + e < op.n[0] - 1u) t[e] = t[e] + nih * scalar_val(q);
+          T v1[NV];
+          if (i0 + e >= 1u) { scalar_val(q0 + e - 1, v1);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) t[q][e] = t[q][e] + ih * v1[q]; }
+          if (i0 + e < op.n[0] - 1u) { scalar_val(q0 + e, v1);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) t[q][e] = t[q][e] + nih * v1[q]; }
         }
       } else {
-        T v[W];
+        T v[NV][W], prev[NV];
         f.template get<W>(q0, v);
-        T prev = (i0 >= 1u) ? scalar_val(q0 - 1) : (T)0;
+        if (i0 >= 1u) scalar_val(q0 - 1, prev);
+        else {
 #pragma unroll
-        for (int e = 0; e < W; ++e) {
-          if (i0 + e >= 1u) t[e] = t[e] + ih * prev;
-          t[e] = t[e] + nih * v[e];            // i < n0-1 holds for the whole group here
-          prev = v[e];
+          for (int q = 0; q < NV; ++q) prev[q] = (T)0;
+        }
+#pragma unroll
+        for (int q = 0; q < NV; ++q) {
+          T pr = prev[q];
+#pragma unroll
+          for (int e = 0; e < W; ++e) {
+            if (i0 + e >= 1u) t[q][e] = t[q][e] + ih * pr;
+            t[q][e] = t[q][e] + nih * v[q][e];            // i < n0-1 holds for the whole group here
+            pr = v[q][e];
+          }
         }
       }
-    } else if (a == 1) {
-      const int st = (int)op.n[0];
-      const int q0 = base + (int)(cc0 - op.n[0] * k);             // row of (i0, j, k)
-      if (j >= 1u) {
-        T v[W];
-        f.template get<W>(q0 - st, v);
-#pragma unroll
-        for (int e = 0; e < W; ++e) t[e] = t[e] + ih * v[e];
-      }
-      if (j < op.n[1] - 1u) {
-        T v[W];
-        f.template get<W>(q0, v);
-#pragma unroll
-        for (int e = 0; e < W; ++e) t[e] = t[e] + nih * v[e];
-      }
     } else {
-      const int st = (int)(op.n[0] * op.n[1]);
-      const int q0 = base + (int)cc0;
-      const unsigned kg = k + op.kofs;
-      if (kg >= 1u) {
-        T v[W];
+      // axes 1 and 2: the two rows of every grid point are W consecutive rows each
+      int st, q0;
+      bool has_lo, has_hi;
+      if (a == 1) {
+        st = (int)op.n[0];
+        q0 = base + (int)(cc0 - op.n[0] * k);                     // row of (i0, j, k)
+        has_lo = j >= 1u;
+        has_hi = j < op.n[1] - 1u;
+      } else {
+        st = (int)(op.n[0] * op.n[1]);
+        q0 = base + (int)cc0;
+        const unsigned kg = k + op.kofs;                          // slabs: global plane number, halo row at q0 - st
+        has_lo = kg >= 1u;
+        has_hi = kg < op.nlast - 1u;
+      }
+      if (has_lo) {
+        T v[NV][W];
         f.template get<W>(q0 - st, v);
 #pragma unroll
-        for (int e = 0; e < W; ++e) t[e] = t[e] + ih * v[e];
+        for (int q = 0; q < NV; ++q)
+#pragma unroll
+          for (int e = 0; e < W; ++e) t[q][e] = t[q][e] + ih * v[q][e];
       }
-      if (kg < op.nlast - 1u) {
-        T v[W];
+      if (has_hi) {
+        T v[NV][W];
         f.template get<W>(q0, v);
 #pragma unroll
-        for (int e = 0; e < W; ++e) t[e] = t[e] + nih * v[e];
+        for (int q = 0; q < NV; ++q)
+#pragma unroll
+          for (int e = 0; e < W; ++e) t[q][e] = t[q][e] + nih * v[q][e];
       }
     }
   }
@@ -428,10 +482,11 @@ __device__ __forceinline__ void op_adjoint_line(const OpDev& op, int mode, const
 
 // single grid point (line wraps, tails)
 template <typename T, typename F>
-__device__ __forceinline__ T op_adjoint_pt(const OpDev& op, int mode, const GridIdx& g, const F& f) {
-  T t[1];
-  op_adjoint_line<T, 1>(op, mode, g, f, t);
-  return t[0];
+__device__ __forceinline__ void op_adjoint_pt(const OpDev& op, int mode, const GridIdx& g, const F& f, T (&t)[F::NV]) {
+  T tt[F::NV][1];
+  op_adjoint_line<T, 1>(op, mode, g, f, tt);
+#pragma unroll
+  for (int q = 0; q < F::NV; ++q) t[q] = tt[q][0];
 }
 
 }  // namespace sipb
