@@ -600,9 +600,9 @@ struct YlArgs {
   ProjDev<T> P;
   const ProjParams<T>* dyn;   // reduction-type projectors: parameters produced on the device
   const T* x;
-  T* y;
+  T* y;                       // y^{k+1} (output; MODE 1 parks v = x_hat - l/rho here for pass 2)
   T* l;
-  T* y_old;
+  const T* y_old;             // y^{k}: the host swaps the y / y_old buffers instead of copying (update_y_l.jl:64)
   T* s;                       // only reduction-type projectors keep s between their two passes
   T* lhat0; T* s0; T* l0; T* y0;   // snapshots of the adaptation scheme
   T rho, gamma;
@@ -628,7 +628,7 @@ template <typename T, int W> __device__ __forceinline__ void store_n(T* p, const
 
 // Processes W consecutive rows starting at r0.
 // MODE 0: element-wise projector, everything in one pass.
-// MODE 1: reduction-type projector, pass 1: y <- v = x_hat - l/rho, s stored, y_old saved.
+// MODE 1: reduction-type projector, pass 1: y <- v = x_hat - l/rho, s stored.
 // MODE 2: reduction-type projector, pass 2: y <- P(v), l update.
 // d[]: MODE 0/2: [0] ||y-s||^2, [1] ||P(s)-s||^2, [2] ||s||^2 ; MODE 1: [0] sum|v|, [1] sum v^2, [2] nnz(v)
 //      ADAPT   : [3] dot(dH,dlh) [4] ||dH||^2 [5] ||dlh||^2 [6] ||dl||^2 [7] ||dG||^2 [8] dot(dG,dl)
@@ -639,7 +639,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
   const bool relaxed = !(gamma == (T)1);
   T s[W], yo[W], lo[W], yn[W], ln[W];
   if (MODE == 0 || MODE == 1) {
-    load_n<T, W>(a.y + r0, yo);
+    if (relaxed || ADAPT) load_n<T, W>(a.y_old + r0, yo);
     load_n<T, W>(a.l + r0, lo);
     op_forward_n<T, W>(a.op, (unsigned)r0, a.x, s);
 #pragma unroll
@@ -665,7 +665,6 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
       }
     }
     store_n<T, W>(a.y + r0, yn);
-    store_n<T, W>(a.y_old + r0, yo);
     if (MODE == 0) store_n<T, W>(a.l + r0, ln);
     else store_n<T, W>(a.s + r0, s);
   } else {
@@ -724,7 +723,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
 
 // out: [0..2] as d[0..2] (MODE 2 writes only [0]); ADAPT sums go to out[4..9]
 template <typename T, int MODE, bool ADAPT>
-__global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
+__device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs, double* out) {
   constexpr int VW = Vec<T>::W;
   constexpr int NR = ADAPT ? 9 : 3;
   ProjDev<T> P = a.P;
@@ -752,6 +751,27 @@ __global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlAr
       for (int i = 0; i < 6; ++i) out[4 + i] = d[3 + i];
     }
   }
+}
+
+template <typename T, int MODE, bool ADAPT>
+__global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
+  yl_body<T, MODE, ADAPT>(a, rs, out);
+}
+
+// All element-wise sets of one PARSDMM iteration in a single launch: blockIdx.y selects the set, every set
+// reduces into its own scratch slice / ticket.  One launch instead of one per set removes the per-kernel
+// ramp, tail and last-block latency (~8 us each at 200^3, most of the time at 256^2) and lets the tail of
+// one set overlap the head of the next.
+constexpr int kYlMulti = 8;
+template <typename T>
+struct YlMultiArgs {
+  YlArgs<T> a[kYlMulti];
+  double* out[kYlMulti];
+};
+template <typename T, bool ADAPT>
+__global__ void __launch_bounds__(kThreads, 4) k_yl_multi(const __grid_constant__ YlMultiArgs<T> m, RedScratch rs) {
+  const RedScratch mine{rs.partials + (size_t)blockIdx.y * kMaxRed * kMaxBlocks, rs.counter + blockIdx.y};
+  yl_body<T, 0, ADAPT>(m.a[blockIdx.y], mine, m.out[blockIdx.y]);
 }
 
 // forward operator only: s = A x      (initial feasibility, PARSDMM_initialize.jl:97-99; unit tests)

@@ -103,6 +103,11 @@ struct DevBuf {
   DevBuf(const DevBuf&) = delete;
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
+  void swap(DevBuf& o) {
+    std::swap(p, o.p);
+    std::swap(base, o.base);
+    std::swap(n, o.n);
+  }
   void release() {
     if (base) cudaFree(base);
     p = base = nullptr;
@@ -135,6 +140,7 @@ struct sipb_ctx {
   int num_sms = 148;
   cudaStream_t stream = nullptr;
   RedScratch rs{nullptr, nullptr};
+  RedScratch rs_multi{nullptr, nullptr};   // kYlMulti slices for the multi-set y/l launch
   double* d_scal = nullptr;   // device scalar slots
   double* h_scal = nullptr;   // pinned mirror
   CgState* d_cg = nullptr;
@@ -608,6 +614,7 @@ struct Problem : sipb_problem {
   std::vector<std::unique_ptr<SetT<T>>> sets;
   std::vector<int64_t> q_offs;
   DevBuf<T> Q, x, x_old, rhs, r, pvec, Ap, m, tmp;
+  YlMultiArgs<T> yl_multi;    // argument block of the multi-set y/l launch (rebuilt every iteration)
   i64 maxM = 0;
   bool m_resident = false;
   SlabGeom sg;                // active when the ctx has a communicator with world > 1
@@ -706,14 +713,11 @@ struct Problem : sipb_problem {
     return SIPB_OK;
   }
   // lower halos of y and l for every set with a D_z block (needed by the rhs / dual-residual gathers);
-  // the y_old halo is the previous y halo (local copy, no transfer)
-  int exchange_yl_halos(bool shift_y_old) {
+  // the y_old halo is the previous y halo: it travels with the buffer when y and y_old trade places
+  int exchange_yl_halos() {
     if (!sg.on) return SIPB_OK;
     for (auto& S : sets) {
       if (!S->z_halo) continue;
-      if (shift_y_old && sg.has_lo)
-        SIPB_CUDA_CHECK(cudaMemcpyAsync(S->y_old.p - sg.plane, S->y.p - sg.plane, sg.plane * sizeof(T),
-                                        cudaMemcpyDeviceToDevice, ctx->stream));
       int rc = exchange(S->y.p, sg.nz_rows(), true, false);
       if (rc) return rc;
       rc = exchange(S->l.p, sg.nz_rows(), true, false);
@@ -1281,7 +1285,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     if (rc) return rc;
     for (auto& S : sets)
       if (S->z_halo) SIPB_CUDA_CHECK(cudaMemsetAsync(S->y_old.p - sg.plane, 0, sg.plane * sizeof(T), c->stream));
-    rc = exchange_yl_halos(false);
+    rc = exchange_yl_halos();
     if (rc) return rc;
   }
 
@@ -1348,10 +1352,23 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     // stop_PARSDMM switches adaptation off in this very iteration the sums are simply discarded
     const bool do_adapt = (adjust_rho || adjust_gamma) && (i % rho_update_frequency == 0);
     const bool fuse_adapt = (i == 1) || do_adapt;
+    YlMultiArgs<T>& ym = yl_multi;
+    int n_multi = 0, g_multi = 1;
+    auto flush_multi = [&]() {
+      if (n_multi == 0) return;
+      const dim3 grid((unsigned)g_multi, (unsigned)n_multi);
+      if (fuse_adapt) LAUNCH(c, KC_YL_FUSED, (k_yl_multi<T, true>), grid, ym, c->rs_multi);
+      else LAUNCH(c, KC_YL_FUSED, (k_yl_multi<T, false>), grid, ym, c->rs_multi);
+      n_multi = 0;
+      g_multi = 1;
+    };
     for (int s = 0; s < p; ++s) {
       SetT<T>& S = *sets[s];
       const bool is_dist = S.desc.set_kind == SIPB_SET_DISTANCE;
       const bool want_feas = feas_it && !is_dist;
+      // copy!(y_old, y) (update_y_l.jl:64) without moving data: the two buffers trade places and the
+      // kernels read y^{k} from y_old while writing y^{k+1}
+      S.y.swap(S.y_old);
       YlArgs<T> ya;
       memset(&ya, 0, sizeof(ya));
       ya.op = S.op;
@@ -1364,9 +1381,12 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       const int base = s * kSlotPerSet;
       const int g = c->grid_for((S.M + Vec<T>::W - 1) / Vec<T>::W);
       if (proj_is_elementwise(S.desc.set_kind)) {
+        // element-wise sets are gathered and updated by one launch per (up to) kYlMulti sets
         ya.want_feas = want_feas ? 1 : 0;
-        if (fuse_adapt) LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, true>), g, ya, c->rs, c->d_scal + base);
-        else LAUNCH(c, KC_YL_FUSED, (k_yl<T, 0, false>), g, ya, c->rs, c->d_scal + base);
+        ym.a[n_multi] = ya;
+        ym.out[n_multi] = c->d_scal + base;
+        g_multi = std::max(g_multi, g);
+        if (++n_multi == kYlMulti) flush_multi();
       } else {
         ya.want_feas = 0;
         LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), g, ya, c->rs, c->d_scal + base + 10);
@@ -1380,11 +1400,16 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
           if (rc) return rc;
         }
       }
-      if (!fuse_rdual)
-        LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
-               (const T*)S.y_old.p, c->rs, c->d_scal + base + 3);
     }
-    { int rc = exchange_yl_halos(true); if (rc) return rc; }   // slabs: halo planes for the next rhs gather
+    flush_multi();
+    if (!fuse_rdual) {
+      for (int s = 0; s < p; ++s) {
+        SetT<T>& S = *sets[s];
+        LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
+               (const T*)S.y_old.p, c->rs, c->d_scal + s * kSlotPerSet + 3);
+      }
+    }
+    { int rc = exchange_yl_halos(); if (rc) return rc; }   // slabs: halo planes for the next rhs gather
     LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
            (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
     { int rc = ctx_sync_scalars(c); if (rc) return rc; }
@@ -1585,6 +1610,9 @@ int sipb_ctx_create(int device, sipb_ctx** out) {
   SIPB_CUDA_CHECK(cudaMalloc(&c->rs.partials, sizeof(double) * kMaxRed * kMaxBlocks));
   SIPB_CUDA_CHECK(cudaMalloc(&c->rs.counter, sizeof(unsigned int)));
   SIPB_CUDA_CHECK(cudaMemset(c->rs.counter, 0, sizeof(unsigned int)));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->rs_multi.partials, sizeof(double) * kMaxRed * kMaxBlocks * kYlMulti));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->rs_multi.counter, sizeof(unsigned int) * kYlMulti));
+  SIPB_CUDA_CHECK(cudaMemset(c->rs_multi.counter, 0, sizeof(unsigned int) * kYlMulti));
   SIPB_CUDA_CHECK(cudaMalloc(&c->d_counter2, sizeof(unsigned int)));
   SIPB_CUDA_CHECK(cudaMemset(c->d_counter2, 0, sizeof(unsigned int)));
   SIPB_CUDA_CHECK(cudaMalloc(&c->d_scal, sizeof(double) * kScalSlots));
@@ -1609,7 +1637,7 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-  cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
+  cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->rs_multi.partials); cudaFree(c->rs_multi.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_l1); cudaFreeHost(c->h_l1);
   cudaFree(c->d_sel); cudaFree(c->d_tie_counts);
   for (int q = 0; q < kMaxRanks; ++q)
