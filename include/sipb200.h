@@ -182,6 +182,12 @@ int sipb_problem_set_ata(sipb_problem* pb, int set_index, const void* R, int64_t
 int sipb_problem_finalize(sipb_problem* pb);
 int sipb_problem_num_q_offsets(sipb_problem* pb, int* nd);
 int sipb_problem_q_offsets(sipb_problem* pb, int64_t* out);     /* Q_offsets, reference order */
+/* How the device holds Q = sum rho_i AtA_i (PARSDMM_initialize.jl:223-229) after finalize:
+ * 0 = CDS arrays [N x nd]; 1 = stencil-class tables (every AtA_i was verified to hold one value per diagonal
+ * on all rows that agree on {first, interior, last} along each grid axis, so one row per class is kept and the
+ * SpMV of cg.jl streams only the vectors; same multiply-adds in the same order -> bit-identical results).
+ * The environment variable SIPB_Q_CLASSES=0 forces the array form. */
+int sipb_problem_q_form(sipb_problem* pb, int* form);
 int sipb_problem_destroy(sipb_problem* pb);
 
 /* Multilevel warm start on the device: nearest-neighbour resampling of the coarse problem's x, l, y into the

@@ -88,6 +88,7 @@ SYMBOLS = [
     ("sipb_problem_set_ata", _I, [_VP, _I, _VP, _I64, _PI64, _I]),
     ("sipb_problem_finalize", _I, [_VP]),
     ("sipb_problem_num_q_offsets", _I, [_VP, _PI]),
+    ("sipb_problem_q_form", _I, [_VP, _PI]),
     ("sipb_problem_q_offsets", _I, [_VP, _PI64]),
     ("sipb_problem_destroy", _I, [_VP]),
     ("sipb_problem_warm_from", _I, [_VP, _VP, C.POINTER(ResampleSeg), _I]),

@@ -38,7 +38,63 @@ struct SpmvArgs {
   const T* x_lo;     // slabs, peer path: the lower / upper neighbour's vector (owned start), read over NVLink
   const T* x_hi;     //   instead of a local halo copy; null => local halo planes
   i64 n_lo;          // rows owned by the lower neighbour
+  // stencil-class form of the matrix (see RowClass below): tab[cls*nd + j] replaces R[j*ld + r]; null => R
+  const T* tab;
+  unsigned gn[3];    // grid
+  unsigned npts;     // grid points (rows per Minkowski half)
 };
+
+// ---------------------------------------------------------------------------------------------
+// Stencil classes.  Every AtA the reference builds from its constant-coefficient difference operators
+// (get_TD_operator.jl) — and therefore Q = sum rho_i AtA_i, which is updated row-uniformly
+// (Q_update!.jl:45-49) — holds the same values on all rows that agree on {first, interior, last} along each
+// grid axis (and on the Minkowski half): 27 (54) classes.  The solver VERIFIES this on the uploaded CDS arrays
+// and then keeps one row per class instead of N: the SpMV streams x and y only ((nd+2) -> 2 words per row)
+// and performs exactly the multiply-adds, in exactly the order, of the array form — bit-identical results.
+// Matrices that fail the check (custom operators) stay in array form.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 54;
+template <typename T> __device__ __forceinline__ unsigned long long value_bits(T v);
+template <> __device__ __forceinline__ unsigned long long value_bits<float>(float v) { return __float_as_uint(v); }
+template <> __device__ __forceinline__ unsigned long long value_bits<double>(double v) {
+  return (unsigned long long)__double_as_longlong(v);
+}
+__device__ __forceinline__ unsigned axis_class(unsigned idx, unsigned n) {
+  return idx == 0u ? 0u : (idx == n - 1u ? 2u : 1u);
+}
+// class of global row g
+__device__ __forceinline__ unsigned row_class(i64 g, const unsigned (&n)[3], unsigned npts) {
+  const unsigned half = g >= (i64)npts ? 1u : 0u;
+  const unsigned c = (unsigned)(g - (i64)half * npts);
+  const unsigned q = c / n[0];
+  const unsigned i = c - q * n[0];
+  const unsigned kk = q / n[1];
+  const unsigned j = q - kk * n[1];
+  return ((half * 3u + axis_class(kk, n[2])) * 3u + axis_class(j, n[1])) * 3u + axis_class(i, n[0]);
+}
+// classes of W consecutive global rows; returns true when all W are equal (=> cls[0])
+template <int W>
+__device__ __forceinline__ bool row_classes(i64 g, const unsigned (&n)[3], unsigned npts, unsigned (&cls)[W]) {
+  const unsigned half = g >= (i64)npts ? 1u : 0u;
+  const unsigned c = (unsigned)(g - (i64)half * npts);
+  const unsigned q = c / n[0];
+  const unsigned i = c - q * n[0];
+  if (i + (unsigned)W <= n[0] && (half || c + (unsigned)W <= npts)) {
+    const unsigned kk = q / n[1];
+    const unsigned j = q - kk * n[1];
+    const unsigned base = ((half * 3u + axis_class(kk, n[2])) * 3u + axis_class(j, n[1])) * 3u;
+    bool same = true;
+#pragma unroll
+    for (int e = 0; e < W; ++e) {
+      cls[e] = base + axis_class(i + e, n[0]);
+      same = same && cls[e] == cls[0];
+    }
+    return same;
+  }
+#pragma unroll
+  for (int e = 0; e < W; ++e) cls[e] = row_class(g + e, n, npts);
+  return false;
+}
 
 // true when the calling block (grid-stride over vector groups of W rows) owns rows within `halo` rows of either
 // end of the local slab — only those rows are read by the neighbours, so only these blocks need
@@ -61,16 +117,31 @@ __device__ __forceinline__ T spmv_x(const SpmvArgs<T>& a, i64 idx) {
 }
 
 // acc[e] for VW consecutive rows starting at r (vector path; r % VW == 0, r + VW <= N)
+// tab: the class table staged in shared memory (null => array form)
 template <typename T>
-__device__ __forceinline__ void spmv_rows_vec(const SpmvArgs<T>& a, i64 r, T (&acc)[Vec<T>::W]) {
+__device__ __forceinline__ void spmv_rows_vec(const SpmvArgs<T>& a, const T* tab, i64 r, T (&acc)[Vec<T>::W]) {
   constexpr int VW = Vec<T>::W;
 #pragma unroll
   for (int e = 0; e < VW; ++e) acc[e] = (T)0;
   const i64 g = a.row0 + r;
+  unsigned cls[VW];
+  bool same = false;
+  if (tab) same = row_classes<VW>(g, a.gn, a.npts, cls);
 #pragma unroll 4
   for (int j = 0; j < a.nd; ++j) {
     T rv[VW], xv[VW];
-    vload_stream<T>(a.R + (i64)j * a.ld + r, rv);
+    if (tab) {
+      if (same) {
+        const T q = tab[cls[0] * a.nd + j];
+#pragma unroll
+        for (int e = 0; e < VW; ++e) rv[e] = q;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) rv[e] = tab[cls[e] * a.nd + j];
+      }
+    } else {
+      vload_stream<T>(a.R + (i64)j * a.ld + r, rv);
+    }
     const i64 o = a.off[j];
     const i64 gc = g + o;
     const i64 li = r + o;
@@ -96,14 +167,27 @@ __device__ __forceinline__ void spmv_rows_vec(const SpmvArgs<T>& a, i64 r, T (&a
 }
 
 template <typename T>
-__device__ __forceinline__ T spmv_row_scalar(const SpmvArgs<T>& a, i64 r) {
+__device__ __forceinline__ T spmv_row_scalar(const SpmvArgs<T>& a, const T* tab, i64 r) {
   T acc = (T)0;
   const i64 g = a.row0 + r;
+  const unsigned cls = tab ? row_class(g, a.gn, a.npts) : 0u;
   for (int j = 0; j < a.nd; ++j) {
     const i64 gc = g + a.off[j];
-    if (gc >= 0 && gc < a.Nglob) acc = acc + a.R[(i64)j * a.ld + r] * spmv_x<T>(a, r + a.off[j]);
+    if (gc >= 0 && gc < a.Nglob) {
+      const T q = tab ? tab[cls * a.nd + j] : a.R[(i64)j * a.ld + r];
+      acc = acc + q * spmv_x<T>(a, r + a.off[j]);
+    }
   }
   return acc;
+}
+
+// stage the class table in shared memory (all threads of the block call this)
+template <typename T>
+__device__ __forceinline__ const T* spmv_stage_table(const SpmvArgs<T>& a, T* tab_s) {
+  if (!a.tab) return nullptr;
+  for (int q = threadIdx.x; q < kMaxClasses * a.nd; q += blockDim.x) tab_s[q] = a.tab[q];
+  __syncthreads();
+  return tab_s;
 }
 
 // y = A x  and (DOT) partial sum of x.*y  -> out_dot[0]
@@ -114,6 +198,8 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
                                                    const int* __restrict__ done_flag, const __grid_constant__ CommDev cd) {
   if (done_flag && *done_flag) return;
   constexpr int VW = Vec<T>::W;
+  __shared__ T tab_s[kMaxClasses * kMaxDiag];
+  const T* tab = spmv_stage_table<T>(a, tab_s);
   double d[1] = {0.0};
   const i64 nvec = a.N / VW;
   if (cd.on) {
@@ -128,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 r = iv * VW;
     T acc[VW];
-    spmv_rows_vec<T>(a, r, acc);
+    spmv_rows_vec<T>(a, tab, r, acc);
     vstore<T>(a.y + r, acc);
     if (DOT) {
       T xc[VW];
@@ -139,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
   }
   // tail rows
   for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < a.N; r += (i64)gridDim.x * blockDim.x) {
-    const T acc = spmv_row_scalar<T>(a, r);
+    const T acc = spmv_row_scalar<T>(a, tab, r);
     a.y[r] = acc;
     if (DOT) d[0] += (double)a.x[r] * (double)acc;
   }
@@ -175,12 +261,14 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
                                                       T* __restrict__ p, T* __restrict__ x_old, RedScratch rs,
                                                       CgState* st, const __grid_constant__ CommDev cd) {
   constexpr int VW = Vec<T>::W;
+  __shared__ T tab_s[kMaxClasses * kMaxDiag];
+  const T* tab = spmv_stage_table<T>(a, tab_s);
   double d[2] = {0.0, 0.0};
   const i64 nvec = a.N / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 row = iv * VW;
     T acc[VW], bv[VW], rv[VW];
-    spmv_rows_vec<T>(a, row, acc);
+    spmv_rows_vec<T>(a, tab, row, acc);
     vload_stream<T>(b + row, bv);
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
@@ -198,7 +286,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
   }
   for (i64 row = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < a.N;
        row += (i64)gridDim.x * blockDim.x) {
-    const T acc = spmv_row_scalar<T>(a, row);
+    const T acc = spmv_row_scalar<T>(a, tab, row);
     const T bv = b[row];
     const T rv = bv - acc;
     d[0] += (double)bv * (double)bv;
@@ -918,6 +1006,75 @@ __global__ void __launch_bounds__(kThreads) k_cds_axpy(i64 N, T* __restrict__ A,
   }
   for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x)
     A[r] = A[r] + alpha * B[r];
+}
+
+// ---- stencil-class tables (see RowClass above) ------------------------------------------------------------
+struct ClassGeom {
+  unsigned n[3];
+  unsigned npts;
+  int nhalf;         // 1, or 2 for Minkowski
+  unsigned kofs;     // slabs: global plane number of the first local plane
+  unsigned nz_loc;   // local planes
+};
+// representative LOCAL row of class `cls`, or -1 when the class has no local row
+__device__ __forceinline__ i64 class_local_row(const ClassGeom& g, unsigned cls) {
+  const unsigned ci = cls % 3u, cj = (cls / 3u) % 3u, ck = (cls / 9u) % 3u, half = cls / 27u;
+  if ((int)half >= g.nhalf) return -1;
+  auto rep = [](unsigned c, unsigned n, unsigned lo, unsigned cnt, bool& ok) -> unsigned {
+    // an index in [lo, lo+cnt) with axis_class == c
+    unsigned idx;
+    if (c == 0u) idx = 0u;
+    else if (c == 2u) idx = n - 1u;
+    else idx = lo > 1u ? lo : 1u;
+    ok = ok && idx >= lo && idx < lo + cnt && axis_class(idx, n) == c;
+    return idx;
+  };
+  bool ok = true;
+  const unsigned i = rep(ci, g.n[0], 0u, g.n[0], ok);
+  const unsigned j = rep(cj, g.n[1], 0u, g.n[1], ok);
+  const unsigned kk = rep(ck, g.n[2], g.kofs, g.nz_loc, ok);
+  if (!ok) return -1;
+  const i64 plane = (i64)g.n[0] * g.n[1];
+  return (i64)half * g.npts + (i64)(kk - g.kofs) * plane + (i64)j * g.n[0] + i;
+}
+// tab[cls*nd + j] = R[j*ld + representative row]   (0 for classes without a local row)
+template <typename T>
+__global__ void k_class_extract(const T* __restrict__ R, i64 ld, int nd, ClassGeom g, T* __restrict__ tab) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= kMaxClasses * nd) return;
+  const unsigned cls = q / nd;
+  const int j = q - cls * nd;
+  const i64 r = class_local_row(g, cls);
+  tab[q] = r >= 0 ? R[(i64)j * ld + r] : (T)0;
+}
+// bad[0] != 0 when some local entry differs (bitwise) from its class value
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_class_verify(const T* __restrict__ R, i64 ld, int nd, i64 N, i64 row0,
+                                                           ClassGeom g, const T* __restrict__ tab, int* bad) {
+  __shared__ T tab_s[kMaxClasses * kMaxDiag];
+  for (int q = threadIdx.x; q < kMaxClasses * nd; q += blockDim.x) tab_s[q] = tab[q];
+  __syncthreads();
+  bool mismatch = false;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x) {
+    const unsigned cls = row_class(row0 + r, g.n, g.npts);
+    for (int j = 0; j < nd; ++j) {
+      const T v = R[(i64)j * ld + r];
+      const T t = tab_s[cls * nd + j];
+      mismatch = mismatch || value_bits<T>(v) != value_bits<T>(t);
+    }
+  }
+  if (mismatch) atomicExch(bad, 1);
+}
+// Q_tab[cls*nq + qcol[j]] += alpha * A_tab[cls*nd + j]      (CDS_scaled_add!.jl:22 on one row per class)
+struct QCols { int c[kMaxDiag]; };
+template <typename T>
+__global__ void k_class_axpy(T* __restrict__ Qt, int nq, const T* __restrict__ At, int nd, QCols qc, T alpha) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= kMaxClasses * nd) return;
+  const int cls = q / nd;
+  const int j = q - cls * nd;
+  T* dst = Qt + cls * nq + qc.c[j];
+  *dst = *dst + alpha * At[q];
 }
 
 // =============================================================================================

@@ -576,6 +576,7 @@ struct sipb_problem {
   virtual int finalize() = 0;
   virtual int solve(const void* m, void* x, void* const* l, void* const* y, const sipb_options* o, sipb_log* log) = 0;
   virtual int q_offsets(std::vector<int64_t>& out) = 0;
+  virtual int q_form() const = 0;
   virtual int warm_from(sipb_problem* coarse, const sipb_resample_seg* segs, int nseg) = 0;
 };
 
@@ -593,7 +594,8 @@ struct SetT {
   i64 Mglob = 0;   // rows of the global operator
   DevBuf<T> y, l, y_old, s, s0, y0, l0, lhat0;   // s only for reduction-type projectors
   DevBuf<T> lo_vec, hi_vec;
-  DevBuf<T> ata;              // [nd][ld]
+  DevBuf<T> ata;              // [nd][ld]   (released once the stencil-class table has been verified)
+  DevBuf<T> ata_tab;          // [kMaxClasses][nd] stencil-class form of AtA
   int nd = 0;
   std::vector<int64_t> offs;
   std::vector<int> qcol;      // column of Q for each diagonal of AtA
@@ -614,6 +616,8 @@ struct Problem : sipb_problem {
   std::vector<std::unique_ptr<SetT<T>>> sets;
   std::vector<int64_t> q_offs;
   DevBuf<T> Q, x, x_old, rhs, r, pvec, Ap, m, tmp;
+  DevBuf<T> Q_tab;            // [kMaxClasses][nq] stencil-class form of Q (replaces Q when q_classes)
+  bool q_classes = false;
   YlMultiArgs<T> yl_multi;    // argument block of the multi-set y/l launch (rebuilt every iteration)
   i64 maxM = 0;
   bool m_resident = false;
@@ -826,9 +830,11 @@ struct Problem : sipb_problem {
         S->qcol[k] = (int)(it - q_offs.begin());
       }
     }
+    { int rc = detect_classes(); if (rc) return rc; }
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf<T>& b, size_t cnt) { if (e == cudaSuccess) e = b.alloc(cnt); };
-    A(Q, (size_t)ld * q_offs.size());
+    if (q_classes) A(Q_tab, (size_t)kMaxClasses * q_offs.size());
+    else A(Q, (size_t)ld * q_offs.size());
     const size_t halo = sg.on ? (size_t)sg.plane : 0;      // one plane on each side (max |offset| of Q)
     auto AH = [&](DevBuf<T>& b, size_t cnt) { if (e == cudaSuccess) e = b.alloc(cnt, halo, halo); };
     AH(x, (size_t)N); A(x_old, (size_t)N); A(rhs, (size_t)N); A(r, (size_t)N); AH(pvec, (size_t)N);
@@ -842,6 +848,80 @@ struct Problem : sipb_problem {
     return SIPB_OK;
   }
 
+  ClassGeom class_geom() const {
+    ClassGeom g;
+    g.n[0] = (unsigned)n[0]; g.n[1] = (unsigned)n[1]; g.n[2] = (unsigned)n[2];
+    g.npts = (unsigned)(n[0] * n[1] * n[2]);     // GLOBAL grid points (rows per Minkowski half)
+    g.nhalf = minkowski ? 2 : 1;
+    g.kofs = sg.on ? (unsigned)sg.k0 : 0u;
+    g.nz_loc = sg.on ? (unsigned)sg.nloc() : (unsigned)n[2];
+    return g;
+  }
+  // Do all AtA_i have one value per stencil class and diagonal (kernels.cuh, "Stencil classes")?  Then keep
+  // the class tables only: Q becomes a [classes][nq] table and the SpMV stops streaming matrix entries.
+  // SIPB_Q_CLASSES=0 keeps the array form (A/B measurements, tests of the general path).
+  int detect_classes() {
+    q_classes = false;
+    const char* env = getenv("SIPB_Q_CLASSES");
+    int ok = !(env && env[0] == '0');
+    if (n[0] * n[1] * n[2] >= ((i64)1 << 31)) ok = 0;
+    if (minkowski && sg.on) ok = 0;
+    sipb_ctx* c = ctx;
+    if (ok) {
+      int* d_bad = (int*)c->d_counter2;
+      SIPB_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+      const ClassGeom g = class_geom();
+      const i64 row0 = sg.on ? sg.plane * sg.k0 : 0;
+      for (auto& S : sets) {
+        SIPB_CUDA_CHECK(S->ata_tab.alloc((size_t)kMaxClasses * S->nd));
+        const int cnt = kMaxClasses * S->nd;
+        LAUNCH(c, KC_Q_UPDATE, k_class_extract<T>, (cnt + kThreads - 1) / kThreads, (const T*)S->ata.p, ld, S->nd, g,
+               S->ata_tab.p);
+        LAUNCH(c, KC_Q_UPDATE, k_class_verify<T>, c->grid_for(N), (const T*)S->ata.p, ld, S->nd, N, row0, g,
+               (const T*)S->ata_tab.p, d_bad);
+      }
+      int bad = 0;
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      SIPB_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
+      ok = bad ? 0 : 1;
+    }
+    if (c->world > 1) {        // every rank must take the same path (the SpMV kernels differ)
+      double v = ok ? 0.0 : 1.0;
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(c->d_scal, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      int rc = c->allreduce(c->d_scal, 1);
+      if (rc) return rc;
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(&v, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+      SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_scal, 0, sizeof(double), c->stream));
+      ok = v == 0.0;
+    }
+    if (ok) {
+      for (auto& S : sets) S->ata.release();
+      q_classes = true;
+    } else {
+      for (auto& S : sets) S->ata_tab.release();
+    }
+    return SIPB_OK;
+  }
+  // Q (+)= alpha * AtA_i in whichever form the problem holds       (CDS_scaled_add!.jl:16-22)
+  void q_add(SetT<T>& S, T alpha) {
+    sipb_ctx* c = ctx;
+    if (q_classes) {
+      QCols qc;
+      for (int k = 0; k < S.nd; ++k) qc.c[k] = S.qcol[k];
+      const int cnt = kMaxClasses * S.nd;
+      LAUNCH(c, KC_Q_UPDATE, k_class_axpy<T>, (cnt + kThreads - 1) / kThreads, Q_tab.p, (int)q_offs.size(),
+             (const T*)S.ata_tab.p, S.nd, qc, alpha);
+    } else {
+      const int gN = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
+      for (int k = 0; k < S.nd; ++k)
+        LAUNCH(c, KC_Q_UPDATE, k_cds_axpy<T>, gN, N, Q.p + (size_t)S.qcol[k] * ld, (const T*)(S.ata.p + (size_t)k * ld),
+               alpha);
+    }
+  }
+
+  int q_form() const override { return q_classes ? 1 : 0; }
   int q_offsets(std::vector<int64_t>& out) override {
     SIPB_REQUIRE(finalized, SIPB_E_STATE, "problem not finalized");
     out = q_offs;
@@ -891,6 +971,9 @@ struct Problem : sipb_problem {
   SpmvArgs<T> spmv_args(const T* xin, T* yout) const {
     SpmvArgs<T> a;
     a.R = Q.p; a.ld = ld; a.nd = (int)q_offs.size();
+    a.tab = q_classes ? Q_tab.p : nullptr;
+    a.gn[0] = (unsigned)n[0]; a.gn[1] = (unsigned)n[1]; a.gn[2] = (unsigned)n[2];
+    a.npts = (unsigned)(n[0] * n[1] * n[2]);
     for (int j = 0; j < a.nd; ++j) a.off[j] = q_offs[j];
     a.N = N; a.row0 = sg.on ? sg.plane * sg.k0 : 0; a.Nglob = Nglob; a.x = xin; a.y = yout;
     a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
@@ -1290,13 +1373,9 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   }
 
   // Q = sum rho_i AtA_i, accumulated set by set, diagonal by diagonal (:223-229)
-  SIPB_CUDA_CHECK(cudaMemsetAsync(Q.p, 0, (size_t)ld * q_offs.size() * sizeof(T), c->stream));
-  const int gN = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
-  for (int i = 0; i < p; ++i) {
-    SetT<T>& S = *sets[i];
-    for (int k = 0; k < S.nd; ++k)
-      LAUNCH(c, KC_Q_UPDATE, k_cds_axpy<T>, gN, N, Q.p + (size_t)S.qcol[k] * ld, (const T*)(S.ata.p + (size_t)k * ld), rho[i]);
-  }
+  if (q_classes) SIPB_CUDA_CHECK(cudaMemsetAsync(Q_tab.p, 0, (size_t)kMaxClasses * q_offs.size() * sizeof(T), c->stream));
+  else SIPB_CUDA_CHECK(cudaMemsetAsync(Q.p, 0, (size_t)ld * q_offs.size() * sizeof(T), c->stream));
+  for (int i = 0; i < p; ++i) q_add(*sets[i], rho[i]);
   // reset tolerance memory (x_solve_tol_ref = TF(1.0), PARSDMM.jl:93)
   c->h_cg->tol_prev = 1.0;
   SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol_prev, &c->h_cg->tol_prev, sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1517,12 +1596,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     // ---------------- Q update (Q_update!.jl:45-49) -------------------------------------------
     for (int s = 0; s < p; ++s) {
       const T logged = (T)LG(log->rho, i - 1, s, p_log);
-      if (rho[s] != logged) {
-        SetT<T>& S = *sets[s];
-        const T alpha = rho[s] - logged;
-        for (int k = 0; k < S.nd; ++k)
-          LAUNCH(c, KC_Q_UPDATE, k_cds_axpy<T>, gN, N, Q.p + (size_t)S.qcol[k] * ld, (const T*)(S.ata.p + (size_t)k * ld), alpha);
-      }
+      if (rho[s] != logged) q_add(*sets[s], rho[s] - logged);
     }
     phase_end(6);
   }
@@ -1822,6 +1896,14 @@ int sipb_problem_q_offsets(sipb_problem* pb, int64_t* out) {
   for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
   return SIPB_OK;
 }
+int sipb_problem_q_form(sipb_problem* pb, int* form) {
+  SIPB_REQUIRE(pb && form, SIPB_E_INVALID, "null argument");
+  std::vector<int64_t> v;
+  int rc = pb->q_offsets(v);      // fails before finalize
+  if (rc) return rc;
+  *form = pb->q_form();
+  return SIPB_OK;
+}
 int sipb_problem_warm_from(sipb_problem* fine, sipb_problem* coarse, const sipb_resample_seg* segs, int nseg) {
   SIPB_REQUIRE(fine && coarse && segs && nseg >= 0, SIPB_E_INVALID, "null argument");
   SIPB_CUDA_CHECK(cudaSetDevice(fine->ctx->device));
@@ -1877,7 +1959,7 @@ static int cds_spmv_impl(sipb_ctx* c, int64_t N, int nd, const void* R, const in
   a.R = dR.p; a.ld = ld; a.nd = nd;
   for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
   a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
-  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
+  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr;
   LAUNCH(c, KC_SPMV, (k_spmv<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), a, c->rs, (double*)nullptr,
          (const int*)nullptr, c->cd_off);
   SIPB_CUDA_CHECK(cudaGetLastError());
@@ -2026,7 +2108,7 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   a.R = dR.p; a.ld = ld; a.nd = nd;
   for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
   a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
-  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
+  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr;
   const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
   cudaEvent_t e0, e1;
   SIPB_CUDA_CHECK(cudaEventCreate(&e0));

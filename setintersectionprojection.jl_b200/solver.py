@@ -100,6 +100,8 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
         _lib.check(lib.sipb_problem_num_q_offsets(handle, C.byref(nd)))
         qo = np.zeros(nd.value, dtype=np.int64)
         _lib.check(lib.sipb_problem_q_offsets(handle, qo.ctypes.data_as(C.POINTER(C.c_int64))))
+        qf = C.c_int(0)
+        _lib.check(lib.sipb_problem_q_form(handle, C.byref(qf)))
     except Exception:
         lib.sipb_problem_destroy(handle)
         raise
@@ -111,6 +113,7 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
         rows = [sum(b - a for a, b in dd.local_td_slices(A, *slab)) for A in TD_OP]
     dev = _DeviceProblem(handle, _problem_key(TF, TD_OP, P_sub, set_Prop, options), p, pp, N, rows, qo)
     dev.slab = slab
+    dev.q_form = "classes" if qf.value == 1 else "arrays"     # how the device holds Q (sipb_problem_q_form)
     dev.N_global = op0.npts * (2 if options.Minkowski else 1)
     dev.rows_global = [A.rows for A in TD_OP]
     return dev

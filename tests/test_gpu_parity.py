@@ -574,3 +574,48 @@ def test_boundary_error_behaviour(sip):
     # 3-D-only operator on a 2-D grid
     with pytest.raises(ValueError):
         sip.get_TD_operator(sip.compgrid((1.0, 1.0), (8, 8)), "D_y", np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# the two device forms of Q (CDS arrays / stencil-class tables) are the same arithmetic
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["config1_f64", "config2_f32", "odd_grid_f32", "minkowski_f64"])
+def test_q_class_tables_bit_identical_to_arrays(sip, case, monkeypatch):
+    """sipb_problem_q_form: every AtA of get_TD_operator.jl has one value per stencil class, so the solver keeps
+    class tables; SIPB_Q_CLASSES=0 forces the CDS arrays of the reference (Q_update!.jl:45-49, cg.jl:84).
+    Both run the same multiply-adds in the same order: x, l, y and every log entry must agree bit for bit."""
+    def solve():
+        opt = sip.PARSDMM_options()
+        if case == "minkowski_f64":
+            b = pr.build_minkowski(sip, (32, 28), np.float64, opt)
+            b["opt"].maxit = 60
+            m = b["m"]
+        else:
+            spec = {"config1_f64": pr.spec_config1((48, 40), np.float64), "config2_f32": pr.spec_config2((24, 20, 16), np.float32),
+                    "odd_grid_f32": pr.spec_config2((7, 5, 3), np.float32)}[case]
+            b = pr.build(sip, copy.deepcopy(spec), opt)
+            m = spec["m"]
+        x, log, l, y = sip.PARSDMM(m.copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+        return x, log, l, y, b["AtA"]._device.q_form
+
+    xa, la, l_a, y_a, form_a = solve()
+    monkeypatch.setenv("SIPB_Q_CLASSES", "0")
+    xb, lb, l_b, y_b, form_b = solve()
+    assert form_a == "classes" and form_b == "arrays"
+    assert np.array_equal(xa, xb)
+    assert np.array_equal(la.cg_it, lb.cg_it) and np.array_equal(la.obj, lb.obj)
+    assert np.array_equal(la.cg_relres, lb.cg_relres, equal_nan=True) and np.array_equal(la.rho, lb.rho)
+    for a, b in zip(l_a + y_a, l_b + y_b):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_q_class_detection_rejects_irregular_matrix(sip):
+    """An AtA that is not constant per stencil class (one perturbed entry) must stay in array form."""
+    spec = pr.spec_config2((12, 10, 8), np.float32)
+    b = pr.build(sip, copy.deepcopy(spec), sip.PARSDMM_options())
+    b["AtA"][1][137, 0] *= np.float32(1.5)
+    x, log, l, y = sip.PARSDMM(spec["m"].copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+    assert b["AtA"]._device.q_form == "arrays"
+    assert np.all(np.isfinite(x))
