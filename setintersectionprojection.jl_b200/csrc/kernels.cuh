@@ -190,6 +190,64 @@ __device__ __forceinline__ const T* spmv_stage_table(const SpmvArgs<T>& a, T* ta
   return tab_s;
 }
 
+// Fast path of the class form: a group of VW rows whose stencil stays inside the vector (and inside the local
+// slab on the peer path) needs no range checks: offsets live in registers (kFastDiag compile-time slots,
+// 32-bit), the matrix values come from the shared-memory table (mostly broadcast loads) and the loop over the
+// diagonals is fully unrolled.  The selection is warp-uniform except near the two ends of the vector (a
+// per-class selection would split almost every warp: each grid line has two boundary groups).  Groups near
+// the ends, and matrices with nd > kFastDiag, take the generic routine; both evaluate the same expression
+// acc = acc + q_j * x[r + off_j], j = 0..nd-1.
+constexpr int kFastDiag = 8;
+template <typename T>
+struct SpmvFast {
+  int off[kFastDiag];
+  i64 maxoff;
+  bool on;
+  __device__ __forceinline__ void init(const SpmvArgs<T>& a, const T* tab) {
+    i64 mo = 0;
+#pragma unroll
+    for (int j = 0; j < kFastDiag; ++j) {
+      const i64 o = j < a.nd ? a.off[j] : 0;
+      off[j] = (int)o;
+      mo = max(mo, o < 0 ? -o : o);
+    }
+    maxoff = mo;
+    on = tab != nullptr && a.nd <= kFastDiag && mo < ((i64)1 << 30);
+  }
+};
+template <typename T>
+__device__ __forceinline__ void spmv_rows(const SpmvArgs<T>& a, const T* tab, const SpmvFast<T>& f, i64 r,
+                                          T (&acc)[Vec<T>::W]) {
+  constexpr int VW = Vec<T>::W;
+  if (f.on) {
+    const i64 g = a.row0 + r;
+    const bool peer = a.x_lo != nullptr || a.x_hi != nullptr;
+    const bool inside = g >= f.maxoff && g + VW + f.maxoff <= a.Nglob &&
+                        (!peer || (r >= f.maxoff && r + VW + f.maxoff <= a.N));
+    if (inside) {        // warp-uniform except in the first / last plane of the vector
+      unsigned cls[VW];
+      row_classes<VW>(g, a.gn, a.npts, cls);
+      const T* tq[VW];
+#pragma unroll
+      for (int e = 0; e < VW; ++e) tq[e] = tab + cls[e] * a.nd;
+      const T* xr = a.x + r;
+#pragma unroll
+      for (int e = 0; e < VW; ++e) acc[e] = (T)0;
+#pragma unroll
+      for (int j = 0; j < kFastDiag; ++j) {
+        if (j < a.nd) {
+          T xv[VW];
+          load_any<T, VW>(xr + f.off[j], xv);
+#pragma unroll
+          for (int e = 0; e < VW; ++e) acc[e] = acc[e] + tq[e][j] * xv[e];
+        }
+      }
+      return;
+    }
+  }
+  spmv_rows_vec<T>(a, tab, r, acc);
+}
+
 // y = A x  and (DOT) partial sum of x.*y  -> out_dot[0]
 // cd.on: p's neighbour planes are read through peer pointers (after p_wait) and the partial of p.Ap is
 // published to every rank's mailbox instead of being written to out_dot.
@@ -200,6 +258,8 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
   constexpr int VW = Vec<T>::W;
   __shared__ T tab_s[kMaxClasses * kMaxDiag];
   const T* tab = spmv_stage_table<T>(a, tab_s);
+  SpmvFast<T> fast;
+  fast.init(a, tab);
   double d[1] = {0.0};
   const i64 nvec = a.N / VW;
   if (cd.on) {
@@ -214,7 +274,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 r = iv * VW;
     T acc[VW];
-    spmv_rows_vec<T>(a, tab, r, acc);
+    spmv_rows<T>(a, tab, fast, r, acc);
     vstore<T>(a.y + r, acc);
     if (DOT) {
       T xc[VW];
@@ -263,12 +323,14 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
   constexpr int VW = Vec<T>::W;
   __shared__ T tab_s[kMaxClasses * kMaxDiag];
   const T* tab = spmv_stage_table<T>(a, tab_s);
+  SpmvFast<T> fast;
+  fast.init(a, tab);
   double d[2] = {0.0, 0.0};
   const i64 nvec = a.N / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 row = iv * VW;
     T acc[VW], bv[VW], rv[VW];
-    spmv_rows_vec<T>(a, tab, row, acc);
+    spmv_rows<T>(a, tab, fast, row, acc);
     vload_stream<T>(b + row, bv);
 #pragma unroll
     for (int e = 0; e < VW; ++e) {
