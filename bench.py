@@ -9,8 +9,9 @@ l1 ball ∩ lateral slope bounds (examples/test_scaling_3D.jl-style).  value = P
 
 * device arm (default): `value` with the problem and m resident in HBM (CUDA-event time of the solves),
   `e2e` through the public API `sip_b200.PARSDMM(m, ...)` with host buffers (H2D of m, D2H of x and log
-  inside the timed region), the roofline of the dominant kernel (CDS SpMV + dot) from a CUDA-event
-  kernel table, and a bounded CPU baseline (the NumPy oracle, rank 0, N=1 only).
+  inside the timed region), the roofline of the dominant kernel class (largest share of the solve; its
+  algorithmic bytes are counted by the library at every launch) from a CUDA-event kernel table, and a
+  bounded CPU baseline (the NumPy oracle, rank 0, N=1 only).
 * --impl reference: the reference's CPU algorithm (oracle port; Julia is not installable here) on the
   host cores, same workload/metric, each step a bounded sample (a few PARSDMM iterations).
 
@@ -273,27 +274,35 @@ def run_device(args, rank, world, local_rank):
     _, lgp, _, _ = call(resident_io=True, profile_kernels=True)      # every rank: the solve contains collectives
     if rank == 0:
         kernels = lgp.timing["kernels"]
-        nd = len(sb["AtA"]._device.q_offsets)
-        alg = (nd + 2) * (N // world) * 4           # per GPU
-        cnt_k, ms_k = kernels.get("cds_spmv_dot", (0, 0.0))
+        kbytes = lgp.timing["kernel_bytes"]         # algorithmic bytes per class, counted by the library at launch
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
             peak, which = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
         else:
             peak, which = 6650.0, "fallback"
-        if cnt_k:
+        tot_ms = sum(v[1] for v in kernels.values())
+        streaming = {k: v for k, v in kernels.items() if kbytes.get(k) and v[1] > 0}
+        if streaming:
+            top = max(streaming, key=lambda k: streaming[k][1])       # the class with the largest share of the solve
+            cnt_k, ms_k = streaming[top]
+            alg = kbytes[top] / cnt_k
             avg_ms = ms_k / cnt_k
             ach = alg / (avg_ms * 1e-3) / 1e9
-            tot_ms = sum(v[1] for v in kernels.values())
             traffic = None       # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-            tpath = os.path.join(ROOT, "profiles", "r01_spmv_traffic.json")
+            tpath = os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")
             if os.path.exists(tpath) and world == 1 and args.workload == "config2":
                 tj = json.load(open(tpath))
-                if tj.get("grid") == [n, n, nz]:
-                    traffic = tj["dram_bytes_per_launch"]
-            roof = {"bound": "hbm", "kernel": "cds_spmv_dot", "achieved": ach, "peak": peak, "peak_source": which,
+                if tj.get("grid") == [n, n, nz] and top in tj.get("kernels", {}):
+                    traffic = tj["kernels"][top]["dram_bytes_per_launch"]
+            roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "peak_source": which,
                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg,
-                    "avg_launch_ms": avg_ms, "launches": cnt_k, "share_of_kernel_time": ms_k / tot_ms if tot_ms else None}
+                    "avg_launch_ms": avg_ms, "launches": cnt_k, "share_of_kernel_time": ms_k / tot_ms if tot_ms else None,
+                    "q_form": sb["AtA"]._device.q_form,
+                    "per_kernel": {k: {"launches": v[0], "ms": round(v[1], 3), "gbs": round(kbytes[k] / (v[1] * 1e-3) / 1e9, 1),
+                                       "frac": round(kbytes[k] / (v[1] * 1e-3) / 1e9 / peak, 3)} for k, v in streaming.items()},
+                    "whole_solve": {"algorithmic_gb": round(sum(kbytes.values()) / 1e9, 3), "kernel_ms": round(tot_ms, 3),
+                                    "gbs": round(sum(kbytes.values()) / (tot_ms * 1e-3) / 1e9, 1),
+                                    "frac": round(sum(kbytes.values()) / (tot_ms * 1e-3) / 1e9 / peak, 3)}}
 
     if rank != 0:
         if dist is not None:
@@ -322,7 +331,7 @@ def run_device(args, rank, world, local_rank):
                                   "slab-iterations/s = %d x PARSDMM iterations/s (one %d^3 slab per GPU)" % (units, n),
                    "step": "one full PARSDMM projection to the reference's stopping rules",
                    "parsdmm_iterations_per_step": iters_per_step, "time_to_tolerance_ms": 1e3 * dev_s_max / args.steps,
-                   "cache": "working set %.1f GB (Q + AtA + 9 vectors per set) >> 126 MB L2, no flush needed" % (N * 4 * 105 / 1e9),
+                   "cache": "working set %.1f GB (x-side vectors + 8 vectors per set) >> 126 MB L2, no flush needed" % (N * 4 * 60 / 1e9),
                    "parallelism": "single GPU" if world == 1 else
                                   "z-slabs over %d GPUs (%s), %s scaling" % (
                                       world, "peer-memory CG reductions + neighbour-plane loads over NVLink (CUDA IPC), NCCL for the "

@@ -139,6 +139,9 @@ typedef struct sipb_log {
   /* kernel table (profile_kernels=1): launches and summed CUDA-event milliseconds per class */
   int64_t kernel_launches[SIPB_N_KERNEL_CLASSES];
   double  kernel_ms[SIPB_N_KERNEL_CLASSES];
+  double  kernel_bytes[SIPB_N_KERNEL_CLASSES];  /* algorithmic bytes moved by the class (always counted): every array
+                                             a kernel must read or write once, gathered vectors with perfect reuse;
+                                             launches queued behind a finished CG count nothing                 */
   int64_t total_launches;                 /* all kernel launches inside sipb_solve (always counted) */
   int64_t h2d_bytes, d2h_bytes;
 } sipb_log;

@@ -27,7 +27,7 @@ mutable struct Log        # sipb_log (arrays are caller-allocated, maxit rows, r
     r_dual_total::Ptr{Float64}; r_pri_total::Ptr{Float64}; obj::Ptr{Float64}; evol_x::Ptr{Float64}
     rho::Ptr{Float64}; gamma::Ptr{Float64}; cg_it::Ptr{Int32}; cg_relres::Ptr{Float64}
     phase_seconds::NTuple{7,Float64}; solve_seconds::Float64; device_seconds::Float64
-    kernel_launches::NTuple{24,Int64}; kernel_ms::NTuple{24,Float64}
+    kernel_launches::NTuple{24,Int64}; kernel_ms::NTuple{24,Float64}; kernel_bytes::NTuple{24,Float64}
     total_launches::Int64; h2d_bytes::Int64; d2h_bytes::Int64
 end
 

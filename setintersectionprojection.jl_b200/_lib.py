@@ -65,6 +65,7 @@ class Log(C.Structure):
                 ("phase_seconds", C.c_double * N_PHASES), ("solve_seconds", C.c_double),
                 ("device_seconds", C.c_double),
                 ("kernel_launches", C.c_int64 * N_KERNEL_CLASSES), ("kernel_ms", C.c_double * N_KERNEL_CLASSES),
+                ("kernel_bytes", C.c_double * N_KERNEL_CLASSES),
                 ("total_launches", C.c_int64), ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64)]
 
 

@@ -313,6 +313,7 @@ struct CgState {
   int flag;         // 0 / -1 / -2 / -9 as cg.jl:29-37
   int maxit;
   int parsdmm_it;   // i of PARSDMM.jl:97 (selects the i<3 tolerance rule); 0 => plain cg with tol given
+  int loops;        // loop iterations actually executed (speculative launches after `done` return at once)
 };
 
 // r = b - Q x ; p = r ; (x_old = x) ; sums bb, rr
@@ -391,6 +392,7 @@ __global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd) {
   const T nb = (T)sqrt(st->bb);
   const T nr = (T)sqrt(st->rr);
   st->iter = 0;
+  st->loops = 0;
   st->done = 0;
   st->flag = -1;
   st->relres = 0.0;
@@ -462,6 +464,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
       if (threadIdx.x == 0) {
         st->flag = -2;          // "Matrix A in cg has to be positive definite"
         st->iter = st->iter + 1;
+        st->loops = st->loops + 1;
         st->relres = 0.0;       // resvec[lastIter] never written
         st->done = 1;
       }
@@ -511,6 +514,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
   }
   if (last_block_ticket(rs.counter, sys) && threadIdx.x == 0) {
     st->iter = it;
+    st->loops = st->loops + 1;
     st->relres = (double)res;
     if (conv) {
       st->flag = 0;

@@ -194,12 +194,16 @@ struct sipb_ctx {
   bool profile = false;
   int64_t launches[SIPB_N_KERNEL_CLASSES];
   double ms[SIPB_N_KERNEL_CLASSES];
+  double bytes[SIPB_N_KERNEL_CLASSES];
   int64_t total_launches = 0;
   struct EvPair { cudaEvent_t a, b; int cls; };
   std::vector<EvPair> ev_used;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  // algorithmic bytes of the launches of a class: every array the kernel has to read or write counted once
+  // (perfect reuse of gathered vectors), the numerator of the roofline in bench.py / DESIGN.md
+  void account(int cls, double nbytes) { bytes[cls] += nbytes; }
   void reset_accounting() {
-    for (int i = 0; i < SIPB_N_KERNEL_CLASSES; ++i) { launches[i] = 0; ms[i] = 0.0; }
+    for (int i = 0; i < SIPB_N_KERNEL_CLASSES; ++i) { launches[i] = 0; ms[i] = 0.0; bytes[i] = 0.0; }
     total_launches = 0;
   }
   int max_grid() const { return std::min(num_sms * 8, kMaxBlocks); }
@@ -1142,6 +1146,9 @@ struct Problem : sipb_problem {
     const CommDev& cd = peer ? c->cd_on : c->cd_off;
     T* pp = pv();
     LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+    const double vecN = (double)N * sizeof(T);
+    const double q_rows = q_classes ? 0.0 : (double)q_offs.size();       // matrix words streamed per row
+    c->account(KC_CG_INIT, (q_rows + 4 + (x_old_out ? 1 : 0)) * vecN);   // Q, x, b -> r, p (, x_old)
     if (!peer && (rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
     LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg, cd);
     int launched = 0;
@@ -1164,6 +1171,10 @@ struct Problem : sipb_problem {
       if (h->done || launched >= max_iter) break;
       batch = std::max(2, launched / 2);
     }
+    // bytes of the loop iterations that ran (launches queued behind `done` return immediately and move nothing)
+    c->account(KC_SPMV_DOT, h->loops * (q_rows + 2) * vecN);                          // Q, p -> Ap
+    c->account(KC_CG_XR, h->loops * 6 * vecN);                                        // x, r, p, Ap -> x, r
+    c->account(KC_CG_P, std::max(0, h->loops - (h->flag == 0 ? 1 : 0)) * 3 * vecN);   // r, p -> p
     if (h->flag == -9) SIPB_CUDA_CHECK(cudaMemsetAsync(xv, 0, N * sizeof(T), c->stream));   // cg.jl:47
     if ((rc = exchange(xv, sg.nloc(), true, true))) return rc;              // halo planes of the new x
     *iters = h->iter;
@@ -1330,7 +1341,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     log->feas_rows = 1;
     log->total_launches = c->total_launches;
     c->collect_profile();
-    for (int q = 0; q < SIPB_N_KERNEL_CLASSES; ++q) { log->kernel_launches[q] = c->launches[q]; log->kernel_ms[q] = c->ms[q]; }
+    for (int q = 0; q < SIPB_N_KERNEL_CLASSES; ++q) {
+      log->kernel_launches[q] = c->launches[q];
+      log->kernel_ms[q] = c->ms[q];
+      log->kernel_bytes[q] = c->bytes[q];
+    }
     phase_end(0);
     log->solve_seconds = now_s() - t_begin;
     log->device_seconds = 0.0;
@@ -1405,6 +1420,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         ra.sets[s].y_old = sets[s]->y_old.p;
         ra.sets[s].rho = rho[s];
       }
+      {
+        double rows = 0;
+        for (int s = 0; s < p; ++s) rows += (double)sets[s]->M;
+        c->account(KC_RHS, ((fuse_rdual && i >= 2 ? 3 : 2) * rows + (double)N) * sizeof(T));   // y, l (, y_old) -> rhs
+      }
       // from the second iteration on the gather also yields the dual residual of iteration i-1
       if (fuse_rdual && i >= 2)
         LAUNCH(c, KC_RHS, (k_rhs<T, true>), c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W)), ra, c->rs,
@@ -1459,7 +1479,12 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       ya.do_snapshot = fuse_adapt ? 1 : 0;
       const int base = s * kSlotPerSet;
       const int g = c->grid_for((S.M + Vec<T>::W - 1) / Vec<T>::W);
+      // streams of M rows: l in, y and l out, y_old in when relaxed or adapting, 4 snapshots in / out
+      const double rowsB = (double)S.M * sizeof(T), colsB = (double)N * sizeof(T);
+      const bool needs_yold = fuse_adapt || !(gamma[s] == (T)1);
+      const double adaptB = (fuse_adapt ? 4 : 0) * rowsB + (ya.do_sums ? 4 : 0) * rowsB;
       if (proj_is_elementwise(S.desc.set_kind)) {
+        c->account(KC_YL_FUSED, colsB + (3 + (needs_yold ? 1 : 0)) * rowsB + adaptB);
         // element-wise sets are gathered and updated by one launch per (up to) kYlMulti sets
         ya.want_feas = want_feas ? 1 : 0;
         ym.a[n_multi] = ya;
@@ -1469,6 +1494,8 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       } else {
         ya.want_feas = 0;
         LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), g, ya, c->rs, c->d_scal + base + 10);
+        c->account(KC_YL_PASS1, colsB + (3 + (!(gamma[s] == (T)1) ? 1 : 0)) * rowsB);     // x, l (, y_old) -> v, s
+        c->account(KC_YL_PASS2, (5 + (needs_yold ? 1 : 0)) * rowsB + adaptB);             // v, s, l (, y_old) -> y, l
         int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
         if (rc) return rc;
         ya.dyn = S.pp_y.p;
@@ -1491,6 +1518,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     { int rc = exchange_yl_halos(); if (rc) return rc; }   // slabs: halo planes for the next rhs gather
     LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
            (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
+    c->account(KC_STOP, 3.0 * N * sizeof(T));                              // x, x_old, m
     { int rc = ctx_sync_scalars(c); if (rc) return rc; }
     {
       T rp_tot = 0, rd_tot = 0;
@@ -1642,7 +1670,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   log->feas_rows = counter;       // output_check_PARSDMM keeps set_feasibility[1:counter,:]
   c->collect_profile();
   log->total_launches = c->total_launches;
-  for (int q = 0; q < SIPB_N_KERNEL_CLASSES; ++q) { log->kernel_launches[q] = c->launches[q]; log->kernel_ms[q] = c->ms[q]; }
+  for (int q = 0; q < SIPB_N_KERNEL_CLASSES; ++q) {
+      log->kernel_launches[q] = c->launches[q];
+      log->kernel_ms[q] = c->ms[q];
+      log->kernel_bytes[q] = c->bytes[q];
+    }
   log->solve_seconds = now_s() - t_begin;
   return SIPB_OK;
 }

@@ -241,6 +241,8 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
     timing["h2d_bytes"], timing["d2h_bytes"] = int(lg.h2d_bytes), int(lg.d2h_bytes)
     timing["kernels"] = {lib.sipb_kernel_class_name(i).decode(): (int(lg.kernel_launches[i]), float(lg.kernel_ms[i]))
                          for i in range(_lib.N_KERNEL_CLASSES) if lg.kernel_launches[i]}
+    timing["kernel_bytes"] = {lib.sipb_kernel_class_name(i).decode(): float(lg.kernel_bytes[i])
+                              for i in range(_lib.N_KERNEL_CLASSES) if lg.kernel_bytes[i]}
     timing["stopped_feasible"] = bool(lg.stopped_feasible)
     log = log_type_PARSDMM(
         set_feasibility=arr["set_feasibility"][:rows_f, :pp], r_dual=arr["r_dual"][:it], r_pri=arr["r_pri"][:it],

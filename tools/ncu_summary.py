@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Summarise Nsight Compute exports into the small, reviewable tables kept under profiles/.
 
-  tools/ncu_summary.py launches <launches.csv>          # per-kernel totals / shares of a --metrics launch list
+  tools/ncu_summary.py launches <launches.csv> [traffic.json nx ny nz]
+                                                        # per-kernel totals / shares (and DRAM bytes per launch) of a
+                                                        # --metrics launch list; optional per-class traffic JSON for bench.py
   tools/ncu_summary.py full <raw.csv>                   # one line per profiled launch of an `ncu --page raw --csv` dump
 """
 import collections
@@ -18,23 +20,56 @@ FULL_COLS = [
 ]
 
 
-def launches(path):
+CLASS_OF = [   # kernel class of the library's table (sipb_kernel_class_name) <- kernel function prefix
+    ("yl_update_fused", "k_yl_multi<"), ("yl_update_pass1", "k_yl<float, 1,"), ("yl_update_pass2", "k_yl<float, 2,"),
+    ("cds_spmv_dot", "k_spmv<float, 1>"), ("cg_init", "k_cg_init<"), ("cg_update_xr", "k_cg_xr<"),
+    ("cg_update_p", "k_cg_p<"), ("rhs_compose", "k_rhs<"), ("stop_reduce", "k_stop<"), ("l1_threshold_pass", "k_l1_pass<"),
+]
+
+
+def launches(path, traffic_json=None, grid=None):
+    """Launch list of `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum] --csv`."""
     rows = list(csv.reader(open(path, errors="ignore")))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr = rows[hi]
-    kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
-    agg = collections.defaultdict(lambda: [0, 0.0])
+    kn, mn, mv, idc = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("ID")
+    agg = collections.defaultdict(lambda: {"ids": set(), "ns": 0.0, "rd": 0.0, "wr": 0.0})
     for r in rows[hi + 1:]:
         if len(r) <= mv:
             continue
-        name = r[kn].split("(")[0].replace("void ", "")
-        agg[name][0] += 1
-        agg[name][1] += float(r[mv].replace(",", ""))
-    tot = sum(v[1] for v in agg.values())
-    print("| kernel | launches | total us | share |\n|---|---:|---:|---:|")
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print("| `%s` | %d | %.1f | %.1f %% |" % (k, v[0], v[1] / 1e3, 100 * v[1] / tot))
-    print("\ntotal %.1f us over %d launches" % (tot / 1e3, sum(v[0] for v in agg.values())))
+        name = r[kn].replace("void ", "")
+        name = name[:name.index("(")] if "(" in name else name
+        a = agg[name]
+        a["ids"].add(r[idc])
+        v = float(r[mv].replace(",", ""))
+        if r[mn] == "gpu__time_duration.sum":
+            a["ns"] += v
+        elif r[mn] == "dram__bytes_read.sum":
+            a["rd"] += v
+        elif r[mn] == "dram__bytes_write.sum":
+            a["wr"] += v
+    tot = sum(v["ns"] for v in agg.values())
+    has_dram = any(v["rd"] or v["wr"] for v in agg.values())
+    print("| kernel | launches | total us | share |" + (" DRAM rd MB/launch | DRAM wr MB/launch |" if has_dram else "") +
+          "\n|---|---:|---:|---:|" + ("---:|---:|" if has_dram else ""))
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
+        n = len(v["ids"])
+        line = "| `%s` | %d | %.1f | %.1f %% |" % (k, n, v["ns"] / 1e3, 100 * v["ns"] / tot)
+        if has_dram:
+            line += " %.1f | %.1f |" % (v["rd"] / n / 1e6, v["wr"] / n / 1e6)
+        print(line)
+    print("\ntotal %.1f us over %d launches" % (tot / 1e3, sum(len(v["ids"]) for v in agg.values())))
+    if traffic_json and has_dram:
+        import json
+        out = {"grid": grid, "source": path, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged "
+               "over all launches of the kernel class in the launch list (cold-cache, serialised replays)", "kernels": {}}
+        for cls, prefix in CLASS_OF:
+            sel = [v for k, v in agg.items() if k.startswith(prefix)]
+            n = sum(len(v["ids"]) for v in sel)
+            if n:
+                out["kernels"][cls] = {"dram_bytes_per_launch": sum(v["rd"] + v["wr"] for v in sel) / n, "launches": n,
+                                       "avg_us": sum(v["ns"] for v in sel) / n / 1e3}
+        json.dump(out, open(traffic_json, "w"), indent=1)
 
 
 def full(path):
@@ -64,4 +99,8 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "launches":      # launches <csv> [traffic.json nx ny nz]
+        extra = sys.argv[3:]
+        launches(sys.argv[2], extra[0] if extra else None, [int(v) for v in extra[1:4]] if len(extra) >= 4 else None)
+    else:
+        full(sys.argv[2])
