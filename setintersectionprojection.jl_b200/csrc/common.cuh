@@ -168,6 +168,7 @@ struct CommDev {
   int* err;                          // device flag: a bounded spin timed out
   unsigned long long* seq;           // device counter: mailbox reductions produced by this rank
   unsigned long long* pv;            // device counter: version of this rank's p vector
+  unsigned long long* bseq;          // device-local flag: last reduction whose global value is in place
   PeerMail* mail[kMaxRanks];         // mail[q]: rank q's mailbox (peer mapped; mail[rank] is local)
 };
 
@@ -224,6 +225,31 @@ __device__ __forceinline__ void mail_collect(const CommDev& cd, double* out) {
   }
 #pragma unroll
   for (int i = 0; i < K; ++i) out[i] = acc[i];
+}
+
+// Collect inside the CONSUMER kernel (every thread of every block calls this before reading out[]): block 0 is
+// the single poller of the peer-written mailbox line; it stores the global value and releases a device-LOCAL
+// sequence flag on which thread 0 of the other blocks waits.  Saves the one-thread collector kernel (two kernel
+// boundaries, ~5 us) per reduction.  Block 0 is dispatched first and waits for nothing on this GPU, so the
+// other blocks cannot starve it.  Read out[] with ld_vol afterwards (L1 may hold the line from an earlier read).
+template <int K>
+__device__ __forceinline__ void mail_collect_all(const CommDev& cd, double* out) {
+  if (threadIdx.x == 0) {
+    const unsigned long long seq = *cd.seq;
+    if (blockIdx.x == 0) {
+      mail_collect<K>(cd, out);
+      __threadfence();
+      *reinterpret_cast<volatile unsigned long long*>(cd.bseq) = seq;
+    } else {
+      const long long t0 = clock64();
+      while (ld_vol(cd.bseq) < seq) {
+        __nanosleep(32);
+        if (clock64() - t0 > kSpinLimit) { *cd.err = 1; break; }
+      }
+      __threadfence();
+    }
+  }
+  __syncthreads();
 }
 
 // thread 0 of the LAST block of a kernel that rewrote p (every block fenced at system scope before its ticket)

@@ -427,7 +427,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
                                                     RedScratch rs, CgState* st, const __grid_constant__ CommDev cd) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
-  const double pAp = st->pAp;       // peer path: made global by k_mail_collect
+  if (cd.on) mail_collect_all<1>(cd, &st->pAp);      // peer path: sum the ranks' partials of p.Ap
+  const double pAp = ld_vol(&st->pAp);
   const T gamma = (T)st->rr;
   const T alpha = gamma / (T)pAp;
   const bool bad = (alpha == (T)INFINITY) || (alpha < (T)0);   // cg.jl:91
@@ -483,7 +484,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
                                                    i64 halo) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
-  const double rr_new = st->rr_new;   // peer path: made global by k_mail_collect
+  if (cd.on) mail_collect_all<1>(cd, &st->rr_new);   // peer path: sum the ranks' partials of r.r
+  const double rr_new = ld_vol(&st->rr_new);
   const T nb = (T)sqrt(st->bb);
   const T res = (T)sqrt(rr_new) / nb;
   const bool conv = res <= (T)st->tol;
@@ -1215,8 +1217,10 @@ __global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict
     }
   }
 }
-__global__ void k_l1_step(L1State* st) {
+// one thread; peer path: first sums the ranks' (C, S) partials from the mailbox (C and S are adjacent)
+__global__ void k_l1_step(L1State* st, const __grid_constant__ CommDev cd) {
   if (st->done) return;
+  if (cd.on) mail_collect<2>(cd, &st->C);
   l1_newton_step(st, st->C, st->S);
 }
 

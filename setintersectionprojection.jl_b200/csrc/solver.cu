@@ -158,7 +158,7 @@ struct sipb_ctx {
   bool p2p = false;
   PeerMail* d_mail = nullptr;                      // this rank's mailbox (exported)
   void* peer_mail_base[kMaxRanks] = {nullptr};     // imported mappings (to close)
-  unsigned long long* d_seq_pv = nullptr;          // [0] seq, [1] pv
+  unsigned long long* d_seq_pv = nullptr;          // [0] seq, [1] pv, [2] bseq
   int* d_p2p_err = nullptr;
   int* h_p2p_err = nullptr;
   CommDev cd_on;                                   // descriptor with the peer path active
@@ -724,14 +724,17 @@ struct Problem : sipb_problem {
   // the y_old halo is the previous y halo: it travels with the buffer when y and y_old trade places
   int exchange_yl_halos() {
     if (!sg.on) return SIPB_OK;
+    SIPB_NCCL_CHECK(NCCL(GroupStart)());      // one fused NCCL launch for all planes of all sets
+    int rc = SIPB_OK;
     for (auto& S : sets) {
       if (!S->z_halo) continue;
-      int rc = exchange(S->y.p, sg.nz_rows(), true, false);
-      if (rc) return rc;
+      rc = exchange(S->y.p, sg.nz_rows(), true, false);
+      if (rc) break;
       rc = exchange(S->l.p, sg.nz_rows(), true, false);
-      if (rc) return rc;
+      if (rc) break;
     }
-    return SIPB_OK;
+    SIPB_NCCL_CHECK(NCCL(GroupEnd)());
+    return rc;
   }
 
   int add_set(const sipb_set_desc* d) override {
@@ -1041,9 +1044,8 @@ struct Problem : sipb_problem {
           LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for((M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused,
                  peer ? c->cd_on : c->cd_off);
           if (!fused) {
-            if (peer) LAUNCH1(c, KC_PARAMS, k_mail_collect<2>, c->cd_on, &c->d_l1->C, (const int*)&c->d_l1->done);
-            else if ((rc = c->allreduce(&c->d_l1->C, 2))) return rc;
-            LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1);
+            if (!peer && (rc = c->allreduce(&c->d_l1->C, 2))) return rc;
+            LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1, peer ? c->cd_on : c->cd_off);
           }
         }
         launched += batch;
@@ -1157,11 +1159,9 @@ struct Problem : sipb_problem {
       for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
         if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
         LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
-        if (peer) LAUNCH1(c, KC_PARAMS, k_mail_collect<1>, cd, &c->d_cg->pAp, (const int*)&c->d_cg->done);
-        else if ((rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;
+        if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;      // peer path: collected inside k_cg_xr
         LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
-        if (peer) LAUNCH1(c, KC_PARAMS, k_mail_collect<1>, cd, &c->d_cg->rr_new, (const int*)&c->d_cg->done);
-        else if ((rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;
+        if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;   // peer path: collected inside k_cg_p
         LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0);
       }
       SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
@@ -1782,8 +1782,8 @@ static int comm_setup_p2p(sipb_ctx* c) {
   memset(&mine, 0, sizeof(mine));
   if (ok) {
     ok = cudaMalloc(&c->d_mail, sizeof(PeerMail)) == cudaSuccess && cudaMemset(c->d_mail, 0, sizeof(PeerMail)) == cudaSuccess &&
-         cudaMalloc(&c->d_seq_pv, 2 * sizeof(unsigned long long)) == cudaSuccess &&
-         cudaMemset(c->d_seq_pv, 0, 2 * sizeof(unsigned long long)) == cudaSuccess &&
+         cudaMalloc(&c->d_seq_pv, 3 * sizeof(unsigned long long)) == cudaSuccess &&
+         cudaMemset(c->d_seq_pv, 0, 3 * sizeof(unsigned long long)) == cudaSuccess &&
          cudaMalloc(&c->d_p2p_err, sizeof(int)) == cudaSuccess && cudaMemset(c->d_p2p_err, 0, sizeof(int)) == cudaSuccess &&
          cudaMallocHost(&c->h_p2p_err, sizeof(int)) == cudaSuccess &&
          cudaIpcGetMemHandle(&mine, c->d_mail) == cudaSuccess;
@@ -1818,6 +1818,7 @@ static int comm_setup_p2p(sipb_ctx* c) {
     c->cd_on.err = c->d_p2p_err;
     c->cd_on.seq = c->d_seq_pv;
     c->cd_on.pv = c->d_seq_pv + 1;
+    c->cd_on.bseq = c->d_seq_pv + 2;
   }
   return SIPB_OK;
 }
