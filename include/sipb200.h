@@ -59,6 +59,7 @@ extern "C" {
 #define SIPB_OP_DZ       3   /* last axis             : offset n1 (2-D) or n1*n2 (3-D) */
 #define SIPB_OP_TV       4   /* vcat(D_z[,D_y],D_x)   (get_discrete_Grad.jl:33,69-72)  */
 #define SIPB_OP_DXZ      5   /* D_z*D_x, 2-D only     (get_TD_operator.jl:69-73)       */
+#define SIPB_OP_SPARSE   6   /* explicit sparse matrix: constraint.custom_TD_OP[1] (setup_constraints.jl:70-72) */
 
 /* Minkowski block placement of an operator (PARSDMM_precompute_distribute_Minkowski.jl:78-88) */
 #define SIPB_BLOCK_PLAIN 0   /* A       (N columns)  */
@@ -71,6 +72,19 @@ typedef struct sipb_problem sipb_problem;
 
 /* One term of the intersection: projector + operator.  Replaces one entry of the reference's
  * (P_sub[i], TD_OP[i], set_Prop.*[i]) triple (setup_constraints.jl:17-102). */
+/* An explicit sparse transform-domain operator (SparseMatrixCSC of the reference) in both orientations, host
+ * arrays, 0-based.  Products follow SparseArrays: (A*x)[r] is a left fold over the stored columns of row r in
+ * ascending column order, (A'*v)[c] over the stored rows of column c in ascending row order. */
+typedef struct sipb_sparse {
+  int64_t rows, cols, nnz;
+  const int64_t* rowptr;   /* [rows+1]  CSR of A                                  */
+  const int32_t* colidx;   /* [nnz]     ascending inside a row                    */
+  const void*    val;      /* [nnz]     TF                                        */
+  const int64_t* colptr;   /* [cols+1]  CSC of A (colptr/rowval/nzval of Julia, minus 1) */
+  const int32_t* rowidx;   /* [nnz]     ascending inside a column                 */
+  const void*    valt;     /* [nnz]     TF                                        */
+} sipb_sparse;
+
 typedef struct sipb_set_desc {
   int32_t set_kind;        /* SIPB_SET_*                                                       */
   int32_t op_kind;         /* SIPB_OP_*                                                        */
@@ -84,6 +98,7 @@ typedef struct sipb_set_desc {
   int32_t fiber_axis;      /* fiber modes (app_mode ("fiber","x"|"y"|"z")): 0, 1 or 2 — axis of the transform-domain grid */
   int32_t reserved;
   int64_t td_n[3];         /* fiber modes: set_Prop.TD_n[i], the transform-domain grid (third entry 1 in 2-D)  */
+  const sipb_sparse* sparse;  /* SIPB_OP_SPARSE: the matrix (copied to the device by sipb_problem_add_set), else NULL */
 } sipb_set_desc;
 
 /* Mirror of PARSDMM_options (SetIntersectionProjection.jl:110-128) after convert_options!. */
@@ -229,6 +244,8 @@ int sipb_project(sipb_ctx* ctx, int dtype, const sipb_set_desc* desc, int64_t M,
 int sipb_op_apply(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const double* h, int op_kind,
                   int block_mode, int adjoint, const void* in, void* out);
 int sipb_op_rows(int ndim, const int64_t* n, int op_kind, int64_t* rows);
+/* the same for an explicit sparse operator (SIPB_OP_SPARSE) */
+int sipb_sparse_apply(sipb_ctx* ctx, int dtype, const sipb_sparse* A, int adjoint, const void* in, void* out);
 /* Q += alpha*B on matching diagonals (CDS_scaled_add!.jl:8-26). */
 int sipb_cds_scaled_add(sipb_ctx* ctx, int dtype, int64_t N, int nd_a, void* A, const int64_t* a_offsets,
                         int nd_b, const void* B, const int64_t* b_offsets, double alpha);

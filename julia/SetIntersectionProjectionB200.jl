@@ -7,10 +7,18 @@
 module SIPB200
 const lib = joinpath(@__DIR__, "libsipb200.so")
 
+struct SparseOp           # sipb_sparse: custom_TD_OP[1] as CSR (of A) and CSC (colptr/rowval/nzval .- 1), host arrays
+    rows::Int64; cols::Int64; nnz::Int64
+    rowptr::Ptr{Int64}; colidx::Ptr{Int32}; val::Ptr{Cvoid}
+    colptr::Ptr{Int64}; rowidx::Ptr{Int32}; valt::Ptr{Cvoid}
+end
+
 struct SetDesc            # sipb_set_desc
     set_kind::Int32; op_kind::Int32; block_mode::Int32; ncvx::Int32
     min::Float64; max::Float64; k::Int64
     min_vec::Ptr{Cvoid}; max_vec::Ptr{Cvoid}
+    fiber_axis::Int32; reserved::Int32; td_n::NTuple{3,Int64}     # fiber modes: axis and set_Prop.TD_n[i]
+    sparse::Ptr{SparseOp}                                         # custom_TD_OP (op_kind 6), else C_NULL
 end
 
 struct Options            # sipb_options
@@ -18,7 +26,7 @@ struct Options            # sipb_options
     adjust_feasibility_rho::Int32; zero_ini_guess::Int32; n_rho_ini::Int32; profile_kernels::Int32
     evol_rel_tol::Float64; feas_tol::Float64; obj_tol::Float64; gamma_ini::Float64
     rho_ini::Ptr{Float64}
-    fixed_iterations::Int32; return_ly::Int32; resident_io::Int32; reserved::Int32
+    fixed_iterations::Int32; return_ly::Int32; resident_io::Int32; warm_resident::Int32
 end
 
 mutable struct Log        # sipb_log (arrays are caller-allocated, maxit rows, row-major)
@@ -35,6 +43,7 @@ check(rc) = rc == 0 || error(unsafe_string(ccall((:sipb_last_error, lib), Cstrin
 
 struct DeviceProjector{TF}        # still callable on a CPU vector: P(v) -> sipb_project
     set_kind::Int32; min::Union{TF,Vector{TF}}; max::Union{TF,Vector{TF}}; k::Int64
+    fiber_axis::Int32; td_n::NTuple{3,Int64}      # ("fiber","x"|"y"|"z") modes of bounds / cardinality
 end
 
 const ctx = Ref{Ptr{Cvoid}}(C_NULL)
@@ -58,7 +67,9 @@ function device_problem(::Type{TF}, AtA, TD_OP, set_Prop, P_sub, comp_grid, opti
                     (i <= pp && P.min isa Real) ? P.min : 0.0, (i <= pp && P.max isa Real) ? P.max : 0.0,
                     i <= pp ? P.k : 0,
                     (i <= pp && P.min isa Vector) ? pointer(P.min) : C_NULL,
-                    (i <= pp && P.max isa Vector) ? pointer(P.max) : C_NULL)
+                    (i <= pp && P.max isa Vector) ? pointer(P.max) : C_NULL,
+                    i <= pp ? P.fiber_axis : 0, 0, i <= pp ? P.td_n : (0, 0, 0),
+                    C_NULL)    # custom_TD_OP: Ref(SparseOp(...)) built from TD_OP[i] (CSC as stored, CSR = sparse(TD_OP[i]'))
         check(ccall((:sipb_problem_add_set, lib), Cint, (Ptr{Cvoid}, Ref{SetDesc}), pb[], d))
         R = AtA[i]::Matrix{TF}; off = Int64.(set_Prop.AtA_offsets[i])      # exactly what mat2CDS returned
         GC.@preserve R off check(ccall((:sipb_problem_set_ata, lib), Cint,

@@ -15,7 +15,7 @@ The directory name contains a dot, so import it through the `sip_b200` shim at t
 from . import _lib
 from .types import (PARSDMM_options, compgrid, convert_options, default_PARSDMM_options, log_type_PARSDMM,
                     set_definitions, set_properties)
-from .operators import (CDS_MVp, CDS_MVp_MT, CDS_scaled_add, TDOperator, cg, get_TD_operator, get_discrete_Grad,
+from .operators import (CDS_MVp, CDS_MVp_MT, CDS_scaled_add, SparseOperator, TDOperator, cg, get_TD_operator, get_discrete_Grad,
                         mat2CDS)
 from .constraints import Projector, get_projector, setup_constraints
 from .precompute import PARSDMM_precompute_distribute, PARSDMM_precompute_distribute_Minkowski
@@ -26,7 +26,7 @@ from .multilevel import (PARSDMM_multi_level, constraint2coarse, interpolate_y_l
 __all__ = [
     "PARSDMM", "PARSDMM_multi_level", "PARSDMM_options", "constraint2coarse", "interpolate_y_l", "resample_nn",
     "setup_multi_level_PARSDMM", "PARSDMM_precompute_distribute", "PARSDMM_precompute_distribute_Minkowski",
-    "Projector", "TDOperator", "CDS_MVp", "CDS_MVp_MT", "CDS_scaled_add", "cg", "compgrid", "convert_options",
+    "Projector", "TDOperator", "SparseOperator", "CDS_MVp", "CDS_MVp_MT", "CDS_scaled_add", "cg", "compgrid", "convert_options",
     "default_PARSDMM_options", "get_TD_operator", "get_discrete_Grad", "get_projector", "log_type_PARSDMM",
     "mat2CDS", "set_definitions", "set_properties", "setup_constraints",
 ]

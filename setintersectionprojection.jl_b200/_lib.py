@@ -17,7 +17,7 @@ SIPB_E_INVALID, SIPB_E_UNSUPPORTED, SIPB_E_CUDA, SIPB_E_NCCL, SIPB_E_STATE, SIPB
 SIPB_F32, SIPB_F64 = 0, 1
 (SET_BOUNDS_SCALAR, SET_BOUNDS_VECTOR, SET_L1, SET_L2, SET_ANNULUS, SET_CARDINALITY, SET_PROX_L1,
  SET_DISTANCE, SET_BOUNDS_FIBER, SET_CARD_FIBER) = range(10)
-OP_IDENTITY, OP_DX, OP_DY, OP_DZ, OP_TV, OP_DXZ = range(6)
+OP_IDENTITY, OP_DX, OP_DY, OP_DZ, OP_TV, OP_DXZ, OP_SPARSE = range(7)
 BLOCK_PLAIN, BLOCK_LEFT, BLOCK_RIGHT, BLOCK_BOTH = range(4)
 N_PHASES = 7
 N_KERNEL_CLASSES = 24
@@ -32,11 +32,19 @@ class SipbError(RuntimeError):
         self.code = code
 
 
+class Sparse(C.Structure):
+    """sipb_sparse: an explicit sparse operator in both orientations (host arrays, 0-based)."""
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int64), ("nnz", C.c_int64),
+                ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("val", C.c_void_p),
+                ("colptr", C.c_void_p), ("rowidx", C.c_void_p), ("valt", C.c_void_p)]
+
+
 class SetDesc(C.Structure):
     _fields_ = [("set_kind", C.c_int32), ("op_kind", C.c_int32), ("block_mode", C.c_int32), ("ncvx", C.c_int32),
                 ("min", C.c_double), ("max", C.c_double), ("k", C.c_int64),
                 ("min_vec", C.c_void_p), ("max_vec", C.c_void_p),
-                ("fiber_axis", C.c_int32), ("reserved", C.c_int32), ("td_n", C.c_int64 * 3)]
+                ("fiber_axis", C.c_int32), ("reserved", C.c_int32), ("td_n", C.c_int64 * 3),
+                ("sparse", C.POINTER(Sparse))]
 
 
 class Options(C.Structure):
@@ -99,6 +107,7 @@ SYMBOLS = [
     ("sipb_project", _I, [_VP, _I, C.POINTER(SetDesc), _I64, _VP, _VP]),
     ("sipb_op_apply", _I, [_VP, _I, _I, _PI64, _PD, _I, _I, _I, _VP, _VP]),
     ("sipb_op_rows", _I, [_I, _PI64, _I, _PI64]),
+    ("sipb_sparse_apply", _I, [_VP, _I, C.POINTER(Sparse), _I, _VP, _VP]),
     ("sipb_cds_scaled_add", _I, [_VP, _I, _I64, _I, _VP, _PI64, _I, _VP, _PI64, _D]),
     ("sipb_bench_spmv", _I, [_VP, _I, _I, _PI64, _I, _I, _I, _PD, _PI64]),
 ]

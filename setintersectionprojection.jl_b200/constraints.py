@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .operators import SPECIAL_OPERATORS, TDOperator, get_TD_operator
+from .operators import SPECIAL_OPERATORS, SparseOperator, TDOperator, get_TD_operator
 from .types import set_properties
 
 _REJECTED = {
@@ -132,8 +132,13 @@ def setup_constraints(constraint, comp_grid, TF):
             raise ValueError("l1 and l2 constraints only available for matrix or tensor mode, currently")   # :65-67
         A, AtA_diag, dense, TD_n, banded = get_TD_operator(comp_grid, c.TD_OP, TF)        # :69
         custom = c.custom_TD_OP[0]
-        if c.set_type != "subspace" and not (isinstance(custom, (list, tuple)) and len(custom) == 0):
-            raise NotImplementedError("custom_TD_OP matrices are not on the device path yet (SURVEY §8f-3)")
+        if c.set_type != "subspace" and not (isinstance(custom, (list, tuple)) and len(custom) == 0):   # :70-72
+            if c.app_mode[0] not in ("matrix", "tensor"):
+                raise NotImplementedError("custom operators are on the device path in matrix/tensor mode only")
+            if not (hasattr(custom, "tocsc") or isinstance(custom, np.ndarray)):
+                raise NotImplementedError("custom_TD_OP must be an explicit (SciPy sparse / dense) matrix; JOLI-style "
+                                          "operators are rejected on the device path")
+            A = SparseOperator(custom, comp_grid.n, comp_grid.d, TF)
         P_sub.append(get_projector(c, comp_grid, special, A, TD_n, TF))                   # :74
         TD_OP.append(A)
         sp_.AtA_diag.append(AtA_diag)

@@ -550,6 +550,7 @@ struct RhsArgs {
   unsigned n[3];
   i64 npts;
   i64 ncols;       // npts or 2*npts
+  int accumulate;  // start from the rhs already in memory (sets processed in several launches) instead of zero
   T* rhs;
   SetRef<T> sets[kMaxSets];
 };
@@ -580,8 +581,12 @@ template <typename T, int G, bool RDUAL>
 __device__ __forceinline__ void rhs_cols(const RhsArgs<T>& a, i64 c0, T (&acc)[G], double* d) {
   GridIdx g0 = grid_decode(c0, a.npts, a.n);
   const bool line = (G == 1) || (g0.i + (unsigned)G <= a.n[0] && (g0.upper || c0 + G <= a.npts));
+  if (a.accumulate) {
+    load_any<T, G>(a.rhs + c0, acc);
+  } else {
 #pragma unroll
-  for (int e = 0; e < G; ++e) acc[e] = (T)0;
+    for (int e = 0; e < G; ++e) acc[e] = (T)0;
+  }
   for (int s = 0; s < a.nsets; ++s) {
     const SetRef<T>& S = a.sets[s];
     if (RDUAL) {
@@ -642,6 +647,60 @@ __global__ void __launch_bounds__(kThreads, 4) k_rhs(const __grid_constant__ Rhs
       for (int q = 0; q < kRdualSets; ++q) out[q] = dr[q];
     }
   }
+}
+
+// =============================================================================================
+// explicit sparse operators (constraint.custom_TD_OP, setup_constraints.jl:70-72)
+//
+// The stencil operators above are matrix-free and fused into the y/l and rhs kernels.  A user-supplied sparse
+// matrix gets its own small kernels instead (so the hot kernels carry no variable-length loops): s = A x is
+// written to the set's s buffer and the fused y/l kernels then see the identity acting on that buffer;
+// A'(rho y + l) is accumulated into rhs between the stencil sets in the reference's set order.  Folds follow
+// SparseArrays: ascending column index inside a row, ascending row index inside a column, from zero.
+// =============================================================================================
+template <typename T>
+struct SparseRef {
+  const long long* rp; const int* ci; const T* va;     // CSR of A
+  const long long* cp; const int* ri; const T* vt;     // CSC of A
+  i64 rows, cols;
+};
+// s = A x                                                     (update_y_l.jl:43, PARSDMM_initialize.jl:97)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_sparse_forward(SparseRef<T> A, const T* __restrict__ x, T* __restrict__ s) {
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < A.rows; r += (i64)gridDim.x * blockDim.x) {
+    T acc = (T)0;
+    for (long long q = A.rp[r]; q < A.rp[r + 1]; ++q) acc = acc + A.va[q] * x[A.ci[q]];
+    s[r] = acc;
+  }
+}
+// t = [t +] A' v  with  v = rho*y + l  (l == null: v = y)          (rhs_compose.jl:28-30)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_sparse_adjoint(SparseRef<T> A, T rho, const T* __restrict__ y,
+                                                             const T* __restrict__ l, T* __restrict__ t, int accumulate) {
+  for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < A.cols; c += (i64)gridDim.x * blockDim.x) {
+    T acc = (T)0;
+    for (long long q = A.cp[c]; q < A.cp[c + 1]; ++q) {
+      const int r = A.ri[q];
+      const T v = l ? rho * y[r] + l[r] : y[r];
+      acc = acc + A.vt[q] * v;
+    }
+    t[c] = accumulate ? t[c] + acc : acc;
+  }
+}
+// || A' (y - y_old) ||^2 -> out[0]                                 (update_y_l.jl:82-84)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_sparse_rdual(SparseRef<T> A, const T* __restrict__ y,
+                                                           const T* __restrict__ y_old, RedScratch rs, double* out) {
+  double d[1] = {0.0};
+  for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < A.cols; c += (i64)gridDim.x * blockDim.x) {
+    T acc = (T)0;
+    for (long long q = A.cp[c]; q < A.cp[c + 1]; ++q) {
+      const int r = A.ri[q];
+      acc = acc + A.vt[q] * (y[r] - y_old[r]);
+    }
+    d[0] += (double)acc * (double)acc;
+  }
+  if (grid_sum<1>(d, rs) && threadIdx.x == 0) out[0] = d[0];
 }
 
 // =============================================================================================

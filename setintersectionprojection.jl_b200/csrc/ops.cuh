@@ -222,79 +222,6 @@ __device__ __forceinline__ bool op_touches_half(int mode, bool upper) {
          (mode == SIPB_BLOCK_RIGHT && upper);
 }
 
-// ---- adjoint: t[e] = (A' v)[g[e]] for W grid points; val(row) supplies v[row] ---------------------
-// `val` takes a SIGNED row index (slab halo rows are addressed with negative indices).
-template <typename T, int W, typename F>
-__device__ __forceinline__ void op_adjoint_n(const OpDev& op, int mode, const GridIdx (&g)[W], F val, T (&t)[W]) {
-#pragma unroll
-  for (int e = 0; e < W; ++e) t[e] = (T)0;
-  switch (op.kind) {
-    case SIPB_OP_IDENTITY:
-#pragma unroll
-      for (int e = 0; e < W; ++e)
-        if (op_touches_half(mode, g[e].upper)) t[e] = t[e] + val(g[e].cc);
-      return;
-    case SIPB_OP_DXZ: {
-      const unsigned w = op.n[0] - 1u;
-      const T a = (T)op.a_xz;
-#pragma unroll
-      for (int e = 0; e < W; ++e) {
-        if (!op_touches_half(mode, g[e].upper)) continue;
-        const unsigned i = g[e].i, j = g[e].j;
-        const bool il = i >= 1u, ih_ = i < op.n[0] - 1u, jl = j >= 1u, jh = j < op.n[1] - 1u;
-        const unsigned q = i + w * j;   // row (i,j)
-        T acc = (T)0;
-        if (il && jl) acc = acc + a * val(q - 1u - w);
-        if (ih_ && jl) acc = acc + (-a) * val(q - w);
-        if (il && jh) acc = acc + (-a) * val(q - 1u);
-        if (ih_ && jh) acc = acc + a * val(q);
-        t[e] = acc;
-      }
-      return;
-    }
-    default: {
-      for (int b = 0; b < op.nblk; ++b) {
-        const int a = op.axis[b];
-        const T ih = (T)op.ih[a];
-        const T nih = -ih;
-        const unsigned base = op.rs[b];
-        if (a == 0) {
-          const unsigned na = op.n[0];
-#pragma unroll
-          for (int e = 0; e < W; ++e) {
-            if (!op_touches_half(mode, g[e].upper)) continue;
-            const unsigned q = base + g[e].cc - (g[e].j + op.n[1] * g[e].k);   // i + (n0-1)*(j + n1*k)
-            if (g[e].i >= 1u) t[e] = t[e] + ih * val(q - 1u);
-            if (g[e].i < na - 1u) t[e] = t[e] + nih * val(q);
-          }
-        } else if (a == 1) {
-          const unsigned na = op.n[1], st = op.n[0];
-#pragma unroll
-          for (int e = 0; e < W; ++e) {
-            if (!op_touches_half(mode, g[e].upper)) continue;
-            const unsigned q = base + g[e].cc - st * g[e].k;                   // i + n0*(j + (n1-1)*k)
-            if (g[e].j >= 1u) t[e] = t[e] + ih * val(q - st);
-            if (g[e].j < na - 1u) t[e] = t[e] + nih * val(q);
-          }
-        } else {
-          // slowest axis: with slabs the row of plane k-1 of the first owned plane lives in the halo plane
-          // stored in front of the block (negative index), boundary tests use GLOBAL plane numbers
-          const unsigned na = op.nlast, st = op.n[0] * op.n[1];
-#pragma unroll
-          for (int e = 0; e < W; ++e) {
-            if (!op_touches_half(mode, g[e].upper)) continue;
-            const int q = (int)(base + g[e].cc);
-            const unsigned kg = g[e].k + op.kofs;
-            if (kg >= 1u) t[e] = t[e] + ih * val(q - (int)st);
-            if (kg < na - 1u) t[e] = t[e] + nih * val(q);
-          }
-        }
-      }
-      return;
-    }
-  }
-}
-
 // ---- value fetchers for the adjoint gathers: NV values per row, W consecutive rows, signed start index ----
 template <typename T>
 struct FetchPlain {          // v[row]

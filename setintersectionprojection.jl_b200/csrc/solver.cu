@@ -498,6 +498,65 @@ struct SlabGeom {
   i64 nz_rows() const { return std::min(k1, nlast - 1) - k0; }   // owned row planes of a D_z block
 };
 
+// Device copy of an explicit sparse operator (SIPB_OP_SPARSE), both orientations.
+template <typename T>
+struct SparseDev {
+  DevBuf<long long> rp, cp;
+  DevBuf<int> ci, ri;
+  DevBuf<T> va, vt;
+  // validates the host arrays (monotone pointers, indices in range and ascending) and uploads them
+  int upload(const sipb_sparse* A, cudaStream_t stream) {
+    SIPB_REQUIRE(A && A->rows >= 1 && A->cols >= 1 && A->nnz >= 0, SIPB_E_INVALID, "bad sparse operator");
+    SIPB_REQUIRE(A->rowptr && A->colptr && (A->nnz == 0 || (A->colidx && A->rowidx && A->val && A->valt)), SIPB_E_INVALID,
+                 "sparse operator with null arrays");
+    SIPB_REQUIRE(A->rows < 2147483647ll && A->cols < 2147483647ll, SIPB_E_UNSUPPORTED,
+                 "operator with more than 2^31-1 rows or columns per GPU");
+    auto check = [](const int64_t* ptr, const int32_t* idx, int64_t nouter, int64_t ninner, int64_t nnz) -> bool {
+      if (ptr[0] != 0 || ptr[nouter] != nnz) return false;
+      for (int64_t r = 0; r < nouter; ++r) {
+        if (ptr[r + 1] < ptr[r]) return false;
+        for (int64_t k = ptr[r]; k < ptr[r + 1]; ++k) {
+          if (idx[k] < 0 || idx[k] >= ninner) return false;
+          if (k > ptr[r] && idx[k] <= idx[k - 1]) return false;
+        }
+      }
+      return true;
+    };
+    SIPB_REQUIRE(check(A->rowptr, A->colidx, A->rows, A->cols, A->nnz), SIPB_E_INVALID,
+                 "CSR arrays of the sparse operator are inconsistent (indices must ascend inside a row)");
+    SIPB_REQUIRE(check(A->colptr, A->rowidx, A->cols, A->rows, A->nnz), SIPB_E_INVALID,
+                 "CSC arrays of the sparse operator are inconsistent (indices must ascend inside a column)");
+    const size_t nz = (size_t)std::max<int64_t>(A->nnz, 1);
+    SIPB_CUDA_CHECK(rp.alloc((size_t)A->rows + 1));
+    SIPB_CUDA_CHECK(cp.alloc((size_t)A->cols + 1));
+    SIPB_CUDA_CHECK(ci.alloc(nz));
+    SIPB_CUDA_CHECK(ri.alloc(nz));
+    SIPB_CUDA_CHECK(va.alloc(nz));
+    SIPB_CUDA_CHECK(vt.alloc(nz));
+    static_assert(sizeof(long long) == sizeof(int64_t), "64-bit pointers expected");
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(rp.p, A->rowptr, ((size_t)A->rows + 1) * 8, cudaMemcpyHostToDevice, stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(cp.p, A->colptr, ((size_t)A->cols + 1) * 8, cudaMemcpyHostToDevice, stream));
+    if (A->nnz) {
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(ci.p, A->colidx, (size_t)A->nnz * 4, cudaMemcpyHostToDevice, stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(ri.p, A->rowidx, (size_t)A->nnz * 4, cudaMemcpyHostToDevice, stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(va.p, A->val, (size_t)A->nnz * sizeof(T), cudaMemcpyHostToDevice, stream));
+      SIPB_CUDA_CHECK(cudaMemcpyAsync(vt.p, A->valt, (size_t)A->nnz * sizeof(T), cudaMemcpyHostToDevice, stream));
+    }
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(stream));
+    rows = A->rows;
+    cols = A->cols;
+    return SIPB_OK;
+  }
+  i64 rows = 0, cols = 0;
+  SparseRef<T> ref() const {
+    SparseRef<T> r;
+    r.rp = rp.p; r.ci = ci.p; r.va = va.p;
+    r.cp = cp.p; r.ri = ri.p; r.vt = vt.p;
+    r.rows = rows; r.cols = cols;
+    return r;
+  }
+};
+
 // `n` is the GLOBAL grid; with an active slab the descriptor addresses the rank's local planes.
 template <typename T>
 static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int block_mode, OpDev* out,
@@ -561,6 +620,24 @@ static int make_op(int ndim, const int64_t* n, const double* h, int op_kind, int
   return SIPB_OK;
 }
 
+// The identity on a vector of M entries: what the fused y/l kernels see for a set with an explicit sparse
+// operator, whose s = A x is produced by k_sparse_forward beforehand.
+static inline OpDev identity_over(i64 M) {
+  OpDev op;
+  memset(&op, 0, sizeof(op));
+  op.kind = SIPB_OP_IDENTITY;
+  op.mode = SIPB_BLOCK_PLAIN;
+  op.nblk = 1;
+  op.n[0] = (unsigned)M; op.n[1] = 1u; op.n[2] = 1u;
+  op.nlast = 1u;
+  op.npts = M; op.rows = M; op.cols = M;
+  op.row_start[0] = 0;
+  for (int b = 1; b < 4; ++b) op.row_start[b] = M;
+  for (int b = 0; b < 4; ++b) op.rs[b] = (unsigned)op.row_start[b];
+  op.ih[0] = op.ih[1] = op.ih[2] = 1.0;
+  return op;
+}
+
 static inline bool op_has_slow_axis_block(const OpDev& op) {
   if (op.kind == SIPB_OP_IDENTITY || op.kind == SIPB_OP_DXZ) return false;
   for (int b = 0; b < op.nblk; ++b)
@@ -598,6 +675,8 @@ struct SetT {
   i64 Mglob = 0;   // rows of the global operator
   DevBuf<T> y, l, y_old, s, s0, y0, l0, lhat0;   // s only for reduction-type projectors
   DevBuf<T> lo_vec, hi_vec;
+  SparseDev<T> sparse;        // SIPB_OP_SPARSE: the explicit operator (op is then the identity over the s buffer)
+  bool is_sparse = false;
   DevBuf<T> ata;              // [nd][ld]   (released once the stencil-class table has been verified)
   DevBuf<T> ata_tab;          // [kMaxClasses][nd] stencil-class form of AtA
   int nd = 0;
@@ -755,17 +834,32 @@ struct Problem : sipb_problem {
     if (d->set_kind == SIPB_SET_L1) SIPB_REQUIRE(d->max > 0.0, SIPB_E_INVALID, "Radius of L1 ball is negative");
     auto S = std::make_unique<SetT<T>>();
     S->desc = *d;
-    int rc = make_op<T>(ndim, n, h, d->op_kind, d->block_mode, &S->op, &sg);
-    if (rc) return rc;
-    S->M = S->op.rows;
-    S->Mglob = op_rows_host(ndim, n, d->op_kind);
+    S->desc.sparse = nullptr;        // the host arrays are not kept
+    int rc;
+    if (d->op_kind == SIPB_OP_SPARSE) {
+      // custom_TD_OP (setup_constraints.jl:70-72): an explicit sparse matrix with N columns
+      SIPB_REQUIRE(!sg.on && !minkowski && !fiber, SIPB_E_UNSUPPORTED,
+                   "explicit sparse operators are single-GPU, non-Minkowski, matrix/tensor mode");
+      SIPB_REQUIRE(d->sparse && d->sparse->cols == npts, SIPB_E_INVALID, "sparse operator must have prod(n) columns");
+      rc = S->sparse.upload(d->sparse, ctx->stream);
+      if (rc) return rc;
+      S->is_sparse = true;
+      S->op = identity_over(d->sparse->rows);
+      S->M = S->op.rows;
+      S->Mglob = S->M;
+    } else {
+      rc = make_op<T>(ndim, n, h, d->op_kind, d->block_mode, &S->op, &sg);
+      if (rc) return rc;
+      S->M = S->op.rows;
+      S->Mglob = op_rows_host(ndim, n, d->op_kind);
+    }
     S->z_halo = sg.on && op_has_slow_axis_block(S->op);
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M); };
     // slabs: y, l, y_old of a set with a D_z block carry the neighbour's last row plane in front
     auto AH = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M, S->z_halo ? (size_t)sg.plane : 0, 0); };
     AH(S->y); AH(S->l); AH(S->y_old); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
-    if (!proj_is_elementwise(d->set_kind)) A(S->s);
+    if (!proj_is_elementwise(d->set_kind) || S->is_sparse) A(S->s);
     if (e == cudaSuccess) e = S->pp_y.alloc(1);
     if (e == cudaSuccess) e = S->pp_f.alloc(1);
     if (e == cudaSuccess) e = S->warm.alloc(2);
@@ -1307,7 +1401,8 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   for (int i = 0; i < nP; ++i) {
     SetT<T>& S = *sets[i];
     T* sv = S.s.p ? S.s.p : tmp.p;    // element-wise sets do not keep s: use the scratch vector
-    LAUNCH(c, KC_OP_APPLY, k_op_forward<T>, c->grid_for(S.M), S.op, (const T*)m.p, sv);
+    if (S.is_sparse) LAUNCH(c, KC_OP_APPLY, k_sparse_forward<T>, c->grid_for(S.M), S.sparse.ref(), (const T*)m.p, sv);
+    else LAUNCH(c, KC_OP_APPLY, k_op_forward<T>, c->grid_for(S.M), S.op, (const T*)m.p, sv);
     int rc = feasibility_of(S, sv, i * kSlotPerSet + 1);
     if (rc) return rc;
   }
@@ -1403,35 +1498,53 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
 
   int last_cg = 1;
   int iters_done = 0;
-  const bool fuse_rdual = p <= kRdualSets;
+  bool any_sparse = false;
+  for (auto& S : sets) any_sparse = any_sparse || S->is_sparse;
+  const bool fuse_rdual = p <= kRdualSets && !any_sparse;
   const int it_limit = o->fixed_iterations > 0 ? std::min(o->fixed_iterations, maxit) : maxit;
   for (int i = 1; i <= it_limit; ++i) {
     // ---------------- rhs (rhs_compose.jl) ---------------------------------------------------
     {
-      RhsArgs<T> ra;
-      memset(&ra, 0, sizeof(ra));
-      ra.nsets = p;
-      ra.n[0] = (unsigned)n[0]; ra.n[1] = (unsigned)n[1]; ra.n[2] = (unsigned)n[2];
-      ra.npts = npts; ra.ncols = N; ra.rhs = rhs.p;
-      for (int s = 0; s < p; ++s) {
-        ra.sets[s].op = sets[s]->op;
-        ra.sets[s].y = sets[s]->y.p;
-        ra.sets[s].l = sets[s]->l.p;
-        ra.sets[s].y_old = sets[s]->y_old.p;
-        ra.sets[s].rho = rho[s];
-      }
-      {
+      // sets are processed in the reference's order; runs of stencil sets go through one gather kernel each,
+      // explicit sparse operators through k_sparse_adjoint in between (rhs += A_i'(rho_i y_i + l_i))
+      const int g_rhs = c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W));
+      bool first = true;
+      int s0 = 0;
+      while (s0 < p) {
+        if (sets[s0]->is_sparse) {
+          SetT<T>& S = *sets[s0];
+          LAUNCH(c, KC_RHS, k_sparse_adjoint<T>, c->grid_for(N), S.sparse.ref(), rho[s0], (const T*)S.y.p, (const T*)S.l.p,
+                 rhs.p, first ? 0 : 1);
+          first = false;
+          ++s0;
+          continue;
+        }
+        int s1 = s0;
+        while (s1 < p && !sets[s1]->is_sparse) ++s1;
+        RhsArgs<T> ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.nsets = s1 - s0;
+        ra.n[0] = (unsigned)n[0]; ra.n[1] = (unsigned)n[1]; ra.n[2] = (unsigned)n[2];
+        ra.npts = npts; ra.ncols = N; ra.rhs = rhs.p;
+        ra.accumulate = first ? 0 : 1;
         double rows = 0;
-        for (int s = 0; s < p; ++s) rows += (double)sets[s]->M;
+        for (int s = s0; s < s1; ++s) {
+          ra.sets[s - s0].op = sets[s]->op;
+          ra.sets[s - s0].y = sets[s]->y.p;
+          ra.sets[s - s0].l = sets[s]->l.p;
+          ra.sets[s - s0].y_old = sets[s]->y_old.p;
+          ra.sets[s - s0].rho = rho[s];
+          rows += (double)sets[s]->M;
+        }
         c->account(KC_RHS, ((fuse_rdual && i >= 2 ? 3 : 2) * rows + (double)N) * sizeof(T));   // y, l (, y_old) -> rhs
+        // from the second iteration on the gather also yields the dual residual of iteration i-1
+        if (fuse_rdual && i >= 2)
+          LAUNCH(c, KC_RHS, (k_rhs<T, true>), g_rhs, ra, c->rs, c->d_scal + kSlotGlobal + 8);
+        else
+          LAUNCH(c, KC_RHS, (k_rhs<T, false>), g_rhs, ra, c->rs, (double*)nullptr);
+        first = false;
+        s0 = s1;
       }
-      // from the second iteration on the gather also yields the dual residual of iteration i-1
-      if (fuse_rdual && i >= 2)
-        LAUNCH(c, KC_RHS, (k_rhs<T, true>), c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W)), ra, c->rs,
-               c->d_scal + kSlotGlobal + 8);
-      else
-        LAUNCH(c, KC_RHS, (k_rhs<T, false>), c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W)), ra, c->rs,
-               (double*)nullptr);
     }
     phase_end(1);
     // ---------------- x-minimisation (argmin_x.jl + cg.jl) -----------------------------------
@@ -1473,6 +1586,10 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       ya.op = S.op;
       ya.P = proj_static(S, rho[s]);
       ya.x = x.p; ya.y = S.y.p; ya.l = S.l.p; ya.y_old = S.y_old.p; ya.s = S.s.p;
+      if (S.is_sparse) {       // s = A x by the sparse kernel; the fused kernels then apply the identity to it
+        LAUNCH(c, KC_OP_APPLY, k_sparse_forward<T>, c->grid_for(S.M), S.sparse.ref(), (const T*)x.p, S.s.p);
+        ya.x = S.s.p;
+      }
       ya.lhat0 = S.lhat0.p; ya.s0 = S.s0.p; ya.l0 = S.l0.p; ya.y0 = S.y0.p;
       ya.rho = rho[s]; ya.gamma = gamma[s];
       ya.do_sums = (do_adapt && i > 1) ? 1 : 0;     // i == 1: snapshot only (all deltas are zero)
@@ -1511,8 +1628,12 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     if (!fuse_rdual) {
       for (int s = 0; s < p; ++s) {
         SetT<T>& S = *sets[s];
-        LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
-               (const T*)S.y_old.p, c->rs, c->d_scal + s * kSlotPerSet + 3);
+        if (S.is_sparse)
+          LAUNCH(c, KC_RDUAL, k_sparse_rdual<T>, c->grid_for(N), S.sparse.ref(), (const T*)S.y.p, (const T*)S.y_old.p, c->rs,
+                 c->d_scal + s * kSlotPerSet + 3);
+        else
+          LAUNCH(c, KC_RDUAL, k_rdual<T>, c->grid_for((npts + Vec<T>::W - 1) / Vec<T>::W), S.op, (const T*)S.y.p,
+                 (const T*)S.y_old.p, c->rs, c->d_scal + s * kSlotPerSet + 3);
       }
     }
     { int rc = exchange_yl_halos(); if (rc) return rc; }   // slabs: halo planes for the next rhs gather
@@ -2093,6 +2214,26 @@ static int op_apply_impl(sipb_ctx* c, int ndim, const int64_t* n, const double* 
 }
 
 template <typename T>
+static int sparse_apply_impl(sipb_ctx* c, const sipb_sparse* A, int adjoint, const void* in, void* out) {
+  SparseDev<T> sd;
+  int rc = sd.upload(A, c->stream);
+  if (rc) return rc;
+  const i64 nin = adjoint ? A->rows : A->cols, nout = adjoint ? A->cols : A->rows;
+  DevBuf<T> di, dout;
+  SIPB_CUDA_CHECK(di.alloc((size_t)nin));
+  SIPB_CUDA_CHECK(dout.alloc((size_t)nout));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(di.p, in, nin * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  if (adjoint)
+    LAUNCH(c, KC_OP_APPLY, k_sparse_adjoint<T>, c->grid_for(nout), sd.ref(), (T)1, (const T*)di.p, (const T*)nullptr, dout.p, 0);
+  else
+    LAUNCH(c, KC_OP_APPLY, k_sparse_forward<T>, c->grid_for(nout), sd.ref(), (const T*)di.p, dout.p);
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(out, dout.p, nout * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
+template <typename T>
 static int cds_scaled_add_impl(sipb_ctx* c, int64_t N, int nd_a, void* A, const int64_t* a_off, int nd_b, const void* B,
                                const int64_t* b_off, double alpha) {
   const i64 ld = (N + 63) / 64 * 64;
@@ -2208,6 +2349,11 @@ int sipb_op_apply(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, const do
   SIPB_REQUIRE(ctx && n && h && in && out, SIPB_E_INVALID, "null argument");
   SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
   DISPATCH(dtype, op_apply_impl, ctx, ndim, n, h, op_kind, block_mode, adjoint, in, out);
+}
+int sipb_sparse_apply(sipb_ctx* ctx, int dtype, const sipb_sparse* A, int adjoint, const void* in, void* out) {
+  SIPB_REQUIRE(ctx && A && in && out, SIPB_E_INVALID, "null argument");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, sparse_apply_impl, ctx, A, adjoint, in, out);
 }
 int sipb_cds_scaled_add(sipb_ctx* ctx, int dtype, int64_t N, int nd_a, void* A, const int64_t* a_offsets, int nd_b,
                         const void* B, const int64_t* b_offsets, double alpha) {

@@ -219,6 +219,84 @@ class TDOperator:
         return R, offs
 
 
+class SparseOperator(TDOperator):
+    """An explicit sparse transform-domain operator: `constraint.custom_TD_OP[1]` of the reference
+    (setup_constraints.jl:70-72, examples/ConstraintSetupExamples.jl:125-146).  Held on the host as a SciPy CSC
+    matrix (the SparseMatrixCSC of the reference); the device gets CSR and CSC copies and applies them with
+    SparseArrays' fold order (ascending column inside a row, ascending row inside a column).
+    Single GPU, non-Minkowski, matrix/tensor mode."""
+
+    def __init__(self, A, n, h, TF):
+        self.kind = "custom"
+        self.TF = np.dtype(TF).type
+        self.ndim = 3 if _is3d(n) else 2
+        self.n = tuple(int(v) for v in n[: self.ndim])
+        self.h = tuple(self.TF(v) for v in h[: self.ndim])
+        self.block_mode = _lib.BLOCK_PLAIN
+        self.op_kind = _lib.OP_SPARSE
+        self.npts = int(np.prod(self.n))
+        A = sp.csc_matrix(A).astype(self.TF)
+        A.sum_duplicates()
+        A.sort_indices()
+        if A.shape[1] != self.npts:
+            raise ValueError("custom operator has %d columns, the grid has %d points" % (A.shape[1], self.npts))
+        if A.shape[0] >= 2 ** 31 - 1 or A.nnz >= 2 ** 31 - 1:
+            raise NotImplementedError("custom operator too large for 32-bit indices")
+        self._sparse = A
+        self._csr = None
+        self._struct = None
+
+    @property
+    def rows(self) -> int:
+        return self._sparse.shape[0]
+
+    def with_block(self, block_mode):
+        raise NotImplementedError("custom operators inside generalized Minkowski sets are not on the device path")
+
+    def __repr__(self):
+        return "SparseOperator(%dx%d, nnz=%d, %s)" % (*self.shape, self._sparse.nnz, self.TF.__name__)
+
+    def tosparse(self) -> sp.csc_matrix:
+        return self._sparse
+
+    def sparse_struct(self) -> _lib.Sparse:
+        """ctypes view (sipb_sparse) of the CSR + CSC arrays; the arrays stay alive with this object."""
+        if self._struct is None:
+            A = self._sparse
+            R = sp.csr_matrix(A)
+            R.sort_indices()
+            keep = dict(rowptr=np.ascontiguousarray(R.indptr, dtype=np.int64), colidx=np.ascontiguousarray(R.indices, dtype=np.int32),
+                        val=np.ascontiguousarray(R.data, dtype=self.TF), colptr=np.ascontiguousarray(A.indptr, dtype=np.int64),
+                        rowidx=np.ascontiguousarray(A.indices, dtype=np.int32), valt=np.ascontiguousarray(A.data, dtype=self.TF))
+            st = _lib.Sparse()
+            st.rows, st.cols, st.nnz = A.shape[0], A.shape[1], A.nnz
+            for k, v in keep.items():
+                setattr(st, k, v.ctypes.data)
+            self._csr = keep
+            self._struct = st
+        return self._struct
+
+    def _apply(self, v, adjoint: bool):
+        v = np.ascontiguousarray(v, dtype=self.TF).ravel()
+        nin, nout = (self.rows, self.cols) if adjoint else (self.cols, self.rows)
+        if v.size != nin:
+            raise ValueError("dimension mismatch: operator is %dx%d, vector has %d" % (*self.shape, v.size))
+        out = np.empty(nout, dtype=self.TF)
+        lib = _lib.load()
+        _lib.check(lib.sipb_sparse_apply(_lib.ctx(), _lib.dtype_code(self.TF), C.byref(self.sparse_struct()),
+                                         1 if adjoint else 0, v.ctypes.data, out.ctypes.data))
+        return out
+
+    def ata_cds(self, zrange=None):
+        """mat2CDS(A'*A) (PARSDMM_precompute_distribute.jl:47,52-55)."""
+        if zrange is not None:
+            raise NotImplementedError("custom operators are single-GPU (no slab decomposition)")
+        A = self._sparse
+        AtA = sp.csc_matrix(sp.csc_matrix(A.T) @ A).astype(self.TF)
+        AtA.sort_indices()
+        return mat2CDS(AtA)
+
+
 class _Adjoint:
     def __init__(self, op: TDOperator):
         self.op = op

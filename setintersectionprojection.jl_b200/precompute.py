@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from . import distributed as dd
-from .operators import TDOperator
+from .operators import SparseOperator, TDOperator
 
 
 class CDSList(list):
@@ -55,7 +55,19 @@ def PARSDMM_precompute_distribute(TD_OP, set_Prop, comp_grid, options):
         zrange = dd.slab_range(TD_OP[0].n[2])
         AtA.slab = zrange
     for i in range(p):
-        R, offs = TD_OP[i].ata_cds(zrange)    # == mat2CDS(TD_OP[i]'*TD_OP[i]) (identity when AtA_diag)
+        if isinstance(TD_OP[i], SparseOperator):
+            # custom operator: the caller describes it through set_Prop (ConstraintSetupExamples.jl:114-117)
+            if not set_Prop.banded[i] or set_Prop.dense[i]:
+                raise NotImplementedError("custom operators must be flagged banded and not dense: the device path solves "
+                                          "the x-subproblem in compressed-diagonal storage only")
+            if set_Prop.AtA_diag[i]:          # :44-45: AtA = I when the caller says A'A is the identity
+                R, offs = np.ones((TD_OP[i].cols, 1), dtype=TF, order="F"), np.array([0], dtype=np.int64)
+            else:
+                R, offs = TD_OP[i].ata_cds(zrange)
+            if offs.size > 32:
+                raise NotImplementedError("A'A of the custom operator has %d diagonals; the device path handles 32" % offs.size)
+        else:
+            R, offs = TD_OP[i].ata_cds(zrange)    # == mat2CDS(TD_OP[i]'*TD_OP[i]) (identity when AtA_diag)
         AtA.append(R)
         set_Prop.AtA_offsets[i] = offs
     set_Prop.AtA_offsets = set_Prop.AtA_offsets[:p]

@@ -34,7 +34,7 @@ def _destroy(handle):
 def _problem_key(TF, TD_OP, P_sub, set_Prop, options):
     items = [np.dtype(TF).str, bool(options.feasibility_only), bool(options.Minkowski)]
     for A in TD_OP:
-        items.append((A.kind, A.n, tuple(float(v) for v in A.h), A.block_mode))
+        items.append((A.kind, A.n, tuple(float(v) for v in A.h), A.block_mode, id(A) if A.kind == "custom" else None))
     for P in P_sub:
         items.append((P.set_kind, float(P.min) if np.ndim(P.min) == 0 else None,
                       float(P.max) if np.ndim(P.max) == 0 else None, P.k,
@@ -84,6 +84,10 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
             else:
                 d = _lib.SetDesc()
                 d.set_kind, d.op_kind, d.block_mode, d.ncvx = _lib.SET_DISTANCE, TD_OP[i].op_kind, TD_OP[i].block_mode, 0
+            if TD_OP[i].op_kind == _lib.OP_SPARSE:          # custom operator: CSR + CSC arrays travel with the descriptor
+                if slab is not None:
+                    raise NotImplementedError("custom operators are single-GPU (no slab decomposition)")
+                d.sparse = C.pointer(TD_OP[i].sparse_struct())
             _lib.check(lib.sipb_problem_add_set(handle, C.byref(d)))
             R = AtA[i]
             if slab is not None and getattr(AtA, "slab", None) is None:       # global CDS given: keep this rank's rows

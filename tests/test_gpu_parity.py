@@ -619,3 +619,67 @@ def test_q_class_detection_rejects_irregular_matrix(sip):
     x, log, l, y = sip.PARSDMM(spec["m"].copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
     assert b["AtA"]._device.q_form == "arrays"
     assert np.all(np.isfinite(x))
+
+
+# ---------------------------------------------------------------------------------------------
+# custom (explicit sparse) transform-domain operators   (setup_constraints.jl:70-72)
+# ---------------------------------------------------------------------------------------------
+def _weighted_gradient(orc, n, d, TF, seed=5):
+    """A user-style operator: the discrete gradient with smoothly varying row weights (banded A'A, values that
+    are NOT constant per stencil class)."""
+    import scipy.sparse as sps
+    A, *_ = orc.get_TD_operator(orc.compgrid(d, n), "TV", TF)
+    w = (1.0 + 0.5 * np.sin(np.arange(A.shape[0]) * 0.37 + seed)).astype(TF)
+    W = sps.csc_matrix(sps.diags(w).astype(TF) @ A).astype(TF)
+    W.sort_indices()
+    return W
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_sparse_operator_apply_bit_exact(sip, orc, TF):
+    n, d = (13, 9, 5), (2.0, 3.0, 1.5)
+    W = _weighted_gradient(orc, n, d, TF)
+    op = sip.SparseOperator(W, n, d, TF)
+    assert op.shape == W.shape
+    x = pr.splitmix_uniform(3, W.shape[1]).astype(TF)
+    v = pr.splitmix_uniform(4, W.shape[0]).astype(TF)
+    assert np.array_equal(op @ x, orc.ops.spmv(W, x))
+    assert np.array_equal(op.T @ v, orc.ops.spmv_t(W, v))
+    with pytest.raises(ValueError):
+        op @ v
+
+
+@pytest.mark.parametrize("TF", [np.float64, np.float32])
+@pytest.mark.parametrize("order", ["custom_middle", "custom_first"])
+def test_parsdmm_custom_sparse_operator(sip, orc, TF, order):
+    """examples/ConstraintSetupExamples.jl:125-146: l1 constraint in the domain of a user-supplied sparse matrix,
+    flagged by hand (AtA_diag=false, dense=false, banded=true), next to stencil-operator sets."""
+    n, d = (32, 28), (25.0, 6.0)
+    m = pr.synthetic_model(n, TF).ravel(order="F")
+    W = _weighted_gradient(orc, n, d, TF)
+    tau = 0.4 * float(np.abs(W.astype(np.float64) @ m.astype(np.float64)).sum())
+
+    def build(api):
+        cg = api.compgrid(d, n)
+        sets = [api.set_definitions("bounds", "identity", 1500.0, 4500.0, ("matrix", "")),
+                api.set_definitions("l1", "identity", 0.0, tau, ("matrix", ""), (W.copy(), False)),
+                api.set_definitions("bounds", "D_z", 0.0, 1e6, ("matrix", ""))]
+        if order == "custom_first":
+            sets = [sets[1], sets[0], sets[2]]
+        ic = 1 if order == "custom_middle" else 0
+        opt = api.PARSDMM_options()
+        opt.FL = TF
+        P_sub, TD_OP, set_Prop = api.setup_constraints(sets, cg, TF)
+        set_Prop.AtA_diag[ic], set_Prop.dense[ic], set_Prop.banded[ic] = False, False, True
+        TD_OP, AtA, l, y = api.PARSDMM_precompute_distribute(TD_OP, set_Prop, cg, opt)
+        return dict(cg=cg, opt=opt, P_sub=P_sub, TD_OP=TD_OP, set_Prop=set_Prop, AtA=AtA)
+
+    ob, sb = build(orc), build(sip)
+    assert np.array_equal(ob["set_Prop"].AtA_offsets[0], sb["set_Prop"].AtA_offsets[0])
+    xo, lo, ll, yy = orc.PARSDMM(m.copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"])
+    xs, ls, l2, y2 = sip.PARSDMM(m.copy(), sb["AtA"], sb["TD_OP"], sb["set_Prop"], sb["P_sub"], sb["cg"], sb["opt"])
+    assert sb["AtA"]._device.q_form == "arrays"           # weighted rows: not constant per stencil class
+    check_parity((xo, lo, ll, yy, ob), (xs, ls, l2, y2, sb), TF)
+    assert len(ls.obj) > 5
+    s = W @ xs
+    assert np.abs(s).sum() <= tau * (1 + 50 * ls.set_feasibility[-2].max() + 1e-3)

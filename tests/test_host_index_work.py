@@ -250,3 +250,41 @@ def test_interpolate_y_l_matches_oracle(sip):
             res.append((l, y))
         for a, b in zip(res[0][0] + res[0][1], res[1][0] + res[1][1]):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_custom_sparse_operator_host_side(sip, TF):
+    """custom_TD_OP (setup_constraints.jl:70-72): the explicit matrix replaces A; PARSDMM_precompute_distribute
+    forms mat2CDS(A'A) from it like the oracle, honouring the caller's set_Prop flags."""
+    n, d = (11, 9), (2.0, 3.0)
+    A, *_ = orc.get_TD_operator(orc.compgrid(d, n), "TV", TF)
+    w = (1.0 + 0.25 * np.cos(np.arange(A.shape[0]))).astype(TF)
+    W = sp.csc_matrix(sp.diags(w).astype(TF) @ A).astype(TF)
+
+    def run(api):
+        cons = [api.set_definitions("l1", "identity", 0.0, 10.0, ("matrix", ""), (W.copy(), False)),
+                api.set_definitions("bounds", "identity", 0.0, 1.0, ("matrix", ""))]
+        opt = api.PARSDMM_options()
+        P_sub, TD_OP, sP = api.setup_constraints(cons, api.compgrid(d, n), TF)
+        sP.AtA_diag[0], sP.dense[0], sP.banded[0] = False, False, True
+        TD_OP, AtA, l, y = api.PARSDMM_precompute_distribute(TD_OP, sP, api.compgrid(d, n), opt)
+        return TD_OP, AtA, sP, l, y
+
+    To, Ao, So, lo, yo = run(orc)
+    Ts, As, Ss, ls, ys = run(sip)
+    assert isinstance(Ts[0], sip.SparseOperator) and same_csc(Ts[0].tosparse(), To[0])
+    for a, b in zip(Ao, As):
+        assert np.array_equal(np.asarray(a), np.asarray(b))
+    for a, b in zip(So.AtA_offsets, Ss.AtA_offsets):
+        assert np.array_equal(a, b)
+    assert [v.size for v in ys] == [v.size for v in yo] == [W.shape[0], W.shape[1], W.shape[1]]
+    st = Ts[0].sparse_struct()
+    assert (st.rows, st.cols, st.nnz) == (W.shape[0], W.shape[1], W.nnz)
+    # the caller did not flag the operator as banded: the reference would take its sparse-Q path, rejected here
+    cons = [sip.set_definitions("l1", "identity", 0.0, 10.0, ("matrix", ""), (W.copy(), False))]
+    P_sub, TD_OP, sP = sip.setup_constraints(cons, sip.compgrid(d, n), TF)
+    sP.AtA_diag[0], sP.banded[0] = False, False
+    with pytest.raises(NotImplementedError):
+        sip.PARSDMM_precompute_distribute(TD_OP, sP, sip.compgrid(d, n), sip.PARSDMM_options())
+    with pytest.raises(ValueError):
+        sip.SparseOperator(W[:, :-1], n, d, TF)
