@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <type_traits>
 
 namespace sipb {
 

@@ -747,9 +747,11 @@ template <typename T> __device__ __forceinline__ T t_min(T a, T b) {
 }
 
 // P(v) for element r with all reduction-derived parameters already known
-template <typename T>
+template <typename T, int PK = -1>
 __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
-  switch (P.kind) {
+  // PK >= 0: the set kind is a compile-time constant (the hot y/l kernels dispatch once per thread instead of
+  // once per element); PK < 0: read it from the descriptor
+  switch (PK >= 0 ? PK : P.kind) {
     case SIPB_SET_BOUNDS_SCALAR:   // max(LB, min(x, UB))   project_bounds!.jl:9
       return t_max<T>(P.lo, t_min<T>(v, P.hi));
     case SIPB_SET_BOUNDS_VECTOR:   // min then max          project_bounds!.jl:21-22
@@ -821,6 +823,8 @@ struct YlArgs {
   T* s;                       // only reduction-type projectors keep s between their two passes
   T* lhat0; T* s0; T* l0; T* y0;   // snapshots of the adaptation scheme
   T rho, gamma;
+  const T* x_old;    // distance term only: also reduce the stop sums ||x-m||^2, ||x_old-x||^2, ||x||^2 (PARSDMM.jl:140-145)
+  double* stop_out;  //   -> stop_out[0..2]; null => the separate k_stop pass does it
   int want_feas;     // also reduce ||P(s)-s||^2 and ||s||^2 (element-wise projectors only)
   int do_sums;       // the six adaptation reductions against the previous snapshots
   int do_snapshot;   // overwrite the snapshots (l_hat_0, y_0, s_0, l_0)
@@ -847,7 +851,7 @@ template <typename T, int W> __device__ __forceinline__ void store_n(T* p, const
 // MODE 2: reduction-type projector, pass 2: y <- P(v), l update.
 // d[]: MODE 0/2: [0] ||y-s||^2, [1] ||P(s)-s||^2, [2] ||s||^2 ; MODE 1: [0] sum|v|, [1] sum v^2, [2] nnz(v)
 //      ADAPT   : [3] dot(dH,dlh) [4] ||dH||^2 [5] ||dlh||^2 [6] ||dl||^2 [7] ||dG||^2 [8] dot(dG,dl)
-template <typename T, int MODE, bool ADAPT, int W>
+template <typename T, int MODE, bool ADAPT, int W, int PK>
 __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P, i64 r0, double* d) {
   const T rho = a.rho, gamma = a.gamma;
   const T rho1 = (T)1.0 / rho;                      // update_y_l.jl:34
@@ -863,12 +867,12 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
       if (relaxed) xh = gamma * s[e] + ((T)1.0 - gamma) * yo[e];     // :72
       const T v = xh - lo[e] * rho1;                                    // :67 / :74
       if (MODE == 0) {
-        yn[e] = proj_apply<T>(P, v, r0 + e);
+        yn[e] = proj_apply<T, PK>(P, v, r0 + e);
         const T rp = -s[e] + yn[e];                                     // :69 / :76
         ln[e] = relaxed ? lo[e] + rho * (-xh + yn[e]) : lo[e] + rho * rp;
         d[0] += (double)rp * (double)rp;
-        if (a.want_feas) {
-          const T pf = proj_apply<T>(P, s[e], r0 + e) - s[e];
+        if (PK != SIPB_SET_DISTANCE && a.want_feas) {
+          const T pf = proj_apply<T, PK>(P, s[e], r0 + e) - s[e];
           d[1] += (double)pf * (double)pf;
           d[2] += (double)s[e] * (double)s[e];
         }
@@ -882,6 +886,23 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
     store_n<T, W>(a.y + r0, yn);
     if (MODE == 0) store_n<T, W>(a.l + r0, ln);
     else store_n<T, W>(a.s + r0, s);
+    if (MODE == 0 && PK == SIPB_SET_DISTANCE) {
+      // the distance term holds s = x and m in registers: the stop / log sums of PARSDMM.jl:140-145 ride along
+      // (same expressions as k_stop); slot layout: d[1] ||x_old-x||^2, d[2] ||x||^2, last slot ||x-m||^2
+      if (a.stop_out) {
+        T xo[W];
+        load_n<T, W>(a.x_old + r0, xo);
+#pragma unroll
+        for (int e = 0; e < W; ++e) {
+          const T xv = s[e];
+          const T dx = xo[e] - xv;
+          d[1] += (double)dx * (double)dx;
+          d[2] += (double)xv * (double)xv;
+          const T o = xv - P.m[r0 + e];
+          d[ADAPT ? 9 : 3] += (double)o * (double)o;
+        }
+      }
+    }
   } else {
     T v[W];
     load_n<T, W>(a.y + r0, v);
@@ -890,7 +911,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
     if (relaxed || ADAPT) load_n<T, W>(a.y_old + r0, yo);
 #pragma unroll
     for (int e = 0; e < W; ++e) {
-      yn[e] = proj_apply<T>(P, v[e], r0 + e);
+      yn[e] = proj_apply<T, PK>(P, v[e], r0 + e);
       const T rp = -s[e] + yn[e];
       if (relaxed) {
         const T xh = gamma * s[e] + ((T)1.0 - gamma) * yo[e];
@@ -937,10 +958,11 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
 }
 
 // out: [0..2] as d[0..2] (MODE 2 writes only [0]); ADAPT sums go to out[4..9]
-template <typename T, int MODE, bool ADAPT>
+// PK: compile-time set kind of the specialised instances (-1: read the kind from the descriptor)
+template <typename T, int MODE, bool ADAPT, int PK>
 __device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs, double* out) {
   constexpr int VW = Vec<T>::W;
-  constexpr int NR = ADAPT ? 9 : 3;
+  constexpr int NR = (ADAPT ? 9 : 3) + (MODE == 0 ? 1 : 0);      // MODE 0: one more slot for the fused stop sums
   ProjDev<T> P = a.P;
   if (a.dyn) {
     P.theta = a.dyn->theta; P.scale = a.dyn->scale; P.fill = a.dyn->fill;
@@ -952,9 +974,9 @@ __device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs
   const i64 M = a.op.rows;
   const i64 nvec = M / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x)
-    yl_rows<T, MODE, ADAPT, VW>(a, P, iv * VW, d);
+    yl_rows<T, MODE, ADAPT, VW, PK>(a, P, iv * VW, d);
   for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x)
-    yl_rows<T, MODE, ADAPT, 1>(a, P, r, d);
+    yl_rows<T, MODE, ADAPT, 1, PK>(a, P, r, d);
   if (grid_sum<NR>(d, rs) && threadIdx.x == 0) {
     out[0] = d[0];
     if (MODE != 2) {
@@ -965,12 +987,19 @@ __device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs
 #pragma unroll
       for (int i = 0; i < 6; ++i) out[4 + i] = d[3 + i];
     }
+    if (MODE == 0 && PK == SIPB_SET_DISTANCE && a.stop_out) {
+      a.stop_out[0] = d[NR - 1];
+      a.stop_out[1] = d[1];
+      a.stop_out[2] = d[2];
+    }
   }
 }
 
 template <typename T, int MODE, bool ADAPT>
 __global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
-  yl_body<T, MODE, ADAPT>(a, rs, out);
+  // one dispatch on the set kind per block: the common kinds run fully specialised bodies
+  if (MODE == 2 && a.P.kind == SIPB_SET_L1) yl_body<T, MODE, ADAPT, SIPB_SET_L1>(a, rs, out);
+  else yl_body<T, MODE, ADAPT, -1>(a, rs, out);
 }
 
 // All element-wise sets of one PARSDMM iteration in a single launch: blockIdx.y selects the set, every set
@@ -986,7 +1015,12 @@ struct YlMultiArgs {
 template <typename T, bool ADAPT>
 __global__ void __launch_bounds__(kThreads, 4) k_yl_multi(const __grid_constant__ YlMultiArgs<T> m, RedScratch rs) {
   const RedScratch mine{rs.partials + (size_t)blockIdx.y * kMaxRed * kMaxBlocks, rs.counter + blockIdx.y};
-  yl_body<T, 0, ADAPT>(m.a[blockIdx.y], mine, m.out[blockIdx.y]);
+  const YlArgs<T>& a = m.a[blockIdx.y];
+  switch (a.P.kind) {       // one dispatch per block: fully specialised bodies for the common set kinds
+    case SIPB_SET_BOUNDS_SCALAR: yl_body<T, 0, ADAPT, SIPB_SET_BOUNDS_SCALAR>(a, mine, m.out[blockIdx.y]); break;
+    case SIPB_SET_DISTANCE: yl_body<T, 0, ADAPT, SIPB_SET_DISTANCE>(a, mine, m.out[blockIdx.y]); break;
+    default: yl_body<T, 0, ADAPT, -1>(a, mine, m.out[blockIdx.y]);
+  }
 }
 
 // forward operator only: s = A x      (initial feasibility, PARSDMM_initialize.jl:97-99; unit tests)
@@ -1094,7 +1128,23 @@ __global__ void __launch_bounds__(kThreads) k_stop(i64 N, i64 npts, int minkowsk
                                                    const T* __restrict__ x_old, const T* __restrict__ m,
                                                    RedScratch rs, double* out) {
   double d[3] = {0.0, 0.0, 0.0};
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x) {
+  constexpr int VW = Vec<T>::W;
+  const i64 nvec = minkowski ? 0 : N / VW;       // plain problems: 16-byte loads; Minkowski / tail: one row at a time
+  for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
+    T xv[VW], xo[VW], mv[VW];
+    vload<T>(x + iv * VW, xv);
+    vload<T>(x_old + iv * VW, xo);
+    vload<T>(m + iv * VW, mv);
+#pragma unroll
+    for (int e = 0; e < VW; ++e) {
+      const T dx = xo[e] - xv[e];
+      d[1] += (double)dx * (double)dx;
+      d[2] += (double)xv[e] * (double)xv[e];
+      const T o = xv[e] - mv[e];
+      d[0] += (double)o * (double)o;
+    }
+  }
+  for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x) {
     const T xv = x[r];
     const T e = x_old[r] - xv;
     d[1] += (double)e * (double)e;

@@ -1500,6 +1500,8 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   int iters_done = 0;
   bool any_sparse = false;
   for (auto& S : sets) any_sparse = any_sparse || S->is_sparse;
+  // obj / evol_x sums (PARSDMM.jl:140-145): reduced by the distance term's y/l update when there is one
+  const bool fuse_stop = !feas_only && !minkowski && getenv("SIPB_FUSE_STOP_OFF") == nullptr;
   const bool fuse_rdual = p <= kRdualSets && !any_sparse;
   const int it_limit = o->fixed_iterations > 0 ? std::min(o->fixed_iterations, maxit) : maxit;
   for (int i = 1; i <= it_limit; ++i) {
@@ -1601,7 +1603,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       const bool needs_yold = fuse_adapt || !(gamma[s] == (T)1);
       const double adaptB = (fuse_adapt ? 4 : 0) * rowsB + (ya.do_sums ? 4 : 0) * rowsB;
       if (proj_is_elementwise(S.desc.set_kind)) {
-        c->account(KC_YL_FUSED, colsB + (3 + (needs_yold ? 1 : 0)) * rowsB + adaptB);
+        if (fuse_stop && is_dist) {       // the distance term also reduces the stop sums (x, m are in registers)
+          ya.x_old = x_old.p;
+          ya.stop_out = c->d_scal + kSlotGlobal;
+        }
+        c->account(KC_YL_FUSED, colsB + (3 + (needs_yold ? 1 : 0) + (ya.stop_out ? 1 : 0)) * rowsB + adaptB);
         // element-wise sets are gathered and updated by one launch per (up to) kYlMulti sets
         ya.want_feas = want_feas ? 1 : 0;
         ym.a[n_multi] = ya;
@@ -1637,9 +1643,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       }
     }
     { int rc = exchange_yl_halos(); if (rc) return rc; }   // slabs: halo planes for the next rhs gather
-    LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for(N), N, npts, minkowski ? 1 : 0, (const T*)x.p, (const T*)x_old.p,
-           (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
-    c->account(KC_STOP, 3.0 * N * sizeof(T));                              // x, x_old, m
+    if (!fuse_stop) {
+      LAUNCH(c, KC_STOP, k_stop<T>, c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), N, npts, minkowski ? 1 : 0, (const T*)x.p,
+             (const T*)x_old.p, (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
+      c->account(KC_STOP, 3.0 * N * sizeof(T));                            // x, x_old, m
+    }
     { int rc = ctx_sync_scalars(c); if (rc) return rc; }
     {
       T rp_tot = 0, rd_tot = 0;
