@@ -42,7 +42,19 @@ struct SpmvArgs {
   const T* tab;
   unsigned gn[3];    // grid
   unsigned npts;     // grid points (rows per Minkowski half)
+  // host-prepared constants of the class-form fast path (spmv_rows): 32-bit offsets, which of them keep 16-byte
+  // alignment, the widest offset, and multiply-shift constants for the divisions by gn[0], gn[1]
+  int fast;                     // 1: available (class form, nd <= kFastDiag, offsets fit 31 bits)
+  int off32[8];
+  unsigned amask;               // bit j: off[j] % VW == 0
+  i64 maxoff;
+  unsigned div_m[2];
+  int div_s[2];
 };
+// floor(n / d) for n < 2^31 by multiply-shift (Granlund & Montgomery: m = ceil(2^(31+l) / d), l = ceil(log2 d))
+__device__ __forceinline__ unsigned fast_div31(unsigned n, unsigned m, int s) {
+  return (unsigned)(((unsigned long long)n * m) >> s);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Stencil classes.  Every AtA the reference builds from its constant-coefficient difference operators
@@ -199,37 +211,30 @@ __device__ __forceinline__ const T* spmv_stage_table(const SpmvArgs<T>& a, T* ta
 // acc = acc + q_j * x[r + off_j], j = 0..nd-1.
 constexpr int kFastDiag = 8;
 template <typename T>
-struct SpmvFast {
-  int off[kFastDiag];
-  i64 maxoff;
-  bool on;
-  __device__ __forceinline__ void init(const SpmvArgs<T>& a, const T* tab) {
-    i64 mo = 0;
-#pragma unroll
-    for (int j = 0; j < kFastDiag; ++j) {
-      const i64 o = j < a.nd ? a.off[j] : 0;
-      off[j] = (int)o;
-      mo = max(mo, o < 0 ? -o : o);
-    }
-    maxoff = mo;
-    on = tab != nullptr && a.nd <= kFastDiag && mo < ((i64)1 << 30);
-  }
-};
-template <typename T>
-__device__ __forceinline__ void spmv_rows(const SpmvArgs<T>& a, const T* tab, const SpmvFast<T>& f, i64 r,
-                                          T (&acc)[Vec<T>::W]) {
+__device__ __forceinline__ void spmv_rows(const SpmvArgs<T>& a, const T* tab, i64 r, T (&acc)[Vec<T>::W]) {
   constexpr int VW = Vec<T>::W;
-  if (f.on) {
+  if (a.fast) {
     const i64 g = a.row0 + r;
     const bool peer = a.x_lo != nullptr || a.x_hi != nullptr;
-    const bool inside = g >= f.maxoff && g + VW + f.maxoff <= a.Nglob &&
-                        (!peer || (r >= f.maxoff && r + VW + f.maxoff <= a.N));
+    const bool inside = g >= a.maxoff && g + VW + a.maxoff <= a.Nglob &&
+                        (!peer || (r >= a.maxoff && r + VW + a.maxoff <= a.N));
     if (inside) {        // warp-uniform except in the first / last plane of the vector
-      unsigned cls[VW];
-      row_classes<VW>(g, a.gn, a.npts, cls);
-      const T* tq[VW];
+      const unsigned n0 = a.gn[0], n1 = a.gn[1];
+      const unsigned half = g >= (i64)a.npts ? 1u : 0u;
+      const unsigned c = (unsigned)(g - (i64)half * a.npts);
+      const unsigned q = fast_div31(c, a.div_m[0], a.div_s[0]);
+      const unsigned i = c - q * n0;
+      unsigned tq[VW];      // first table entry of each row's class
+      if (i + (unsigned)VW <= n0 && (half || c + (unsigned)VW <= a.npts)) {     // the group stays on one grid line
+        const unsigned kk = fast_div31(q, a.div_m[1], a.div_s[1]);
+        const unsigned j = q - kk * n1;
+        const unsigned base = ((half * 3u + axis_class(kk, a.gn[2])) * 3u + axis_class(j, n1)) * 3u;
 #pragma unroll
-      for (int e = 0; e < VW; ++e) tq[e] = tab + cls[e] * a.nd;
+        for (int e = 0; e < VW; ++e) tq[e] = (base + axis_class(i + e, n0)) * (unsigned)a.nd;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VW; ++e) tq[e] = row_class(g + e, a.gn, a.npts) * (unsigned)a.nd;
+      }
       const T* xr = a.x + r;
 #pragma unroll
       for (int e = 0; e < VW; ++e) acc[e] = (T)0;
@@ -237,9 +242,15 @@ __device__ __forceinline__ void spmv_rows(const SpmvArgs<T>& a, const T* tab, co
       for (int j = 0; j < kFastDiag; ++j) {
         if (j < a.nd) {
           T xv[VW];
-          load_any<T, VW>(xr + f.off[j], xv);
+          const T* xp = xr + a.off32[j];
+          if ((a.amask >> j) & 1u) {
+            vload<T>(xp, xv);
+          } else {
 #pragma unroll
-          for (int e = 0; e < VW; ++e) acc[e] = acc[e] + tq[e][j] * xv[e];
+            for (int e = 0; e < VW; ++e) xv[e] = xp[e];
+          }
+#pragma unroll
+          for (int e = 0; e < VW; ++e) acc[e] = acc[e] + tab[tq[e] + j] * xv[e];
         }
       }
       return;
@@ -252,14 +263,12 @@ __device__ __forceinline__ void spmv_rows(const SpmvArgs<T>& a, const T* tab, co
 // cd.on: p's neighbour planes are read through peer pointers (after p_wait) and the partial of p.Ap is
 // published to every rank's mailbox instead of being written to out_dot.
 template <typename T, bool DOT>
-__global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs, double* out_dot,
+__global__ void __launch_bounds__(kThreads, 6) k_spmv(SpmvArgs<T> a, RedScratch rs, double* out_dot,
                                                    const int* __restrict__ done_flag, const __grid_constant__ CommDev cd) {
   if (done_flag && *done_flag) return;
   constexpr int VW = Vec<T>::W;
   __shared__ T tab_s[kMaxClasses * kMaxDiag];
   const T* tab = spmv_stage_table<T>(a, tab_s);
-  SpmvFast<T> fast;
-  fast.init(a, tab);
   double d[1] = {0.0};
   const i64 nvec = a.N / VW;
   if (cd.on) {
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(kThreads) k_spmv(SpmvArgs<T> a, RedScratch rs,
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 r = iv * VW;
     T acc[VW];
-    spmv_rows<T>(a, tab, fast, r, acc);
+    spmv_rows<T>(a, tab, r, acc);
     vstore<T>(a.y + r, acc);
     if (DOT) {
       T xc[VW];
@@ -324,14 +333,12 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
   constexpr int VW = Vec<T>::W;
   __shared__ T tab_s[kMaxClasses * kMaxDiag];
   const T* tab = spmv_stage_table<T>(a, tab_s);
-  SpmvFast<T> fast;
-  fast.init(a, tab);
   double d[2] = {0.0, 0.0};
   const i64 nvec = a.N / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x) {
     const i64 row = iv * VW;
     T acc[VW], bv[VW], rv[VW];
-    spmv_rows<T>(a, tab, fast, row, acc);
+    spmv_rows<T>(a, tab, row, acc);
     vload_stream<T>(b + row, bv);
 #pragma unroll
     for (int e = 0; e < VW; ++e) {

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <unordered_map>
 #include <vector>
 
 #include <dlfcn.h>
@@ -211,6 +212,27 @@ struct sipb_ctx {
     i64 g = (work_items + kThreads - 1) / kThreads;
     if (g < 1) g = 1;
     return (int)std::min<i64>(g, max_grid());
+  }
+  // Grid-stride kernels run best with exactly one resident wave: more blocks than fit leave a partial last wave
+  // (e.g. 1184 blocks at 5 blocks/SM = 1.6 waves, the second one 60 % full).  The occupancy of each kernel is
+  // queried once and cached.
+  std::unordered_map<const void*, int> occ_cache;
+  int grid_fit(const void* kernel, i64 work_items) {
+    auto it = occ_cache.find(kernel);
+    int occ;
+    if (it == occ_cache.end()) {
+      occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 0) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = 4;
+      }
+      occ_cache[kernel] = occ;
+    } else {
+      occ = it->second;
+    }
+    i64 g = (work_items + kThreads - 1) / kThreads;
+    if (g < 1) g = 1;
+    return (int)std::min<i64>(g, std::min(num_sms * occ, kMaxBlocks));
   }
   void pre_launch(int cls) {
     launches[cls]++;
@@ -686,6 +708,7 @@ struct SetT {
   DevBuf<ProjParams<T>> pp_y, pp_f;   // dynamic projector parameters: y-update / feasibility
   DevBuf<double> warm;        // [2] warm-start thresholds (y-update, feasibility)
   bool z_halo = false;        // slabs: y, l, y_old have a halo plane in front (D_z block)
+  int l1_last[2] = {5, 5};    // Newton passes the last l1 threshold search needed (y-update / feasibility)
 };
 
 template <typename T>
@@ -1076,6 +1099,26 @@ struct Problem : sipb_problem {
     a.gn[0] = (unsigned)n[0]; a.gn[1] = (unsigned)n[1]; a.gn[2] = (unsigned)n[2];
     a.npts = (unsigned)(n[0] * n[1] * n[2]);
     for (int j = 0; j < a.nd; ++j) a.off[j] = q_offs[j];
+    // constants of the class-form fast path
+    a.fast = 0; a.amask = 0u; a.maxoff = 0;
+    for (int j = 0; j < 8; ++j) a.off32[j] = 0;
+    for (int q = 0; q < 2; ++q) {
+      const unsigned d = (unsigned)n[q];
+      int l = 0;
+      while ((1ull << l) < d) ++l;
+      a.div_m[q] = (unsigned)(((1ull << (31 + l)) + d - 1) / d);
+      a.div_s[q] = 31 + l;
+    }
+    if (q_classes && a.nd <= kFastDiag) {
+      a.fast = 1;
+      for (int j = 0; j < a.nd; ++j) {
+        const i64 o = q_offs[j];
+        a.maxoff = std::max<i64>(a.maxoff, o < 0 ? -o : o);
+        a.off32[j] = (int)o;
+        if (o % Vec<T>::W == 0) a.amask |= 1u << j;
+      }
+      if (a.maxoff >= ((i64)1 << 30)) a.fast = 0;
+    }
     a.N = N; a.row0 = sg.on ? sg.plane * sg.k0 : 0; a.Nglob = Nglob; a.x = xin; a.y = yout;
     a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0;
     return a;
@@ -1131,11 +1174,14 @@ struct Problem : sipb_problem {
     if (kind == SIPB_SET_L1) {
       LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)Mg, warm, c->d_l1, pp);
       int launched = 0;
+      int& last = S.l1_last[warm == S.warm.p ? 0 : 1];
       for (;;) {
-        const int batch = (launched == 0) ? (sg.on ? 4 : 6) : 8;
+        // passes are queued speculatively (they return at once after `done`); the warm-started search mostly
+        // repeats the pass count of the previous iteration, so the first batch is sized from it
+        const int batch = (launched == 0) ? std::min(std::max(last + 1, 2), 6) : 8;
         for (int b = 0; b < batch; ++b) {
           const bool peer = sg.on && c->p2p;
-          LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_for((M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused,
+          LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_fit((const void*)k_l1_pass<T>, (M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused,
                  peer ? c->cd_on : c->cd_off);
           if (!fused) {
             if (!peer && (rc = c->allreduce(&c->d_l1->C, 2))) return rc;
@@ -1147,6 +1193,7 @@ struct Problem : sipb_problem {
         SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (c->h_l1->done || launched >= 256) break;
       }
+      last = c->h_l1->passes;
       LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
     } else if (kind == SIPB_SET_CARD_FIBER) {
       card_fiber(S.desc, v);            // projects every fiber in place; the apply pass is then a pass-through
@@ -1237,11 +1284,14 @@ struct Problem : sipb_problem {
     SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->parsdmm_it, &h->parsdmm_it, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (parsdmm_it == 0)
       SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol, &h->tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
     const bool peer = p_shared != nullptr;            // peer-memory collectives instead of NCCL inside the CG
     const CommDev& cd = peer ? c->cd_on : c->cd_off;
     T* pp = pv();
-    LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+    const i64 nvecN = (N + Vec<T>::W - 1) / Vec<T>::W;
+    // (k_cg_init measured faster with two waves than with one: 2.03 vs 2.68 ms per solve at 200^3)
+    const int g_init = c->grid_for(nvecN), g_mv = c->grid_fit((const void*)k_spmv<T, true>, nvecN),
+              g_xr = c->grid_fit((const void*)k_cg_xr<T>, nvecN), g_p = c->grid_fit((const void*)k_cg_p<T>, nvecN);
+    LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
     const double vecN = (double)N * sizeof(T);
     const double q_rows = q_classes ? 0.0 : (double)q_offs.size();       // matrix words streamed per row
     c->account(KC_CG_INIT, (q_rows + 4 + (x_old_out ? 1 : 0)) * vecN);   // Q, x, b -> r, p (, x_old)
@@ -1252,11 +1302,11 @@ struct Problem : sipb_problem {
     for (;;) {
       for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
         if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
-        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
+        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g_mv, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
         if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;      // peer path: collected inside k_cg_xr
-        LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
+        LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g_xr, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
         if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;   // peer path: collected inside k_cg_p
-        LAUNCH(c, KC_CG_P, k_cg_p<T>, g, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0);
+        LAUNCH(c, KC_CG_P, k_cg_p<T>, g_p, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0);
       }
       SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
       if (peer) SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_p2p_err, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -1509,7 +1559,9 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     {
       // sets are processed in the reference's order; runs of stencil sets go through one gather kernel each,
       // explicit sparse operators through k_sparse_adjoint in between (rhs += A_i'(rho_i y_i + l_i))
-      const int g_rhs = c->grid_for((N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W));
+      const i64 ngrp = (N + 2 * Vec<T>::W - 1) / (2 * Vec<T>::W);
+      const int g_rhs = (fuse_rdual && i >= 2) ? c->grid_fit((const void*)k_rhs<T, true>, ngrp)
+                                               : c->grid_fit((const void*)k_rhs<T, false>, ngrp);
       bool first = true;
       int s0 = 0;
       while (s0 < p) {
@@ -1597,7 +1649,11 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       ya.do_sums = (do_adapt && i > 1) ? 1 : 0;     // i == 1: snapshot only (all deltas are zero)
       ya.do_snapshot = fuse_adapt ? 1 : 0;
       const int base = s * kSlotPerSet;
-      const int g = c->grid_for((S.M + Vec<T>::W - 1) / Vec<T>::W);
+      const i64 nvecM = (S.M + Vec<T>::W - 1) / Vec<T>::W;
+      const int g = proj_is_elementwise(S.desc.set_kind)
+                        ? (fuse_adapt ? c->grid_fit((const void*)k_yl_multi<T, true>, nvecM)
+                                      : c->grid_fit((const void*)k_yl_multi<T, false>, nvecM))
+                        : c->grid_for(nvecM);
       // streams of M rows: l in, y and l out, y_old in when relaxed or adapting, 4 snapshots in / out
       const double rowsB = (double)S.M * sizeof(T), colsB = (double)N * sizeof(T);
       const bool needs_yold = fuse_adapt || !(gamma[s] == (T)1);
@@ -1616,14 +1672,19 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         if (++n_multi == kYlMulti) flush_multi();
       } else {
         ya.want_feas = 0;
-        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), g, ya, c->rs, c->d_scal + base + 10);
+        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), c->grid_fit((const void*)k_yl<T, 1, false>, nvecM), ya, c->rs,
+               c->d_scal + base + 10);
         c->account(KC_YL_PASS1, colsB + (3 + (!(gamma[s] == (T)1) ? 1 : 0)) * rowsB);     // x, l (, y_old) -> v, s
         c->account(KC_YL_PASS2, (5 + (needs_yold ? 1 : 0)) * rowsB + adaptB);             // v, s, l (, y_old) -> y, l
         int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
         if (rc) return rc;
         ya.dyn = S.pp_y.p;
-        if (fuse_adapt) LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, true>), g, ya, c->rs, c->d_scal + base);
-        else LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, false>), g, ya, c->rs, c->d_scal + base);
+        if (fuse_adapt)
+          LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, true>), c->grid_fit((const void*)k_yl<T, 2, true>, nvecM), ya, c->rs,
+                 c->d_scal + base);
+        else
+          LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, false>), c->grid_fit((const void*)k_yl<T, 2, false>, nvecM), ya, c->rs,
+                 c->d_scal + base);
         if (want_feas) {
           rc = feasibility_of(S, S.s.p, base + 1);
           if (rc) return rc;
@@ -2121,7 +2182,7 @@ static int cds_spmv_impl(sipb_ctx* c, int64_t N, int nd, const void* R, const in
   a.R = dR.p; a.ld = ld; a.nd = nd;
   for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
   a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
-  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr;
+  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr; a.fast = 0;
   LAUNCH(c, KC_SPMV, (k_spmv<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), a, c->rs, (double*)nullptr,
          (const int*)nullptr, c->cd_off);
   SIPB_CUDA_CHECK(cudaGetLastError());
@@ -2290,7 +2351,7 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   a.R = dR.p; a.ld = ld; a.nd = nd;
   for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
   a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
-  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr;
+  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr; a.fast = 0;
   const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
   cudaEvent_t e0, e1;
   SIPB_CUDA_CHECK(cudaEventCreate(&e0));
