@@ -118,11 +118,22 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
+def cpu_threads():
+    from oracle import cpu_baseline as cb
+    return cb.threads()
+
+
+CPU_IMPL = ("threaded C/OpenMP restatement of the reference's vector phases (oracle/c/ref_kernels.c: per-diagonal CDS "
+            "passes, BLAS-1 style CG passes, sort-based l1 projection) driven by the NumPy oracle's control flow")
+
+
 def cpu_sample(n, iters):
-    """Run `iters` PARSDMM iterations of the n^3 workload with the CPU oracle; returns (its/s over the
-    iteration phases, seconds of the iteration phases, setup + initialization seconds, iterations done).
+    """Run `iters` PARSDMM iterations of the n^3 workload with the threaded CPU baseline (oracle/cpu_baseline.py:
+    the oracle's control flow and scalar rules, vector phases in C/OpenMP on all host cores); returns (its/s over
+    the iteration phases, seconds of the iteration phases, setup + initialization seconds, iterations done).
     The operator set-up is cached between calls (it is outside the PARSDMM call in the reference too)."""
     import problems as pr
+    from oracle import cpu_baseline as cb
     orc = pr.OracleAPI()
     t0 = time.perf_counter()
     if n not in _CPU_CACHE:
@@ -130,9 +141,9 @@ def cpu_sample(n, iters):
         opt = tweak_options(orc.PARSDMM_options())
         _CPU_CACHE[n] = (spec, pr.build(orc, spec, opt))
     spec, ob = _CPU_CACHE[n]
-    ob["opt"].maxit = iters
     t_setup = time.perf_counter() - t0
-    x, log, _, _ = orc.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"])
+    x, log, _, _ = cb.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"],
+                              constraint=ob["cons"], max_iterations=iters)
     t_iter = sum(v for k, v in log.timing.items() if k != "initialization")
     done = len(log.obj)
     return done / t_iter, t_iter, t_setup + log.timing.get("initialization", 0.0), done
@@ -146,7 +157,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     n = args.n
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     iters = args.cpu_iters
     secs, its = [], []
     t_start = time.perf_counter()
@@ -161,9 +172,8 @@ def run_reference(args, rank, world):
                 break
     value = float(sum(its) / sum(secs))
     nz = n * args.gpus if args.scaling == "weak" else n
-    sample = ("first %d PARSDMM iterations of one %d^3 Float32 slab per step (NumPy oracle; BLAS dot/norm threads only); "
-              "the rate counts the iteration phases only — operator set-up and PARSDMM_initialize are excluded, "
-              "which favours the CPU" % (iters, n))
+    sample = ("first %d PARSDMM iterations of one %d^3 Float32 slab per step; %s; the rate counts the iteration phases "
+              "only — operator set-up and PARSDMM_initialize are excluded, which favours the CPU" % (iters, n, CPU_IMPL))
     line = {
         "impl": "reference", "metric": "parsdmm_iterations_per_second", "value": value, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": len(secs), "warmup": warm, "steps_requested": args.steps,
@@ -172,8 +182,8 @@ def run_reference(args, rank, world):
         "data": "synthetic",
         "config": {"workload": "3D %dx%dx%d Float32 bounds ∩ anisotropic TV l1 ∩ D_x,D_y slope bounds (BASELINE configs[1], "
                                "test_scaling_3D-style)" % (n, n, nz), "grid": [n, n, nz],
-                   "note": "CPU restatement of the reference algorithm (NumPy/SciPy oracle); the Julia reference cannot "
-                           "be installed in this image (no Julia, no network)"},
+                   "note": "CPU restatement of the reference algorithm on %d OpenMP threads; the Julia reference cannot "
+                           "be installed in this image (no Julia, no network)" % cores},
         "cpu_baseline": {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -312,10 +322,9 @@ def run_device(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         v, t_iter, t_setup, done = cpu_sample(n, args.cpu_iters)
-        cpu = {"value": v, "unit": "iterations/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "first %d PARSDMM iterations of the same %d^3 workload with the NumPy oracle (%.1f s of iteration "
-                         "phases; %.1f s of set-up and initialization excluded)" % (done, n, t_iter, t_setup),
-               "threads": "NumPy: BLAS threads for dot/norm, everything else single-threaded"}
+        cpu = {"value": v, "unit": "iterations/s", "cores": cpu_threads(), "kind": "port",
+               "sample": "first %d PARSDMM iterations of the same %d^3 workload (%.1f s of iteration phases; %.1f s of "
+                         "set-up and initialization excluded); %s" % (done, n, t_iter, t_setup, CPU_IMPL)}
 
     value = its_all / dev_s_max
     line = {
@@ -359,7 +368,7 @@ def main():
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
     ap.add_argument("--size", "--n", dest="n", type=int, default=200,
                     help="grid width (BASELINE configs[1] uses 200); use --size under torchrun (its parser claims --n)")
-    ap.add_argument("--cpu-iters", type=int, default=4, help="PARSDMM iterations in the bounded CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=12, help="PARSDMM iterations in the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
                     help="config2 = BASELINE configs[1] (default, the bench line); config3 = configs[2] (TV cardinality)")

@@ -137,14 +137,82 @@ def update_y_l(x, p, i, y, y_old, l, l_old, rho, gamma, prox, TD_OP, log, P_sub,
     return counter
 
 
+def adapt_decide(TF, d_dHh_dlh, n_d_H_hat, n_d_l_hat, n_d_l, n_d_G_hat, d_dGh_dl, rho_ii, gamma_ii, adjust_rho,
+                 adjust_gamma):
+    """Scalar part of adapt_rho_gamma.jl:31-37,55-126 for one set: from the six reductions to the new
+    (rho_i, gamma_i).  All arguments are TF scalars."""
+    safeguard = TF(1e-10) if TF == np.float64 else TF(1e-6)        # :31-35
+    eps_correlation = TF(0.3)                                      # :37
+    with np.errstate(all="ignore"):
+        alpha_reliable = False                                 # :55-59
+        alpha_correlation = TF(0)
+        if (n_d_H_hat * n_d_l_hat) > safeguard and (n_d_H_hat ** 2) > safeguard and d_dHh_dlh > safeguard:
+            alpha_reliable = True
+            alpha_correlation = d_dHh_dlh / (n_d_H_hat * n_d_l_hat)
+        beta_reliable = False                                  # :61-65
+        beta_correlation = TF(0)
+        if (n_d_G_hat * n_d_l) > safeguard and (n_d_G_hat ** 2) > safeguard and d_dGh_dl > safeguard:
+            beta_reliable = True
+            beta_correlation = d_dGh_dl / (n_d_G_hat * n_d_l)
+
+        alpha_comp = False                                     # :67-77
+        alpha_hat = TF(0)
+        if alpha_reliable and alpha_correlation > eps_correlation:
+            alpha_comp = True
+            alpha_hat_MG = d_dHh_dlh / (n_d_H_hat ** 2)
+            alpha_hat_SD = (n_d_l_hat ** 2) / d_dHh_dlh
+            if (TF(2.0) * alpha_hat_MG) > alpha_hat_SD:
+                alpha_hat = alpha_hat_MG
+            else:
+                alpha_hat = alpha_hat_SD - alpha_hat_MG / TF(2.0)
+        beta_comp = False                                      # :79-89
+        beta_hat = TF(0)
+        if beta_reliable and beta_correlation > eps_correlation:
+            beta_comp = True
+            beta_hat_MG = d_dGh_dl / (n_d_G_hat ** 2)
+            beta_hat_SD = (n_d_l ** 2) / d_dGh_dl
+            if (TF(2.0) * beta_hat_MG) > beta_hat_SD:
+                beta_hat = beta_hat_MG
+            else:
+                beta_hat = beta_hat_SD - beta_hat_MG / TF(2.0)
+
+        if adjust_rho and not adjust_gamma:                    # :92-101
+            if alpha_comp and beta_comp:
+                rho_ii = np.sqrt(alpha_hat * beta_hat)
+            elif alpha_comp and not beta_comp:
+                rho_ii = alpha_hat
+            elif not alpha_comp and beta_comp:
+                rho_ii = beta_hat
+        elif adjust_rho and adjust_gamma:                      # :102-115
+            if alpha_comp and beta_comp:
+                rho_ii = np.sqrt(alpha_hat * beta_hat)
+                gamma_ii = TF(1.0) + ((TF(2.0) * np.sqrt(alpha_hat * beta_hat)) / (alpha_hat + beta_hat))
+            elif alpha_comp and not beta_comp:
+                rho_ii = alpha_hat
+                gamma_ii = TF(1.9)
+            elif not alpha_comp and beta_comp:
+                rho_ii = beta_hat
+                gamma_ii = TF(1.1)
+            else:
+                gamma_ii = TF(1.5)
+        elif not adjust_rho and adjust_gamma:                  # :116-126
+            if alpha_comp and beta_comp:
+                gamma_ii = TF(1.0) + ((TF(2.0) * np.sqrt(alpha_hat * beta_hat)) / (alpha_hat + beta_hat))
+            elif alpha_comp and not beta_comp:
+                gamma_ii = TF(1.9)
+            elif not alpha_comp and beta_comp:
+                gamma_ii = TF(1.1)
+            else:
+                gamma_ii = TF(1.5)
+    return rho_ii, gamma_ii
+
+
 # ----------------------------------------------------------------------------------------------
 # adapt_rho_gamma.jl:8-132
 # ----------------------------------------------------------------------------------------------
 def adapt_rho_gamma(gamma, rho, adjust_gamma, adjust_rho, y, y_old, s, s_0, l, l_hat_0, l_0, l_old, y_0, p,
                     l_hat):
     TF = rho.dtype.type
-    safeguard = TF(1e-10) if TF == np.float64 else TF(1e-6)        # :31-35
-    eps_correlation = TF(0.3)                                      # :37
     with np.errstate(all="ignore"):
         for ii in range(p):
             l_hat[ii][:] = l_old[ii] + rho[ii] * (-s[ii] + y_old[ii])      # :41
@@ -159,66 +227,8 @@ def adapt_rho_gamma(gamma, rho, adjust_gamma, adjust_rho, y, y_old, s, s_0, l, l
             n_d_G_hat = norm2(d_G_hat)
             d_dGh_dl = dot(d_G_hat, d_l)                           # :53
 
-            alpha_reliable = False                                 # :55-59
-            alpha_correlation = TF(0)
-            if (n_d_H_hat * n_d_l_hat) > safeguard and (n_d_H_hat ** 2) > safeguard and d_dHh_dlh > safeguard:
-                alpha_reliable = True
-                alpha_correlation = d_dHh_dlh / (n_d_H_hat * n_d_l_hat)
-            beta_reliable = False                                  # :61-65
-            beta_correlation = TF(0)
-            if (n_d_G_hat * n_d_l) > safeguard and (n_d_G_hat ** 2) > safeguard and d_dGh_dl > safeguard:
-                beta_reliable = True
-                beta_correlation = d_dGh_dl / (n_d_G_hat * n_d_l)
-
-            alpha_comp = False                                     # :67-77
-            alpha_hat = TF(0)
-            if alpha_reliable and alpha_correlation > eps_correlation:
-                alpha_comp = True
-                alpha_hat_MG = d_dHh_dlh / (n_d_H_hat ** 2)
-                alpha_hat_SD = (n_d_l_hat ** 2) / d_dHh_dlh
-                if (TF(2.0) * alpha_hat_MG) > alpha_hat_SD:
-                    alpha_hat = alpha_hat_MG
-                else:
-                    alpha_hat = alpha_hat_SD - alpha_hat_MG / TF(2.0)
-            beta_comp = False                                      # :79-89
-            beta_hat = TF(0)
-            if beta_reliable and beta_correlation > eps_correlation:
-                beta_comp = True
-                beta_hat_MG = d_dGh_dl / (n_d_G_hat ** 2)
-                beta_hat_SD = (n_d_l ** 2) / d_dGh_dl
-                if (TF(2.0) * beta_hat_MG) > beta_hat_SD:
-                    beta_hat = beta_hat_MG
-                else:
-                    beta_hat = beta_hat_SD - beta_hat_MG / TF(2.0)
-
-            if adjust_rho and not adjust_gamma:                    # :92-101
-                if alpha_comp and beta_comp:
-                    rho[ii] = np.sqrt(alpha_hat * beta_hat)
-                elif alpha_comp and not beta_comp:
-                    rho[ii] = alpha_hat
-                elif not alpha_comp and beta_comp:
-                    rho[ii] = beta_hat
-            elif adjust_rho and adjust_gamma:                      # :102-115
-                if alpha_comp and beta_comp:
-                    rho[ii] = np.sqrt(alpha_hat * beta_hat)
-                    gamma[ii] = TF(1.0) + ((TF(2.0) * np.sqrt(alpha_hat * beta_hat)) / (alpha_hat + beta_hat))
-                elif alpha_comp and not beta_comp:
-                    rho[ii] = alpha_hat
-                    gamma[ii] = TF(1.9)
-                elif not alpha_comp and beta_comp:
-                    rho[ii] = beta_hat
-                    gamma[ii] = TF(1.1)
-                else:
-                    gamma[ii] = TF(1.5)
-            elif not adjust_rho and adjust_gamma:                  # :116-126
-                if alpha_comp and beta_comp:
-                    gamma[ii] = TF(1.0) + ((TF(2.0) * np.sqrt(alpha_hat * beta_hat)) / (alpha_hat + beta_hat))
-                elif alpha_comp and not beta_comp:
-                    gamma[ii] = TF(1.9)
-                elif not alpha_comp and beta_comp:
-                    gamma[ii] = TF(1.1)
-                else:
-                    gamma[ii] = TF(1.5)
+            rho[ii], gamma[ii] = adapt_decide(TF, d_dHh_dlh, n_d_H_hat, n_d_l_hat, n_d_l, n_d_G_hat, d_dGh_dl, rho[ii],
+                                              gamma[ii], adjust_rho, adjust_gamma)
     return rho, gamma, l_hat
 
 
