@@ -161,6 +161,12 @@ typedef struct sipb_log {
   int64_t h2d_bytes, d2h_bytes;
 } sipb_log;
 
+/* Environment switches (read when the object they affect is created; for A/B measurements and tests):
+ *   SIPB_Q_CLASSES=0      sipb_problem_finalize keeps Q / AtA as CDS arrays (see sipb_problem_q_form)
+ *   SIPB_P2P=0            sipb_comm_init uses NCCL for the CG reductions and halos instead of peer memory
+ *   SIPB_FUSE_STOP_OFF=1  sipb_solve reduces the obj / evol_x sums in a separate pass instead of inside the
+ *                         distance term's y/l update */
+
 /* ---- library / context ------------------------------------------------------------------- */
 int         sipb_abi_version(void);
 const char* sipb_last_error(void);

@@ -1,17 +1,20 @@
 // kernels.cuh — hand-written sm_100a kernels of the PARSDMM iteration.
 //
-// One kernel per reference routine (all HBM-bandwidth bound, one pass over their operands):
-//   k_spmv            CDS_MVp_MT.jl:9-25 + Ax_CDS_MT (argmin_x.jl:72-78) [+ dot(p,Ap), cg.jl:88]
+// Kernels by reference routine (all HBM-bandwidth bound; one pass over their operands):
+//   k_spmv            CDS_MVp_MT.jl:9-25 + Ax_CDS_MT (argmin_x.jl:72-78) [+ dot(p,Ap), cg.jl:88]; Q as CDS arrays
+//                     or as verified stencil-class tables (k_class_extract / k_class_verify / k_class_axpy)
 //   k_cg_init         argmin_x.jl:33-37 + cg.jl:47-76   (one SpMV instead of the reference's two)
 //   k_cg_xr / k_cg_p  cg.jl:86-114
-//   k_rhs             rhs_compose.jl:24-36
-//   k_yl              update_y_l.jl:39-94 with the projector / prox fused in
-//   k_rdual           update_y_l.jl:82-84
-//   k_adapt           adapt_rho_gamma.jl:41-53 + snapshots PARSDMM.jl:164-207 (+ a_is_b_min_c_MT!.jl)
-//   k_stop            PARSDMM.jl:140-145
-//   k_cds_axpy        CDS_scaled_add!.jl:16-22 / Q assembly PARSDMM_initialize.jl:223-229
+//   k_rhs             rhs_compose.jl:24-36 (+ the dual residual of the previous iteration, update_y_l.jl:82-84)
+//   k_yl_multi, k_yl  update_y_l.jl:39-94 with the projector / prox fused in, the six reductions of
+//                     adapt_rho_gamma.jl:41-53, the snapshots of PARSDMM.jl:164-207 and (distance term) the
+//                     obj / evol_x sums of PARSDMM.jl:140-145
+//   k_rdual, k_stop   stand-alone versions of the two fused reductions (Minkowski, feasibility_only, last iteration)
+//   k_cds_axpy        CDS_scaled_add!.jl:16-22 / Q assembly PARSDMM_initialize.jl:223-229 (array form of Q)
+//   k_sparse_*        custom_TD_OP (setup_constraints.jl:70-72): explicit sparse operators
 //   k_l1_pass         project_l1_Duchi!.jl:33-46 replaced by a sort-free Newton (Michelot) threshold search
 //   k_radix_hist/...  project_cardinality!.jl:18-19 replaced by a radix select with index-ordered ties
+//   k_card_fiber_*    project_cardinality!.jl:23-113 (fiber modes);  k_resample_nn  PARSDMM_multi_level.jl:61-82
 #pragma once
 #include "common.cuh"
 #include "ops.cuh"
