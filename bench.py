@@ -118,9 +118,32 @@ class ClockSampler:
 _CPU_CACHE = {}
 
 
+_CPU_MODE = {"threaded": None}
+
+
+def cpu_threaded_available():
+    """The C/OpenMP baseline needs gcc (or the prebuilt oracle/_cbuild/libsipref.so); without it the CPU legs fall
+    back to the plain NumPy oracle and say so."""
+    if _CPU_MODE["threaded"] is None:
+        try:
+            from oracle import cpu_baseline as cb
+            cb.threads()
+            _CPU_MODE["threaded"] = True
+        except Exception as e:       # noqa: BLE001
+            print("bench.py: threaded CPU baseline unavailable (%s); timing the NumPy oracle instead" % e, file=sys.stderr)
+            _CPU_MODE["threaded"] = False
+    return _CPU_MODE["threaded"]
+
+
 def cpu_threads():
+    if not cpu_threaded_available():
+        return 1
     from oracle import cpu_baseline as cb
     return cb.threads()
+
+
+def cpu_impl():
+    return CPU_IMPL if cpu_threaded_available() else "NumPy/SciPy oracle (single-threaded apart from BLAS dot/norm)"
 
 
 CPU_IMPL = ("threaded C/OpenMP restatement of the reference's vector phases (oracle/c/ref_kernels.c: per-diagonal CDS "
@@ -133,7 +156,6 @@ def cpu_sample(n, iters):
     the iteration phases, seconds of the iteration phases, setup + initialization seconds, iterations done).
     The operator set-up is cached between calls (it is outside the PARSDMM call in the reference too)."""
     import problems as pr
-    from oracle import cpu_baseline as cb
     orc = pr.OracleAPI()
     t0 = time.perf_counter()
     if n not in _CPU_CACHE:
@@ -142,8 +164,13 @@ def cpu_sample(n, iters):
         _CPU_CACHE[n] = (spec, pr.build(orc, spec, opt))
     spec, ob = _CPU_CACHE[n]
     t_setup = time.perf_counter() - t0
-    x, log, _, _ = cb.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"],
-                              constraint=ob["cons"], max_iterations=iters)
+    if cpu_threaded_available():
+        from oracle import cpu_baseline as cb
+        x, log, _, _ = cb.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"],
+                                  constraint=ob["cons"], max_iterations=iters)
+    else:
+        ob["opt"].maxit = min(iters, 4)
+        x, log, _, _ = orc.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"])
     t_iter = sum(v for k, v in log.timing.items() if k != "initialization")
     done = len(log.obj)
     return done / t_iter, t_iter, t_setup + log.timing.get("initialization", 0.0), done
@@ -173,7 +200,7 @@ def run_reference(args, rank, world):
     value = float(sum(its) / sum(secs))
     nz = n * args.gpus if args.scaling == "weak" else n
     sample = ("first %d PARSDMM iterations of one %d^3 Float32 slab per step; %s; the rate counts the iteration phases "
-              "only — operator set-up and PARSDMM_initialize are excluded, which favours the CPU" % (iters, n, CPU_IMPL))
+              "only — operator set-up and PARSDMM_initialize are excluded, which favours the CPU" % (iters, n, cpu_impl()))
     line = {
         "impl": "reference", "metric": "parsdmm_iterations_per_second", "value": value, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": len(secs), "warmup": warm, "steps_requested": args.steps,
@@ -324,7 +351,7 @@ def run_device(args, rank, world, local_rank):
         v, t_iter, t_setup, done = cpu_sample(n, args.cpu_iters)
         cpu = {"value": v, "unit": "iterations/s", "cores": cpu_threads(), "kind": "port",
                "sample": "first %d PARSDMM iterations of the same %d^3 workload (%.1f s of iteration phases; %.1f s of "
-                         "set-up and initialization excluded); %s" % (done, n, t_iter, t_setup, CPU_IMPL)}
+                         "set-up and initialization excluded); %s" % (done, n, t_iter, t_setup, cpu_impl())}
 
     value = its_all / dev_s_max
     line = {
