@@ -167,9 +167,9 @@ def cpu_sample(n, iters):
     if cpu_threaded_available():
         from oracle import cpu_baseline as cb
         x, log, _, _ = cb.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"],
-                                  constraint=ob["cons"], max_iterations=iters)
+                                  constraint=ob["cons"], max_iterations=iters if iters > 0 else None)
     else:
-        ob["opt"].maxit = min(iters, 4)
+        ob["opt"].maxit = min(iters, 4) if iters > 0 else 4
         x, log, _, _ = orc.PARSDMM(spec["m"].copy(), ob["AtA"], ob["TD_OP"], ob["set_Prop"], ob["P_sub"], ob["cg"], ob["opt"])
     t_iter = sum(v for k, v in log.timing.items() if k != "initialization")
     done = len(log.obj)
@@ -199,8 +199,10 @@ def run_reference(args, rank, world):
                 break
     value = float(sum(its) / sum(secs))
     nz = n * args.gpus if args.scaling == "weak" else n
-    sample = ("first %d PARSDMM iterations of one %d^3 Float32 slab per step; %s; the rate counts the iteration phases "
-              "only — operator set-up and PARSDMM_initialize are excluded, which favours the CPU" % (iters, n, cpu_impl()))
+    sample = ("%s of one %d^3 Float32 slab per step; %s; the rate counts the iteration phases only — operator set-up "
+              "and PARSDMM_initialize are excluded, which favours the CPU"
+              % ("one full projection (%d PARSDMM iterations)" % its[-1] if iters <= 0 else "first %d PARSDMM iterations" % iters,
+                 n, cpu_impl()))
     line = {
         "impl": "reference", "metric": "parsdmm_iterations_per_second", "value": value, "unit": "iterations/s",
         "n_gpus": args.gpus, "steps": len(secs), "warmup": warm, "steps_requested": args.steps,
@@ -350,8 +352,10 @@ def run_device(args, rank, world, local_rank):
     if world == 1 and not args.no_cpu:
         v, t_iter, t_setup, done = cpu_sample(n, args.cpu_iters)
         cpu = {"value": v, "unit": "iterations/s", "cores": cpu_threads(), "kind": "port",
-               "sample": "first %d PARSDMM iterations of the same %d^3 workload (%.1f s of iteration phases; %.1f s of "
-                         "set-up and initialization excluded); %s" % (done, n, t_iter, t_setup, cpu_impl())}
+               "sample": "%s of the same %d^3 workload (%d PARSDMM iterations, %.1f s of iteration phases; %.1f s of "
+                         "set-up and initialization excluded); %s"
+                         % ("one full projection" if args.cpu_iters <= 0 else "the first iterations", n, done, t_iter, t_setup,
+                            cpu_impl())}
 
     value = its_all / dev_s_max
     line = {
@@ -395,7 +399,8 @@ def main():
     ap.add_argument("--impl", default="device", choices=["device", "reference"])
     ap.add_argument("--size", "--n", dest="n", type=int, default=200,
                     help="grid width (BASELINE configs[1] uses 200); use --size under torchrun (its parser claims --n)")
-    ap.add_argument("--cpu-iters", type=int, default=12, help="PARSDMM iterations in the bounded CPU sample")
+    ap.add_argument("--cpu-iters", type=int, default=0,
+                    help="PARSDMM iterations in the bounded CPU sample (0 = one full projection to the stopping rules)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3"],
                     help="config2 = BASELINE configs[1] (default, the bench line); config3 = configs[2] (TV cardinality)")
