@@ -50,7 +50,9 @@ extern "C" {
 #define SIPB_SET_DISTANCE      7   /* prox_l2s!.jl:3-6: the 1/2||x-m||^2 term (PARSDMM_initialize.jl:64-71) */
 #define SIPB_SET_BOUNDS_FIBER  8   /* project_bounds!.jl:38-88: per-fiber bounds, max then min, bounds indexed along the fiber */
 #define SIPB_SET_CARD_FIBER    9   /* project_cardinality!.jl:23-113: k largest magnitudes of every fiber (stable ties) */
-#define SIPB_SET_KIND_MAX      9
+#define SIPB_SET_CARD_SLICE   10   /* project_cardinality!.jl:115-146: k largest magnitudes of every 2-D slice of a 3-D
+                                      tensor; fiber_axis = the axis the slices are orthogonal to ("x","y","z" -> 0,1,2) */
+#define SIPB_SET_KIND_MAX     10
 
 /* transform-domain operator kinds (get_TD_operator.jl:12-95, get_discrete_Grad.jl) */
 #define SIPB_OP_IDENTITY 0

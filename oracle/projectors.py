@@ -172,3 +172,32 @@ def project_cardinality_fiber(x: np.ndarray, k: int, TD_n, mode) -> np.ndarray:
     np.put_along_axis(Xm, drop, TF(0.0), axis=0)
     x[:] = X.ravel(order="F")
     return x
+
+
+def project_cardinality_slice(x: np.ndarray, k: int, TD_n, mode) -> np.ndarray:
+    """project_cardinality!.jl:115-146 (3-D tensor, slice modes): every 2-D slice orthogonal to `mode[2]` keeps its k
+    largest magnitudes; ties are broken by the position inside the permuted / reshaped slice (stable sortperm),
+    which is the column-major order of the remaining two axes.  As in the reference the "x" and "y" modes work on
+    a permuted COPY — the input is NOT mutated and the projected vector is only returned — while "z" (a plain
+    reshape) mutates the input."""
+    TF = x.dtype.type
+    n1, n2, n3 = (int(v) for v in TD_n)
+    X = x.reshape((n1, n2, n3), order="F")
+    if mode[1] == "x":
+        Xp = np.transpose(X, (1, 2, 0)).reshape((n2 * n3, n1), order="F").copy(order="F")       # :122-124
+    elif mode[1] == "y":
+        Xp = np.transpose(X, (0, 2, 1)).reshape((n1 * n3, n2), order="F").copy(order="F")       # :125-127
+    elif mode[1] == "z":
+        Xp = X.reshape((n1 * n2, n3), order="F")                                                 # :128 (shares memory)
+    else:
+        raise ValueError("unknown slice direction")
+    order = np.argsort(-np.abs(Xp), axis=0, kind="stable")                                       # :133-136
+    np.put_along_axis(Xp, order[int(k):], TF(0.0), axis=0)
+    if mode[1] == "x":
+        out = np.transpose(Xp.reshape((n2, n3, n1), order="F"), (2, 0, 1))                       # :139-141
+    elif mode[1] == "y":
+        out = np.transpose(Xp.reshape((n1, n3, n2), order="F"), (0, 2, 1))                       # :142-144
+    else:
+        x[:] = Xp.reshape(-1, order="F")
+        return x
+    return np.ascontiguousarray(out.reshape(-1, order="F"))

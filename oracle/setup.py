@@ -29,6 +29,8 @@ def get_projector(constraint, comp_grid, A, TD_n, TF):
         mode = tuple(constraint.app_mode)
         if st == "bounds":                                                   # get_projector.jl:16
             return lambda x: proj.project_bounds_fiber(x, cmin, cmax, TD_n, mode)
+        if st == "cardinality" and mode[0] == "slice":                       # get_projector.jl:96, slice modes
+            return lambda x: proj.project_cardinality_slice(x, int(cmax), TD_n, mode)
         if st == "cardinality":                                              # get_projector.jl:96
             return lambda x: proj.project_cardinality_fiber(x, int(cmax), TD_n, mode)
         raise NotImplementedError("oracle: fiber/slice modes exist for bounds and cardinality only")

@@ -16,7 +16,7 @@ SIPB_OK = 0
 SIPB_E_INVALID, SIPB_E_UNSUPPORTED, SIPB_E_CUDA, SIPB_E_NCCL, SIPB_E_STATE, SIPB_E_MISSING_DIAG = -1, -2, -3, -4, -5, -6
 SIPB_F32, SIPB_F64 = 0, 1
 (SET_BOUNDS_SCALAR, SET_BOUNDS_VECTOR, SET_L1, SET_L2, SET_ANNULUS, SET_CARDINALITY, SET_PROX_L1,
- SET_DISTANCE, SET_BOUNDS_FIBER, SET_CARD_FIBER) = range(10)
+ SET_DISTANCE, SET_BOUNDS_FIBER, SET_CARD_FIBER, SET_CARD_SLICE) = range(11)
 OP_IDENTITY, OP_DX, OP_DY, OP_DZ, OP_TV, OP_DXZ, OP_SPARSE = range(7)
 BLOCK_PLAIN, BLOCK_LEFT, BLOCK_RIGHT, BLOCK_BOTH = range(4)
 N_PHASES = 7

@@ -62,6 +62,10 @@ class Projector:
             raise ValueError("vector bounds have %d entries, input has %d" % (self.min_vec.size, v.size))
         d = self.descriptor()
         lib = _lib.load()
+        if self.set_kind == _lib.SET_CARD_SLICE and self.fiber_axis != 2:
+            # the reference's x / y slice modes work on a permuted COPY and return it; the argument is left untouched
+            # (project_cardinality!.jl:115-118 "code currently does not mutate the input for slice projections")
+            v = v.copy()
         _lib.check(lib.sipb_project(_lib.ctx(), _lib.dtype_code(self.TF), C.byref(d), v.size, v.ctypes.data, None))
         return v
 
@@ -79,9 +83,22 @@ def get_projector(constraint, comp_grid, special_operator_list, A, TD_n, TF) -> 
     lo, hi = constraint.min, constraint.max
     if constraint.app_mode[0] not in ("matrix", "tensor"):
         # fiber application modes (get_projector.jl:12-18,92-98; project_bounds!.jl:38-88,
-        # project_cardinality!.jl:23-113); slice modes are rejected
+        # project_cardinality!.jl:23-113) and the slice mode of cardinality on 3-D tensors (:115-146)
+        if constraint.app_mode[0] == "slice" and st == "cardinality":
+            if len(TD_n) != 3:
+                raise NotImplementedError("slice modes exist for 3-D tensors only")
+            if constraint.TD_OP in ("TV", "D2D", "D3D"):
+                raise ValueError("slice modes need a single-block operator (the TV output is not a grid)")
+            try:
+                axis = {"x": 0, "y": 1, "z": 2}[constraint.app_mode[1]]
+            except KeyError:
+                raise ValueError("slice direction %r is not valid" % (constraint.app_mode[1],))
+            return Projector(_lib.SET_CARD_SLICE, TF, k=int(hi), name="cardinality(slice)", fiber_axis=axis, td_n=TD_n)
+        if constraint.app_mode[0] == "slice" and st == "bounds":
+            raise NotImplementedError("bound constraints per slice of a tensor currently not implemented, yet...")   # project_bounds!.jl:83
         if constraint.app_mode[0] != "fiber" or st not in ("bounds", "cardinality"):
-            raise NotImplementedError("only the fiber application mode of bounds and cardinality is on the device path")
+            raise NotImplementedError("only the fiber modes of bounds / cardinality and the slice mode of cardinality are "
+                                      "on the device path")
         if constraint.TD_OP in ("TV", "D2D", "D3D"):
             raise ValueError("fiber modes need a single-block operator (the TV output is not a grid)")
         nd = len(TD_n)

@@ -773,6 +773,7 @@ __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
       else if (P.fiber_axis == 2) c = q / (P.td[0] * P.td[1]);
       return t_min<T>(t_max<T>(v, P.lo_vec[c]), P.hi_vec[c]);       // project_bounds!.jl:46,50,65-77
     }
+    case SIPB_SET_CARD_SLICE:
     case SIPB_SET_CARD_FIBER:      // already projected in place by k_card_fiber_* (pass-through)
       return v;
     case SIPB_SET_DISTANCE: {      // (x*rho + m) / (rho + 1.0) in Float64   prox_l2s!.jl:4
@@ -1465,6 +1466,23 @@ __global__ void __launch_bounds__(kThreads) k_card_fiber_contig(T* __restrict__ 
       if (e < L && (key < prefix || (tie && seen + before >= need))) fib[e] = (T)0;
       seen += __popc(bal);
     }
+  }
+}
+
+// slice modes (project_cardinality!.jl:122-129,138-145): permutedims + reshape so that every slice orthogonal to
+// `axis` becomes one contiguous column, in the reference's element order inside the slice
+//   axis 0: dst[(j + d1*k) + d1*d2*i]   axis 1: dst[(i + d0*k) + d0*d2*j]   (inverse != 0: the way back)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_slice_permute(const T* __restrict__ src, T* __restrict__ dst, unsigned d0,
+                                                            unsigned d1, unsigned d2, int axis, int inverse) {
+  const i64 n = (i64)d0 * d1 * d2;
+  for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (i64)gridDim.x * blockDim.x) {
+    const unsigned i = (unsigned)(q % d0);
+    const unsigned j = (unsigned)((q / d0) % d1);
+    const unsigned kk = (unsigned)(q / ((i64)d0 * d1));
+    const i64 t = axis == 0 ? ((i64)j + (i64)d1 * kk) + (i64)d1 * d2 * i : ((i64)i + (i64)d0 * kk) + (i64)d0 * d2 * j;
+    if (inverse) dst[q] = src[t];
+    else dst[t] = src[q];
   }
 }
 

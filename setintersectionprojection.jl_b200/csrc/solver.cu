@@ -697,6 +697,7 @@ struct SetT {
   i64 Mglob = 0;   // rows of the global operator
   DevBuf<T> y, l, y_old, s, s0, y0, l0, lhat0;   // s only for reduction-type projectors
   DevBuf<T> lo_vec, hi_vec;
+  DevBuf<T> perm;             // SIPB_SET_CARD_SLICE, x / y slices: slice-major scratch copy
   SparseDev<T> sparse;        // SIPB_OP_SPARSE: the explicit operator (op is then the identity over the s buffer)
   bool is_sparse = false;
   DevBuf<T> ata;              // [nd][ld]   (released once the stencil-class table has been verified)
@@ -845,7 +846,8 @@ struct Problem : sipb_problem {
     SIPB_REQUIRE(d->set_kind >= SIPB_SET_BOUNDS_SCALAR && d->set_kind <= SIPB_SET_KIND_MAX, SIPB_E_UNSUPPORTED,
                  "set type is outside the device hot path (rank, nuclear, subspace, histogram and slice modes are "
                  "rejected)");
-    const bool fiber = d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_CARD_FIBER;
+    const bool fiber = d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_CARD_FIBER ||
+                       d->set_kind == SIPB_SET_CARD_SLICE;
     if (fiber) {
       SIPB_REQUIRE(!sg.on && !minkowski, SIPB_E_UNSUPPORTED, "fiber modes are single-GPU, non-Minkowski");
       SIPB_REQUIRE(d->fiber_axis >= 0 && d->fiber_axis < ndim, SIPB_E_INVALID, "fiber axis outside the grid");
@@ -883,6 +885,7 @@ struct Problem : sipb_problem {
     auto AH = [&](DevBuf<T>& b) { if (e == cudaSuccess) e = b.alloc((size_t)S->M, S->z_halo ? (size_t)sg.plane : 0, 0); };
     AH(S->y); AH(S->l); AH(S->y_old); A(S->s0); A(S->y0); A(S->l0); A(S->lhat0);
     if (!proj_is_elementwise(d->set_kind) || S->is_sparse) A(S->s);
+    if (d->set_kind == SIPB_SET_CARD_SLICE && d->fiber_axis != 2) A(S->perm);
     if (e == cudaSuccess) e = S->pp_y.alloc(1);
     if (e == cudaSuccess) e = S->pp_f.alloc(1);
     if (e == cudaSuccess) e = S->warm.alloc(2);
@@ -1147,9 +1150,24 @@ struct Problem : sipb_problem {
   }
 
   // per-fiber cardinality in place (project_cardinality!.jl:23-113)
-  void card_fiber(const sipb_set_desc& d, T* v) {
+  void card_fiber(SetT<T>& S, T* v) {
     sipb_ctx* c = ctx;
+    const sipb_set_desc& d = S.desc;
     const unsigned d0 = (unsigned)d.td_n[0], d1 = (unsigned)d.td_n[1], d2 = (unsigned)d.td_n[2];
+    if (d.set_kind == SIPB_SET_CARD_SLICE) {
+      // every slice orthogonal to fiber_axis is one long "fiber" once it is contiguous (project_cardinality!.jl:115-146)
+      const i64 M = (i64)d0 * d1 * d2;
+      if (d.fiber_axis == 2) {                        // z: the n3 planes are contiguous already
+        LAUNCH(c, KC_TIES, k_card_fiber_contig<T>, c->grid_for((i64)d2 * 32), v, (i64)d2, d0 * d1, (long long)d.k);
+        return;
+      }
+      const i64 nsl = d.fiber_axis == 0 ? d0 : d1;
+      const unsigned L = d.fiber_axis == 0 ? d1 * d2 : d0 * d2;
+      LAUNCH(c, KC_TIES, k_slice_permute<T>, c->grid_for(M), (const T*)v, S.perm.p, d0, d1, d2, d.fiber_axis, 0);
+      LAUNCH(c, KC_TIES, k_card_fiber_contig<T>, c->grid_for(nsl * 32), S.perm.p, nsl, L, (long long)d.k);
+      LAUNCH(c, KC_TIES, k_slice_permute<T>, c->grid_for(M), (const T*)S.perm.p, v, d0, d1, d2, d.fiber_axis, 1);
+      return;
+    }
     if (d.fiber_axis == 0) {
       const i64 nfib = (i64)d1 * d2;
       LAUNCH(c, KC_TIES, k_card_fiber_contig<T>, c->grid_for(nfib * 32), v, nfib, d0, (long long)d.k);
@@ -1195,8 +1213,8 @@ struct Problem : sipb_problem {
       }
       last = c->h_l1->passes;
       LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
-    } else if (kind == SIPB_SET_CARD_FIBER) {
-      card_fiber(S.desc, v);            // projects every fiber in place; the apply pass is then a pass-through
+    } else if (kind == SIPB_SET_CARD_FIBER || kind == SIPB_SET_CARD_SLICE) {
+      card_fiber(S, v);            // projects every fiber in place; the apply pass is then a pass-through
     } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {
       LAUNCH1(c, KC_PARAMS, k_l2_params<T>, stats, kind, S.desc.min, S.desc.max, (double)Mg, pp);
     } else if (kind == SIPB_SET_CARDINALITY) {
@@ -1243,10 +1261,18 @@ struct Problem : sipb_problem {
   }
 
   // relative feasibility numerator/denominator of the vector sv (= A x) -> d_scal[slot], [slot+1]
-  int feasibility_of(SetT<T>& S, T* sv, int slot) {
+  // in_loop: the feasibility logged every 10th iteration (update_y_l.jl:90-94) relies on P_sub mutating its
+  // argument; the reference's slice-mode cardinality does NOT for x / y slices (project_cardinality!.jl:115-118:
+  // permutedims copies), so there the logged value is ||s - s|| / ||s|| = 0 — reproduced here.
+  int feasibility_of(SetT<T>& S, T* sv, int slot, bool in_loop = false) {
     sipb_ctx* c = ctx;
     const i64 M = S.M;
     ProjDev<T> P = proj_static(S, (T)0);
+    if (in_loop && S.desc.set_kind == SIPB_SET_CARD_SLICE && S.desc.fiber_axis != 2) {
+      LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, sv, (const T*)sv, P, (const ProjParams<T>*)S.pp_f.p, 0, c->rs,
+             c->d_scal + slot);
+      return SIPB_OK;
+    }
     if (proj_is_elementwise(S.desc.set_kind)) {
       LAUNCH(c, KC_FEAS, k_feas_dyn<T>, c->grid_for(M), M, sv, (const T*)nullptr, P, (const ProjParams<T>*)nullptr, 0,
              c->rs, c->d_scal + slot);
@@ -1256,7 +1282,8 @@ struct Problem : sipb_problem {
     LAUNCH(c, KC_VEC_STATS, k_vec_stats<T>, c->grid_for(M), M, sv, c->rs, c->d_scal + stat_slot);
     T* vec = sv;
     const T* ref = nullptr;
-    if (S.desc.set_kind == SIPB_SET_CARDINALITY || S.desc.set_kind == SIPB_SET_CARD_FIBER) {   // in-place work on a scratch copy
+    if (S.desc.set_kind == SIPB_SET_CARDINALITY || S.desc.set_kind == SIPB_SET_CARD_FIBER ||
+        S.desc.set_kind == SIPB_SET_CARD_SLICE) {   // in-place work on a scratch copy
       SIPB_CUDA_CHECK(cudaMemcpyAsync(tmp.p, sv, M * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
       vec = tmp.p;
       ref = sv;
@@ -1686,7 +1713,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
           LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, false>), c->grid_fit((const void*)k_yl<T, 2, false>, nvecM), ya, c->rs,
                  c->d_scal + base);
         if (want_feas) {
-          rc = feasibility_of(S, S.s.p, base + 1);
+          rc = feasibility_of(S, S.s.p, base + 1, true);
           if (rc) return rc;
         }
       }
@@ -2231,6 +2258,7 @@ static int project_impl(sipb_ctx* c, const sipb_set_desc* d, int64_t M, void* v,
   SIPB_CUDA_CHECK(S.pp_f.alloc(1));
   SIPB_CUDA_CHECK(S.warm.alloc(2));
   SIPB_CUDA_CHECK(P.tmp.alloc((size_t)M));
+  if (d->set_kind == SIPB_SET_CARD_SLICE && d->fiber_axis != 2) SIPB_CUDA_CHECK(S.perm.alloc((size_t)M));
   SIPB_CUDA_CHECK(cudaMemsetAsync(S.warm.p, 0, 2 * sizeof(double), c->stream));
   SIPB_CUDA_CHECK(cudaMemsetAsync(S.pp_f.p, 0, sizeof(ProjParams<T>), c->stream));
   SIPB_CUDA_CHECK(cudaMemcpyAsync(S.s.p, v, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
@@ -2405,7 +2433,8 @@ int sipb_project(sipb_ctx* ctx, int dtype, const sipb_set_desc* desc, int64_t M,
   SIPB_REQUIRE(ctx && desc && v, SIPB_E_INVALID, "null argument");
   SIPB_REQUIRE(desc->set_kind >= SIPB_SET_BOUNDS_SCALAR && desc->set_kind <= SIPB_SET_KIND_MAX, SIPB_E_UNSUPPORTED,
                "set type is outside the device hot path");
-  if (desc->set_kind == SIPB_SET_BOUNDS_FIBER || desc->set_kind == SIPB_SET_CARD_FIBER) {
+  if (desc->set_kind == SIPB_SET_BOUNDS_FIBER || desc->set_kind == SIPB_SET_CARD_FIBER ||
+      desc->set_kind == SIPB_SET_CARD_SLICE) {
     SIPB_REQUIRE(desc->fiber_axis >= 0 && desc->fiber_axis < 3 && desc->td_n[0] >= 1 && desc->td_n[1] >= 1 &&
                      desc->td_n[2] >= 1 && desc->td_n[0] * desc->td_n[1] * desc->td_n[2] == M,
                  SIPB_E_INVALID, "td_n / fiber_axis do not match the vector");

@@ -683,3 +683,56 @@ def test_parsdmm_custom_sparse_operator(sip, orc, TF, order):
     assert len(ls.obj) > 5
     s = W @ xs
     assert np.abs(s).sum() <= tau * (1 + 50 * ls.set_feasibility[-2].max() + 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# slice-mode cardinality on 3-D tensors   (project_cardinality!.jl:115-146, test_projectors.jl:81-93)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("TF", [np.float64, np.float32])
+def test_slice_cardinality_projector(sip, orc, TF):
+    n = (13, 9, 7)
+    X = np.random.default_rng(11).standard_normal(n).astype(TF)
+    X[2, :, :] = np.sign(X[2, :, :])            # slices full of ties: the stable order decides
+    X[:, 4, :] = TF(0.5) * np.sign(X[:, 4, :])
+    X[:, :, 3] = TF(2.0)
+    for direction, axis, k in (("x", 0, 7), ("y", 1, 6), ("z", 2, 5)):
+        outs = []
+        for api in (orc, sip):
+            cons = [api.set_definitions("cardinality", "identity", 0, k, ("slice", direction))]
+            P = api.setup_constraints(cons, api.compgrid((1.0, 1.0, 1.0), n), TF)[0][0]
+            v = X.ravel(order="F").copy()
+            out = P(v)
+            outs.append((out, v))
+        (oo, vo), (so, vs) = outs
+        assert np.array_equal(so, oo)                                        # values and support bit exact (stable ties)
+        assert np.all(np.count_nonzero(so.reshape(n, order="F"), axis=tuple(a for a in range(3) if a != axis)) == k)
+        # x / y slices: the reference works on a permuted copy (input untouched); z: in place
+        assert np.array_equal(vs, vo) and (np.array_equal(vs, X.ravel(order="F")) == (direction != "z"))
+
+
+def test_parsdmm_with_slice_cardinality(sip, orc):
+    """PARSDMM with bounds and a per-x-slice cardinality set on D_z.  The in-loop feasibility of an x / y slice set
+    is identically 0 in the reference (its projector does not mutate the argument update_y_l.jl:93 relies on):
+    reproduced by oracle and device."""
+    TF = np.float64
+    n, d = (12, 10, 8), (25.0, 25.0, 10.0)
+    m = pr.synthetic_model(n, TF)
+    res = []
+    for api in (orc, sip):
+        cg = api.compgrid(d, n)
+        cons = [api.set_definitions("bounds", "identity", 1500.0, 4600.0, ("tensor", "")),
+                api.set_definitions("cardinality", "D_z", 0, 25, ("slice", "x")),
+                api.set_definitions("cardinality", "D_x", 0, 30, ("slice", "z"))]
+        opt = api.PARSDMM_options()
+        opt.FL, opt.maxit = TF, 40
+        P_sub, TD_OP, set_Prop = api.setup_constraints(cons, cg, TF)
+        TD_OP, AtA, l, y = api.PARSDMM_precompute_distribute(TD_OP, set_Prop, cg, opt)
+        res.append(api.PARSDMM(m.copy(), AtA, TD_OP, set_Prop, P_sub, cg, opt))
+    (xo, lo_, ll, yy), (xs, ls, l2, y2) = res
+    assert len(ls.obj) == len(lo_.obj) and np.array_equal(ls.cg_it, lo_.cg_it)
+    assert relerr(xs, xo) < TOL[TF]
+    assert np.array_equal(y2[1] != 0, yy[1] != 0) and np.array_equal(y2[2] != 0, yy[2] != 0)
+    assert np.allclose(ls.set_feasibility, lo_.set_feasibility, rtol=50 * TOL[TF], atol=1e-12)
+    assert ls.set_feasibility[0, 1] > 0 and np.all(ls.set_feasibility[1:-1, 1] == 0)        # the quirk
+    yz = y2[2].reshape((n[0] - 1, n[1], n[2]), order="F")
+    assert np.all(np.count_nonzero(yz, axis=(0, 1)) <= 30)
