@@ -127,7 +127,7 @@ def cpu_threaded_available():
     if _CPU_MODE["threaded"] is None:
         try:
             from oracle import cpu_baseline as cb
-            cb.threads()
+            cb.use_all_cores()           # torchrun exports OMP_NUM_THREADS=1; the baseline gets every host core
             _CPU_MODE["threaded"] = True
         except Exception as e:       # noqa: BLE001
             print("bench.py: threaded CPU baseline unavailable (%s); timing the NumPy oracle instead" % e, file=sys.stderr)

@@ -34,6 +34,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build_c.build())
         _LIB.sipref_threads.restype = C.c_int
+        _LIB.sipref_set_threads.restype, _LIB.sipref_set_threads.argtypes = None, [C.c_int]
         for sfx, real in (("f32", C.c_float), ("f64", C.c_double)):
             def f(name, res, args):
                 fn = getattr(_LIB, "sipref_%s_%s" % (name, sfx))
@@ -60,6 +61,17 @@ def lib():
 
 def threads() -> int:
     return int(lib().sipref_threads())
+
+
+def use_all_cores() -> int:
+    """Use every core this process may run on, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().sipref_set_threads(int(n))
+    return threads()
 
 
 class _K:
