@@ -22,7 +22,6 @@ import scipy.sparse as sp
 from . import build_c
 from . import operators as ops
 from . import parsdmm as P
-from . import projectors as proj
 from .sip_types import convert_options, eps, log_type_PARSDMM
 
 _LIB = None

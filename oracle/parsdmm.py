@@ -11,7 +11,6 @@ code is written as np.float64 here and every TF literal as TF(...).
 from __future__ import annotations
 
 import time
-import warnings
 
 import numpy as np
 

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .operators import SPECIAL_OPERATORS, SparseOperator, TDOperator, get_TD_operator
+from .operators import SPECIAL_OPERATORS, SparseOperator, get_TD_operator
 from .types import set_properties
 
 _REJECTED = {

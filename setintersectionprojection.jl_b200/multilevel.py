@@ -15,7 +15,6 @@ import copy
 
 import numpy as np
 
-import ctypes as C
 
 from . import _lib
 from . import distributed as dd
