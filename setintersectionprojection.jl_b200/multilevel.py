@@ -15,7 +15,6 @@ import copy
 
 import numpy as np
 
-
 from . import _lib
 from . import distributed as dd
 from .constraints import setup_constraints
