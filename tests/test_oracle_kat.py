@@ -152,6 +152,33 @@ def test_projectors():
     assert np.array_equal(proj.project_l2(x, 1.234 * np.linalg.norm(x)), y)
 
 
+def test_projectors_fiber_and_slice_modes():
+    """test_projectors.jl:56-93: exactly k non-zeros per column / row / fiber / slice of random data, for every
+    direction; slice modes "x" and "y" return the result without mutating the input, "z" works in place
+    (project_cardinality!.jl:115-146)."""
+    rng = np.random.default_rng(7)
+    X = rng.standard_normal((50, 100))
+    Y = proj.project_cardinality_fiber(X.ravel(order="F").copy(), 7, X.shape, ("fiber", "x")).reshape(X.shape, order="F")
+    assert np.all(np.count_nonzero(Y, axis=0) == 7)
+    Y = proj.project_cardinality_fiber(X.ravel(order="F").copy(), 11, X.shape, ("fiber", "z")).reshape(X.shape, order="F")
+    assert np.all(np.count_nonzero(Y, axis=1) == 11)
+    n = (50, 60, 30)
+    X = rng.standard_normal(n)
+    for direction, axis, k in (("x", 0, 7), ("y", 1, 6), ("z", 2, 4)):
+        Y = proj.project_cardinality_fiber(X.ravel(order="F").copy(), k, n, ("fiber", direction)).reshape(n, order="F")
+        assert np.all(np.count_nonzero(Y, axis=axis) == k)
+    for direction, axis, k in (("x", 0, 7), ("y", 1, 6), ("z", 2, 5)):
+        v = X.ravel(order="F").copy()
+        out = proj.project_cardinality_slice(v, k, n, ("slice", direction)).reshape(n, order="F")
+        assert np.all(np.count_nonzero(out, axis=tuple(a for a in range(3) if a != axis)) == k)
+        assert np.array_equal(v, X.ravel(order="F")) == (direction != "z")
+    # kept entries are the k largest magnitudes of the slice
+    out = proj.project_cardinality_slice(X.ravel(order="F").copy(), 7, n, ("slice", "x")).reshape(n, order="F")
+    for i in (0, 17, 49):
+        kept = np.abs(out[i][out[i] != 0])
+        assert kept.min() >= np.sort(np.abs(X[i]).ravel())[-7]
+
+
 def test_julia_pairwise_cumsum_matches_exact_sum():
     rng = np.random.default_rng(5)
     for n in (1, 2, 127, 128, 129, 1000, 40000):
