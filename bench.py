@@ -348,6 +348,25 @@ def run_device(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    # BASELINE.json's second metric, "CDS-SpMV HBM GB/s": the compressed-diagonal SpMV + dot kernel of cg.jl on the
+    # CDS ARRAYS of this grid (nd = 7 diagonals), timed alone back to back (sipb_bench_spmv, CUDA events) — the
+    # solve itself no longer streams the matrix when Q is held as stencil-class tables (roofline.q_form).
+    cds = None
+    if world == 1 and roof is not None:
+        try:
+            import ctypes as C
+            L = sip._lib
+            n3 = (C.c_int64 * 3)(n, n, nz)
+            ms_, nb_ = C.c_double(0.0), C.c_int64(0)
+            L.check(L.load().sipb_bench_spmv(L.ctx(), 0, 3, n3, 3, 20, 0, C.byref(ms_), C.byref(nb_)))
+            if ms_.value > 0:
+                gbs = nb_.value / (ms_.value * 1e-3) / 1e9
+                cds = {"form": "arrays", "avg_launch_ms": ms_.value, "algorithmic_bytes_per_launch": nb_.value,
+                       "gbs": gbs, "frac": gbs / roof["peak"], "launches": 20}
+        except Exception as e:       # noqa: BLE001 - an auxiliary figure must never take the bench line down
+            print("bench.py: CDS SpMV unit timing skipped (%s)" % e, file=sys.stderr)
+        roof["cds_spmv_arrays"] = cds
+
     cpu = None
     if world == 1 and not args.no_cpu:
         v, t_iter, t_setup, done = cpu_sample(n, args.cpu_iters)
