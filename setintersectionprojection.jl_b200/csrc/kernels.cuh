@@ -1289,6 +1289,8 @@ struct L1State {
 __device__ __forceinline__ void l1_newton_step(L1State* st, double C, double S) {
   const double theta = st->theta;
   st->passes += 1;
+  st->C = C;                 // kept for the host: C == M at the fix point triggers the reference's lv-1 cap (k_l1_cap)
+  st->S = S;
   if (C == 0.0) {            // theta at/above max|v|: restart from the left end
     st->theta = 0.0;
     st->on_left = 1;
@@ -1342,6 +1344,24 @@ __global__ void k_l1_step(L1State* st, const __grid_constant__ CommDev cd) {
   if (st->done) return;
   if (cd.on) mail_collect<2>(cd, &st->C);
   l1_newton_step(st, st->C, st->S);
+}
+
+// min |v| as an order-preserving magnitude key -> atomicMin on out[0] (initialised to ~0ull by the host).
+// Only needed when EVERY entry stays above the l1 threshold: the reference's scan stops at lv-1
+// (project_l1_Duchi!.jl:42-46), so its theta then comes from the lv-1 largest entries (see k_l1_cap).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_absmin_key(i64 M, const T* __restrict__ v, unsigned long long* out) {
+  unsigned long long k = ~0ull;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    const unsigned long long q = mag_key<T>(v[r]);
+    k = q < k ? q : k;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long q = __shfl_xor_sync(0xffffffffu, k, o);
+    k = q < k ? q : k;
+  }
+  if ((threadIdx.x & 31) == 0 && k != ~0ull) atomicMin(out, k);
 }
 
 // =============================================================================================

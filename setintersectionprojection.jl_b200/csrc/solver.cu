@@ -322,6 +322,21 @@ __global__ void k_l1_end(L1State* st, double* warm, ProjParams<T>* pp) {
   *warm = st->theta;
 }
 
+// project_l1_Duchi!.jl:42-46: the scan `while u[rho+1] > (sv[rho+1]-b)/(rho+1) && (rho+1) < lv` stops at rho = lv-1,
+// so when every entry is active (C == M at the exact root) the reference takes
+//   theta = max(0, (sv[lv-1] - b)/(lv-1)),   sv[lv-1] = sum|v| - min|v|
+// instead of the exact root (S - b)/M.  `minkey`: min |v| as a magnitude key (k_absmin_key).
+template <typename T>
+__global__ void k_l1_cap(L1State* st, const unsigned long long* minkey, ProjParams<T>* pp) {
+  if (st->theta < 0.0 || st->C != st->M || st->M < 2.0) return;
+  T umin;
+  if (sizeof(T) == 4) umin = (T)__uint_as_float((unsigned)*minkey);
+  else umin = (T)__longlong_as_double((long long)*minkey);
+  const T sv = (T)(st->S1 - (double)umin);
+  const T th = (sv - (T)st->tau) / (T)(st->M - 1.0);
+  pp->theta = th > (T)0 ? th : (T)0;
+}
+
 // l2 ball / annulus parameters from sum v^2     (project_l2!.jl:8-13, project_annulus!.jl:8-18)
 template <typename T>
 __global__ void k_l2_params(const double* stats, int kind, double smin, double smax, double M, ProjParams<T>* pp) {
@@ -1211,8 +1226,20 @@ struct Problem : sipb_problem {
         SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
         if (c->h_l1->done || launched >= 256) break;
       }
+      SIPB_REQUIRE(c->h_l1->done, SIPB_E_STATE, "l1 threshold search did not converge within 256 passes");
       last = c->h_l1->passes;
       LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
+      if (c->h_l1->theta >= 0.0 && c->h_l1->C == c->h_l1->M && Mg >= 2) {
+        // every entry is above the threshold: reproduce the reference's lv-1 cap (project_l1_Duchi!.jl:42-46)
+        unsigned long long* mk = c->d_tie_counts;
+        SIPB_CUDA_CHECK(cudaMemsetAsync(mk, 0xff, sizeof(unsigned long long), c->stream));
+        LAUNCH(c, KC_L1_PASS, k_absmin_key<T>, c->grid_for(M), M, (const T*)v, mk);
+        if (sg.on) {
+          c->nccl_calls++;
+          SIPB_NCCL_CHECK(NCCL(AllReduce)(mk, mk, 1, ncclUint64, ncclMin, c->comm, c->stream));
+        }
+        LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
+      }
     } else if (kind == SIPB_SET_CARD_FIBER || kind == SIPB_SET_CARD_SLICE) {
       card_fiber(S, v);            // projects every fiber in place; the apply pass is then a pass-through
     } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {

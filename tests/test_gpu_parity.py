@@ -183,6 +183,31 @@ def test_projectors_match_oracle(sip, orc, TF):
     assert np.array_equal(_P(sip, "prox_l1", 0.0, 3.0, TF)(x.copy()), orc.proj.prox_l1(x.copy(), TF(3.0)))
 
 
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+def test_l1_all_entries_active_cap(sip, orc, TF):
+    """project_l1_Duchi!.jl:42-46: the scan stops at rho = lv-1, so when EVERY entry stays above the threshold the
+    reference uses theta = max(0, (sv[lv-1]-b)/(lv-1)) instead of the exact root — including theta = 0, i.e. the
+    vector comes back unprojected.  The device reproduces this (k_l1_cap)."""
+    v = np.array([3.0, -2.5, 2.8, 3.1], dtype=TF)
+    for tau in (10.0, 11.0, 5.0, 1.0):                    # 10, 11: theta = 0 (unchanged); 5, 1: capped but positive
+        want = orc.proj.project_l1_Duchi(v.copy(), TF(tau))
+        got = _P(sip, "l1", 0.0, tau, TF, n=(2, 2))(v.copy())
+        assert relerr(got, want) < 20 * np.finfo(TF).eps, (tau, got, want)
+    assert np.array_equal(_P(sip, "l1", 0.0, 10.0, TF, n=(2, 2))(v.copy()), v)
+    rng = np.random.default_rng(3)
+    w = (5.0 + rng.random(1000)).astype(TF) * np.where(rng.random(1000) < 0.5, -1, 1).astype(TF)
+    tau = TF(np.abs(w).sum() * 0.97)                       # exact root 0.03*mean < min|w|: all 1000 entries active
+    want = orc.proj.project_l1_Duchi(w.copy(), tau)
+    got = _P(sip, "l1", 0.0, tau, TF, n=(500, 2))(w.copy())
+    assert relerr(got, want) < 20 * np.finfo(TF).eps
+    # a vector with ONE inactive entry takes the exact root (no cap)
+    w[7] = TF(1e-3)
+    tau = TF(np.abs(w).sum() * 0.97)
+    want = orc.proj.project_l1_Duchi(w.copy(), tau)
+    got = _P(sip, "l1", 0.0, tau, TF, n=(500, 2))(w.copy())
+    assert relerr(got, want) < 20 * np.finfo(TF).eps and got[7] == 0
+
+
 def test_rejected_sets(sip):
     for st in ("rank", "nuclear", "subspace", "histogram"):
         with pytest.raises(NotImplementedError):
