@@ -165,6 +165,7 @@ typedef struct sipb_log {
 
 /* Environment switches (read when the object they affect is created; for A/B measurements and tests):
  *   SIPB_Q_CLASSES=0      sipb_problem_finalize keeps Q / AtA as CDS arrays (see sipb_problem_q_form)
+ *   SIPB_SPMV_TILE=0      the CG uses the generic grid-stride SpMV instead of the tiled TMA-staged kernel
  *   SIPB_P2P=0            sipb_comm_init uses NCCL for the CG reductions and halos instead of peer memory
  *   SIPB_FUSE_STOP_OFF=1  sipb_solve reduces the obj / evol_x sums in a separate pass instead of inside the
  *                         distance term's y/l update */
@@ -261,6 +262,16 @@ int sipb_cds_scaled_add(sipb_ctx* ctx, int dtype, int64_t N, int nd_a, void* A, 
  * returns average milliseconds per launch over `reps` launches after `warmup`. */
 int sipb_bench_spmv(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, int warmup, int reps,
                     int flush_l2, double* avg_ms, int64_t* algorithmic_bytes);
+
+/* the same with a choice of matrix form (0 = CDS arrays, (nd+2)*N*s algorithmic bytes; 1 = stencil-class tables,
+ * 2*N*s) and of kernel (tiled = 1: the TMA-staged plane sweep of spmv_tile.cuh; 0: the generic grid-stride kernel) */
+int sipb_bench_spmv2(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, int warmup, int reps, int flush_l2,
+                     int form, int tiled, double* avg_ms, int64_t* algorithmic_bytes);
+/* y = A*x (CDS_MVp_MT.jl:9-25) for a CDS matrix living on a 3-D grid: takes the tiled kernel when the offsets are a
+ * subset of {0, +-1, +-n1, +-n1*n2} and a grid line is a whole number of 16-byte vectors (*used_tiled = 1),
+ * otherwise the generic kernel.  Unit-test entry point of the tiled SpMV. */
+int sipb_cds_spmv_grid(sipb_ctx* ctx, int dtype, const int64_t* n, int nd, const void* R, const int64_t* offsets,
+                       const void* x, void* y, int* used_tiled);
 
 #ifdef __cplusplus
 }

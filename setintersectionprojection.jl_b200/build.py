@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsipb200.so")
 SOURCES = ["solver.cu"]
-HEADERS = ["common.cuh", "ops.cuh", "kernels.cuh", os.path.join("..", "..", "include", "sipb200.h")]
+HEADERS = ["common.cuh", "ops.cuh", "kernels.cuh", "spmv_tile.cuh", os.path.join("..", "..", "include", "sipb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",            # the reference (Julia, no fast-math) never contracts a*b+c
               "-Xcompiler", "-fPIC", "-shared"]
@@ -27,7 +27,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    extra = os.environ.get("SIPB_NVCC_EXTRA", "").split()       # e.g. -DSIPB_TILE_ITEMS_F32=2 for kernel experiments
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
           [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
     print("[sipb200] " + " ".join(cmd), file=sys.stderr)
     subprocess.run(cmd, check=True, cwd=CSRC)

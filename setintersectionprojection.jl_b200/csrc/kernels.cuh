@@ -1,6 +1,7 @@
 // kernels.cuh — hand-written sm_100a kernels of the PARSDMM iteration.
 //
 // Kernels by reference routine (all HBM-bandwidth bound; one pass over their operands):
+//   k_spmv_tile       (spmv_tile.cuh) the same SpMV / CG prologue for 3-D stencils as a plane sweep with TMA-staged tiles
 //   k_spmv            CDS_MVp_MT.jl:9-25 + Ax_CDS_MT (argmin_x.jl:72-78) [+ dot(p,Ap), cg.jl:88]; Q as CDS arrays
 //                     or as verified stencil-class tables (k_class_extract / k_class_verify / k_class_axpy)
 //   k_cg_init         argmin_x.jl:33-37 + cg.jl:47-76   (one SpMV instead of the reference's two)
@@ -327,6 +328,10 @@ struct CgState {
   int parsdmm_it;   // i of PARSDMM.jl:97 (selects the i<3 tolerance rule); 0 => plain cg with tol given
   int loops;        // loop iterations actually executed (speculative launches after `done` return at once)
 };
+
+}  // namespace sipb
+#include "spmv_tile.cuh"     // tiled, TMA-staged SpMV / CG prologue for 3-D stencils (uses SpmvArgs, CgState, CommDev)
+namespace sipb {
 
 // r = b - Q x ; p = r ; (x_old = x) ; sums bb, rr
 template <typename T>

@@ -682,6 +682,146 @@ static inline bool op_has_slow_axis_block(const OpDev& op) {
   return false;
 }
 
+// Geometry of the tiled SpMV (spmv_tile.cuh) for Q with offsets `offs` on the grid n (slab: nloc local planes
+// starting at global plane kofs).  ok = 0 when the matrix / grid is outside what the tiled kernel handles (the
+// generic k_spmv then runs): 2-D or Minkowski problems, lines that are not a whole number of 16-byte vectors,
+// offsets other than {0, +-1, +-n0, +-n0*n1}, SIPB_SPMV_TILE=0.
+template <typename T>
+static TileGeom plan_tile(int ndim, const int64_t* n, bool minkowski, const std::vector<int64_t>& offs, i64 nloc,
+                          i64 kofs, bool has_lo, bool has_hi, int num_sms) {
+  TileGeom g;
+  memset(&g, 0, sizeof(g));
+  const char* env = getenv("SIPB_SPMV_TILE");
+  if (env && env[0] == '0') return g;
+  constexpr int VW = Vec<T>::W;
+  if (ndim != 3 || minkowski || offs.empty() || (int)offs.size() > kTileDiag) return g;
+  const i64 n0 = n[0], n1 = n[1], P = n0 * n1;
+  int present = 0;
+  if (n0 % VW != 0 || n0 < VW || n1 < 2 || nloc < 1 || P * (nloc + 2) >= ((i64)1 << 31)) return g;
+  for (size_t d = 0; d < offs.size(); ++d) {
+    const i64 o = offs[d];
+    int code = -1;
+    if (o == 0) code = 0;
+    else if (o == -1) code = 1;
+    else if (o == 1) code = 2;
+    else if (o == -n0) code = 3;
+    else if (o == n0) code = 4;
+    else if (o == -P) code = 5;
+    else if (o == P) code = 6;
+    if (code < 0 || ((present >> code) & 1)) return g;
+    g.code[d] = code;
+    present |= 1 << code;
+    g.dcol[code] = (int)d;
+  }
+  if (present != (1 << kTileSlots) - 1) return g;    // the full 7-point stencil only
+  g.gpl = (int)(n0 / VW);
+  if (g.gpl > kThreads) return g;                    // one column group per thread
+  g.LPP = kThreads / g.gpl;                          // lines per pass of the CTA
+  g.BD = std::min(kThreads, (g.LPP * g.gpl + 31) / 32 * 32);
+  // accumulation order: one of the compiled permutations restricted to the slots this matrix has
+  g.order = -1;
+  for (int ord = 0; ord < kTileNumOrders && g.order < 0; ++ord) {
+    size_t d = 0;
+    for (int pos = 0; pos < kTileSlots; ++pos)
+      if ((present >> tile_order_slot(ord, pos)) & 1) {
+        if (d >= offs.size() || g.code[d] != tile_order_slot(ord, pos)) { d = offs.size() + 1; break; }
+        ++d;
+      }
+    if (d == offs.size()) g.order = ord;
+  }
+  if (g.order < 0) return g;
+  const int cap = kTileMinCtas * num_sms;            // resident CTAs
+  const size_t smem_budget = (size_t)(226 * 1024) / kTileMinCtas - 3 * 1024;      // per CTA, beside the static part
+  const size_t tab_bytes = 27 * kTileDiag * sizeof(T);
+  // choose the tile height: few re-read halo lines / planes, all CTA slots busy, at least 3 stages
+  double best = 1e300;
+  int bestTJ = 0, bestKC = 0, bestNS = 0;
+  const int tj_max = (int)std::min<i64>(n1, (i64)g.LPP * TileItems<T>::n);
+  for (int tj = 1; tj <= tj_max; ++tj) {
+    const int JT = (int)((n1 + tj - 1) / tj);
+    const int TJ = (int)((n1 + JT - 1) / JT);
+    if (TJ != tj) continue;                          // balanced heights only
+    const size_t stage = (size_t)(TJ + 2) * n0 * sizeof(T);
+    const int NS = (int)std::min<size_t>(kTileMaxStages, (smem_budget - tab_bytes) / stage);
+    if (NS < 3) continue;
+    int KC = (int)std::max<i64>(1, std::min<i64>(nloc, cap / JT));
+    if (KC > 1 && nloc / KC < 4) KC = (int)std::max<i64>(1, nloc / 4);        // at least ~4 planes per sweep
+    const double planes = (double)nloc / KC;
+    const double units = (double)JT * KC;
+    const double waves = std::ceil(units / cap);
+    // time model: a CTA moves (TJ + 2 halo) lines x (planes + 2 extra plane-tiles + ~3 plane-times of pipeline
+    // fill); CTAs of one wave run side by side; too few CTAs cannot keep the SMs busy; passes of the CTA that
+    // cover no line of the tile idle their threads.  (Measured at 512^3: TJ = 8 / 256 CTAs beats the evenly
+    // spread TJ = 7 / 296 CTAs, 326 vs 341 us — taller tiles re-read fewer halo lines.)
+    const double passes = std::ceil((double)TJ / g.LPP);
+    const double cost = waves * (TJ + 2.0) * (planes + 5.0) * std::max(1.0, 0.5 * cap / units) * (passes * g.LPP / TJ);
+    if (cost < best) { best = cost; bestTJ = TJ; bestKC = KC; bestNS = NS; }
+  }
+  if (!bestTJ) return g;
+  g.TJ = bestTJ;
+  g.JT = (int)((n1 + g.TJ - 1) / g.TJ);
+  g.KC = bestKC;
+  g.NS = bestNS;
+  g.nloc = (int)nloc;
+  g.kofs = (int)kofs;
+  g.n2g = (int)n[2];
+  g.has_lo = has_lo ? 1 : 0;
+  g.has_hi = has_hi ? 1 : 0;
+  g.stage_elems = (int)((g.TJ + 2) * n0);
+  g.grid = std::min(g.JT * g.KC, cap);
+  g.smem_bytes = (size_t)g.NS * g.stage_elems * sizeof(T) + tab_bytes;
+  g.ok = 1;
+  if (getenv("SIPB_TILE_DEBUG"))
+    fprintf(stderr, "[sipb200] tiled SpMV plan: grid %lldx%lldx%lld TJ=%d JT=%d KC=%d NS=%d BD=%d LPP=%d order=%d CTAs=%d smem=%zu\n",
+            (long long)n0, (long long)n1, (long long)nloc, g.TJ, g.JT, g.KC, g.NS, g.BD, g.LPP, g.order, g.grid, g.smem_bytes);
+  return g;
+}
+// the tiled kernels use more dynamic shared memory than the default limit: opt in once per instantiation
+template <typename K>
+static int tile_opt_in(K kernel, size_t bytes) {
+  static std::unordered_map<const void*, size_t> done;
+  auto it = done.find((const void*)kernel);
+  if (it != done.end() && it->second >= bytes) return SIPB_OK;
+  SIPB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+  done[(const void*)kernel] = 200 * 1024;
+  return SIPB_OK;
+}
+// launch k_spmv_tile<T, MODE, ARR, ORD> with the block size / dynamic shared memory of the geometry
+template <typename T, int MODE, bool ARR, int ORD>
+static int launch_tile_ord(sipb_ctx* c, int cls, const TileGeom& g, const SpmvArgs<T>& a, const TileInit<T>& ti,
+                           double* out_dot, const int* done_flag, CgState* st, const CommDev& cd) {
+  int rc = tile_opt_in(k_spmv_tile<T, MODE, ARR, ORD>, g.smem_bytes);
+  if (rc) return rc;
+  c->pre_launch(cls);
+  k_spmv_tile<T, MODE, ARR, ORD><<<g.grid, g.BD, g.smem_bytes, c->stream>>>(a, g, ti, c->rs, out_dot, done_flag, st, cd);
+  c->post_launch();
+  return SIPB_OK;
+}
+template <typename T, int MODE>
+static int launch_tile(sipb_ctx* c, int cls, const TileGeom& g, bool arrays, const SpmvArgs<T>& a, const TileInit<T>& ti,
+                       double* out_dot, const int* done_flag, CgState* st, const CommDev& cd) {
+  // the array form of the matrix has a tiled body for the plain product only (unit tests, micro-benchmark); the
+  // solver streams CDS arrays through the generic kernel, which is at the HBM roofline for them
+#define SIPB_TILE_CASE(ORD)                                                                              \
+  case ORD:                                                                                              \
+    if (arrays) {                                                                                        \
+      if constexpr (MODE == 1)                                                                           \
+        return launch_tile_ord<T, 1, true, ORD>(c, cls, g, a, ti, out_dot, done_flag, st, cd);           \
+      break;                                                                                             \
+    }                                                                                                    \
+    return launch_tile_ord<T, MODE, false, ORD>(c, cls, g, a, ti, out_dot, done_flag, st, cd);
+  switch (g.order) {
+    SIPB_TILE_CASE(0)
+    SIPB_TILE_CASE(1)
+    SIPB_TILE_CASE(2)
+    default: break;
+  }
+#undef SIPB_TILE_CASE
+  set_error("tiled SpMV: accumulation order without a compiled body");
+  return SIPB_E_STATE;
+}
+static_assert(kTileNumOrders == 3, "launch_tile dispatches three orders");
+
 // =============================================================================================
 // problem
 // =============================================================================================
@@ -740,6 +880,7 @@ struct Problem : sipb_problem {
   DevBuf<T> Q, x, x_old, rhs, r, pvec, Ap, m, tmp;
   DevBuf<T> Q_tab;            // [kMaxClasses][nq] stencil-class form of Q (replaces Q when q_classes)
   bool q_classes = false;
+  TileGeom tile;              // geometry of the tiled SpMV (tile.ok == 0: generic kernel)
   YlMultiArgs<T> yl_multi;    // argument block of the multi-set y/l launch (rebuilt every iteration)
   i64 maxM = 0;
   bool m_resident = false;
@@ -792,6 +933,7 @@ struct Problem : sipb_problem {
 
   Problem(sipb_ctx* c, int dt, int nd_, const int64_t* n_, const double* h_, bool mk, bool fo) {
     ctx = c; dtype = dt; ndim = nd_; minkowski = mk; feas_only = fo;
+    memset(&tile, 0, sizeof(tile));
     for (int a = 0; a < 3; ++a) { n[a] = (a < nd_) ? n_[a] : 1; h[a] = (a < nd_) ? h_[a] : 1.0; }
     npts = n[0] * n[1] * n[2];
     Nglob = mk ? 2 * npts : npts;
@@ -986,6 +1128,8 @@ struct Problem : sipb_problem {
       for (int64_t o : q_offs)
         SIPB_REQUIRE(std::llabs((long long)o) <= sg.plane, SIPB_E_UNSUPPORTED, "CDS offset wider than one halo plane");
     { int rc = setup_peer_p(); if (rc) return rc; }
+    tile = plan_tile<T>(ndim, n, minkowski, q_offs, sg.on ? sg.nloc() : n[2], sg.on ? sg.k0 : 0, sg.on && sg.has_lo,
+                        sg.on && sg.has_hi, ctx->num_sms);
     finalized = true;
     return SIPB_OK;
   }
@@ -1345,7 +1489,13 @@ struct Problem : sipb_problem {
     // (k_cg_init measured faster with two waves than with one: 2.03 vs 2.68 ms per solve at 200^3)
     const int g_init = c->grid_for(nvecN), g_mv = c->grid_fit((const void*)k_spmv<T, true>, nvecN),
               g_xr = c->grid_fit((const void*)k_cg_xr<T>, nvecN), g_p = c->grid_fit((const void*)k_cg_p<T>, nvecN);
-    LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+    if (tile.ok && q_classes) {
+      const TileInit<T> ti{b, r.p, pp, x_old_out};
+      if ((rc = launch_tile<T, 2>(c, KC_CG_INIT, tile, !q_classes, spmv_args(xv, nullptr), ti, nullptr, nullptr, c->d_cg, cd)))
+        return rc;
+    } else {
+      LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+    }
     const double vecN = (double)N * sizeof(T);
     const double q_rows = q_classes ? 0.0 : (double)q_offs.size();       // matrix words streamed per row
     c->account(KC_CG_INIT, (q_rows + 4 + (x_old_out ? 1 : 0)) * vecN);   // Q, x, b -> r, p (, x_old)
@@ -1356,7 +1506,14 @@ struct Problem : sipb_problem {
     for (;;) {
       for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
         if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
-        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g_mv, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
+        if (tile.ok && q_classes) {
+          const TileInit<T> ti{nullptr, nullptr, nullptr, nullptr};
+          if ((rc = launch_tile<T, 1>(c, KC_SPMV_DOT, tile, false, spmv_args_peer(Ap.p), ti, &c->d_cg->pAp,
+                                      (const int*)&c->d_cg->done, c->d_cg, cd)))
+            return rc;
+        } else {
+          LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g_mv, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
+        }
         if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;      // peer path: collected inside k_cg_xr
         LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g_xr, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
         if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;   // peer path: collected inside k_cg_p
@@ -2382,9 +2539,44 @@ static int cds_scaled_add_impl(sipb_ctx* c, int64_t N, int nd_a, void* A, const 
   return SIPB_OK;
 }
 
+// y = A x for a CDS matrix on a 3-D grid through the tiled kernel when the geometry allows (unit tests of
+// spmv_tile.cuh: arbitrary values on the 7 stencil diagonals, including the entries that wrap around line / plane ends)
+template <typename T>
+static int cds_spmv_grid_impl(sipb_ctx* c, const int64_t* n, int nd, const void* R, const int64_t* offs, const void* x,
+                              void* y, int* used_tiled) {
+  const i64 N = n[0] * n[1] * n[2];
+  const i64 ld = (N + 63) / 64 * 64;
+  DevBuf<T> dR, dx, dy;
+  int rc = upload_cds<T>(c, N, nd, R, ld, dR);
+  if (rc) return rc;
+  SIPB_CUDA_CHECK(dx.alloc((size_t)N));
+  SIPB_CUDA_CHECK(dy.alloc((size_t)N));
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(dx.p, x, N * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+  SpmvArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  a.R = dR.p; a.ld = ld; a.nd = nd;
+  for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
+  a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
+  a.gn[0] = (unsigned)n[0]; a.gn[1] = (unsigned)n[1]; a.gn[2] = (unsigned)n[2]; a.npts = (unsigned)N;
+  const TileGeom tg = plan_tile<T>(3, n, false, std::vector<int64_t>(offs, offs + nd), n[2], 0, false, false, c->num_sms);
+  *used_tiled = tg.ok;
+  if (tg.ok) {
+    const TileInit<T> ti{nullptr, nullptr, nullptr, nullptr};
+    rc = launch_tile<T, 1>(c, KC_SPMV, tg, true, a, ti, nullptr, nullptr, nullptr, c->cd_off);
+    if (rc) return rc;
+  } else {
+    LAUNCH(c, KC_SPMV, (k_spmv<T, false>), c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W), a, c->rs, (double*)nullptr,
+           (const int*)nullptr, c->cd_off);
+  }
+  SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemcpyAsync(y, dy.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  return SIPB_OK;
+}
+
 template <typename T>
 static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, int reps, int flush_l2, double* avg_ms,
-                           int64_t* alg_bytes) {
+                           int64_t* alg_bytes, int form, int tiled) {
   const i64 N = n[0] * n[1] * (ndim == 3 ? n[2] : 1);
   const i64 ld = (N + 63) / 64 * 64;
   std::vector<int64_t> offs;
@@ -2394,20 +2586,33 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   offs.push_back(-n[0]); offs.push_back(-1); offs.push_back(1); offs.push_back(n[0]);
   if (ndim == 3) offs.push_back(n[0] * n[1]);
   const int nd = (int)offs.size();
-  DevBuf<T> dR, dx, dy, flush;
-  SIPB_CUDA_CHECK(dR.alloc((size_t)ld * nd));
+  DevBuf<T> dR, dx, dy, flush, dtab;
+  if (form == 1) {
+    // stencil-class form: one row per class, the matrix is not streamed
+    std::vector<T> tab((size_t)kMaxClasses * nd, (T)0.25);
+    SIPB_CUDA_CHECK(dtab.alloc(tab.size()));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(dtab.p, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+  }
+  SIPB_CUDA_CHECK(dR.alloc(form == 1 ? 64 : (size_t)ld * nd));
   SIPB_CUDA_CHECK(dx.alloc((size_t)N));
   SIPB_CUDA_CHECK(dy.alloc((size_t)N));
   const size_t flush_elems = (size_t)(256u << 20) / sizeof(T);
   if (flush_l2) SIPB_CUDA_CHECK(flush.alloc(flush_elems));
-  LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), (i64)ld * nd, dR.p, (T)0.25);
+  if (form != 1) LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), (i64)ld * nd, dR.p, (T)0.25);
   LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), N, dx.p, (T)1.5);
-  SpmvArgs<T> a;
-  a.R = dR.p; a.ld = ld; a.nd = nd;
-  for (int j = 0; j < nd; ++j) a.off[j] = offs[j];
-  a.N = N; a.row0 = 0; a.Nglob = N; a.x = dx.p; a.y = dy.p;
-  a.x_lo = nullptr; a.x_hi = nullptr; a.n_lo = 0; a.tab = nullptr; a.fast = 0;
-  const int g = c->grid_for((N + Vec<T>::W - 1) / Vec<T>::W);
+  // the argument block of a throw-away problem gives the class-form constants of the generic kernel too
+  Problem<T> PB(c, sizeof(T) == 4 ? SIPB_F32 : SIPB_F64, ndim, n, std::vector<double>{1, 1, 1}.data(), false, true);
+  PB.q_offs = offs;
+  PB.q_classes = form == 1;
+  SpmvArgs<T> a = PB.spmv_args(dx.p, dy.p);
+  a.R = dR.p; a.ld = ld;
+  a.tab = form == 1 ? dtab.p : nullptr;
+  TileGeom tg;
+  memset(&tg, 0, sizeof(tg));
+  if (tiled) tg = plan_tile<T>(ndim, n, false, offs, ndim == 3 ? n[2] : 1, 0, false, false, c->num_sms);
+  SIPB_REQUIRE(!tiled || tg.ok, SIPB_E_UNSUPPORTED, "the tiled SpMV does not handle this grid");
+  const int g = c->grid_fit((const void*)k_spmv<T, true>, (N + Vec<T>::W - 1) / Vec<T>::W);
   cudaEvent_t e0, e1;
   SIPB_CUDA_CHECK(cudaEventCreate(&e0));
   SIPB_CUDA_CHECK(cudaEventCreate(&e1));
@@ -2415,7 +2620,13 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   for (int it = 0; it < warmup + reps; ++it) {
     if (flush_l2) LAUNCH(c, KC_FILL, k_fill<T>, c->max_grid(), (i64)flush_elems, flush.p, (T)it);
     SIPB_CUDA_CHECK(cudaEventRecord(e0, c->stream));
-    LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, a, c->rs, c->d_scal, (const int*)nullptr, c->cd_off);
+    if (tg.ok) {
+      const TileInit<T> ti{nullptr, nullptr, nullptr, nullptr};
+      int rc = launch_tile<T, 1>(c, KC_SPMV_DOT, tg, form != 1, a, ti, c->d_scal, nullptr, nullptr, c->cd_off);
+      if (rc) return rc;
+    } else {
+      LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g, a, c->rs, c->d_scal, (const int*)nullptr, c->cd_off);
+    }
     SIPB_CUDA_CHECK(cudaEventRecord(e1, c->stream));
     SIPB_CUDA_CHECK(cudaEventSynchronize(e1));
     float ms = 0.f;
@@ -2425,8 +2636,10 @@ static int bench_spmv_impl(sipb_ctx* c, int ndim, const int64_t* n, int warmup, 
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   SIPB_CUDA_CHECK(cudaGetLastError());
+  SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_scal, 0, sizeof(double), c->stream));
+  SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   *avg_ms = total / std::max(1, reps);
-  *alg_bytes = (int64_t)(nd + 2) * N * (int64_t)sizeof(T);
+  *alg_bytes = (int64_t)((form == 1 ? 0 : nd) + 2) * N * (int64_t)sizeof(T);
   return SIPB_OK;
 }
 
@@ -2490,7 +2703,22 @@ int sipb_bench_spmv(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, int wa
                     double* avg_ms, int64_t* algorithmic_bytes) {
   SIPB_REQUIRE(ctx && n && avg_ms && algorithmic_bytes, SIPB_E_INVALID, "null argument");
   SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
-  DISPATCH(dtype, bench_spmv_impl, ctx, ndim, n, warmup, reps, flush_l2, avg_ms, algorithmic_bytes);
+  DISPATCH(dtype, bench_spmv_impl, ctx, ndim, n, warmup, reps, flush_l2, avg_ms, algorithmic_bytes, 0, 0);
+}
+int sipb_bench_spmv2(sipb_ctx* ctx, int dtype, int ndim, const int64_t* n, int warmup, int reps, int flush_l2, int form,
+                     int tiled, double* avg_ms, int64_t* algorithmic_bytes) {
+  SIPB_REQUIRE(ctx && n && avg_ms && algorithmic_bytes, SIPB_E_INVALID, "null argument");
+  SIPB_REQUIRE(form == 0 || form == 1, SIPB_E_INVALID, "form must be 0 (CDS arrays) or 1 (stencil classes)");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, bench_spmv_impl, ctx, ndim, n, warmup, reps, flush_l2, avg_ms, algorithmic_bytes, form, tiled);
+}
+int sipb_cds_spmv_grid(sipb_ctx* ctx, int dtype, const int64_t* n, int nd, const void* R, const int64_t* offsets,
+                       const void* x, void* y, int* used_tiled) {
+  SIPB_REQUIRE(ctx && n && R && offsets && x && y && used_tiled, SIPB_E_INVALID, "null argument");
+  SIPB_REQUIRE(nd >= 1 && nd <= kMaxDiag, SIPB_E_UNSUPPORTED, "number of diagonals outside [1,32]");
+  SIPB_REQUIRE(n[0] >= 2 && n[1] >= 2 && n[2] >= 2, SIPB_E_INVALID, "grid dimensions must be >= 2");
+  SIPB_CUDA_CHECK(cudaSetDevice(ctx->device));
+  DISPATCH(dtype, cds_spmv_grid_impl, ctx, n, nd, R, offsets, x, y, used_tiled);
 }
 
 }  // extern "C"

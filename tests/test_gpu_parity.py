@@ -79,6 +79,56 @@ def test_cds_spmv_bit_exact(sip, orc, TF, n):
     assert np.allclose(got, native, rtol=0, atol=10 * np.finfo(TF).eps * np.abs(native).max())
 
 
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+@pytest.mark.parametrize("n,order", [((8, 6, 5), "q"), ((24, 20, 17), "q"), ((40, 28, 20), "z"), ((64, 50, 9), "sorted"),
+                                     ((200, 37, 12), "q"), ((512, 9, 4), "z"), ((4, 3, 2), "q"), ((256, 5, 3), "q")])
+def test_cds_spmv_tiled_bit_exact(sip, orc, TF, n, order):
+    """The tiled, TMA-staged plane-sweep SpMV (spmv_tile.cuh) against CDS_MVp (CDS_MVp.jl:9-28): random values on
+    all seven stencil diagonals — INCLUDING the entries that wrap around line and plane ends, which a general CDS
+    matrix may hold — in three accumulation orders; results must be bit-identical."""
+    import ctypes as C
+    L = sip._lib
+    n0, n1, n2 = n
+    N, P = n0 * n1 * n2, n0 * n1
+    off = {"q": [0, -P, -n0, -1, 1, n0, P], "z": [0, -P, P, -1, 1, -n0, n0], "sorted": [-P, -n0, -1, 0, 1, n0, P]}[order]
+    off = np.array(off, dtype=np.int64)
+    rng = np.random.default_rng(11)
+    R = np.asfortranarray(rng.standard_normal((N, off.size)).astype(TF))
+    x = rng.standard_normal(N).astype(TF)
+    want = orc.ops.CDS_MVp(N, off.size, R, off, x, np.zeros(N, dtype=TF))
+    got = np.empty(N, dtype=TF)
+    used = C.c_int(0)
+    n3 = (C.c_int64 * 3)(*n)
+    L.check(L.load().sipb_cds_spmv_grid(L.ctx(), L.dtype_code(TF), n3, off.size, R.ctypes.data,
+                                        off.ctypes.data_as(C.POINTER(C.c_int64)), x.ctypes.data, got.ctypes.data, C.byref(used)))
+    assert used.value == 1            # these grids are inside the tiled kernel's domain
+    assert np.array_equal(got, want)
+    # a subset of the diagonals (a D_x-only Q) is outside the tiled kernel's domain (full 7-point stencils): generic kernel
+    sub = np.array([0, -1, 1], dtype=np.int64)
+    Rs = np.asfortranarray(R[:, [0, 3, 4]]) if order == "q" else np.asfortranarray(R[:, :3])
+    want = orc.ops.CDS_MVp(N, 3, Rs, sub, x, np.zeros(N, dtype=TF))
+    L.check(L.load().sipb_cds_spmv_grid(L.ctx(), L.dtype_code(TF), n3, 3, Rs.ctypes.data,
+                                        sub.ctypes.data_as(C.POINTER(C.c_int64)), x.ctypes.data, got.ctypes.data, C.byref(used)))
+    assert used.value == 0 and np.array_equal(got, want)
+
+
+def test_cds_spmv_grid_falls_back_outside_tile_domain(sip, orc):
+    import ctypes as C
+    L = sip._lib
+    n = (13, 11, 7)
+    N, P = 13 * 11 * 7, 13 * 11
+    off = np.array([0, -P, -13, -1, 1, 13, P], dtype=np.int64)
+    rng = np.random.default_rng(12)
+    R = np.asfortranarray(rng.standard_normal((N, 7)).astype(np.float32))
+    x = rng.standard_normal(N).astype(np.float32)
+    got = np.empty(N, dtype=np.float32)
+    used = C.c_int(1)
+    L.check(L.load().sipb_cds_spmv_grid(L.ctx(), 0, (C.c_int64 * 3)(*n), 7, R.ctypes.data,
+                                        off.ctypes.data_as(C.POINTER(C.c_int64)), x.ctypes.data, got.ctypes.data, C.byref(used)))
+    assert used.value == 0
+    assert np.array_equal(got, orc.ops.CDS_MVp(N, 7, R, off, x, np.zeros(N, dtype=np.float32)))
+
+
 def test_cds_spmv_random_offsets(sip, orc):
     """random banded matrix (test_CDS_Mvp.jl:13-22 second half), Float64."""
     import scipy.sparse as sp
