@@ -149,7 +149,9 @@ typedef struct sipb_log {
   double* gamma;                /* [maxit][p]  */
   int32_t* cg_it;               /* [maxit]     */
   double* cg_relres;
-  double  phase_seconds[SIPB_N_PHASES];   /* host wall time per TimerOutputs section, same order   */
+  double  phase_seconds[SIPB_N_PHASES];   /* DEVICE time per TimerOutputs section, same order: CUDA events on the
+                                             solver's stream close every phase (the stopping-rule and adaptation
+                                             sections are host scalar work: their entries hold the device idle gap) */
   double  solve_seconds;                  /* whole sipb_solve call incl. H2D/D2H                    */
   double  device_seconds;                 /* CUDA-event time of the whole solve on the stream, after the
                                              H2D of m is enqueued and before the D2H of x                 */
@@ -205,6 +207,13 @@ int sipb_problem_add_set(sipb_problem* pb, const sipb_set_desc* desc);
  * [rows x nd] host TF, offsets int64[nd] ascending. */
 int sipb_problem_set_ata(sipb_problem* pb, int set_index, const void* R, int64_t rows,
                          const int64_t* offsets, int nd);
+/* AtA[i] as one row per stencil class instead of the [rows x nd] array: tab is host TF[54][nd], tab[cls*nd + j] =
+ * AtA[r, r + offsets[j]] for any row r of class cls = ((half*3 + c(k))*3 + c(j))*3 + c(i), c = 0 / 1 / 2 for the
+ * first / an interior / the last index of the axis (half = second Minkowski half).  Every A'A the reference builds
+ * from get_TD_operator.jl has this structure; passing the table skips forming, uploading and verifying the array
+ * (PARSDMM_precompute_distribute.jl:44-55 costs 8 GB and ~7 s at 512^3).  All sets of a problem must then come as
+ * tables (a problem with a custom sparse operator uses sipb_problem_set_ata for every set). */
+int sipb_problem_set_ata_classes(sipb_problem* pb, int set_index, const void* tab, const int64_t* offsets, int nd);
 /* uploads, builds Q_offsets in the reference's order (PARSDMM_initialize.jl:217-221). */
 int sipb_problem_finalize(sipb_problem* pb);
 int sipb_problem_num_q_offsets(sipb_problem* pb, int* nd);

@@ -95,6 +95,7 @@ SYMBOLS = [
     ("sipb_problem_create", _I, [_VP, _I, _I, _PI64, _PD, _I, _I, C.POINTER(_VP)]),
     ("sipb_problem_add_set", _I, [_VP, C.POINTER(SetDesc)]),
     ("sipb_problem_set_ata", _I, [_VP, _I, _VP, _I64, _PI64, _I]),
+    ("sipb_problem_set_ata_classes", _I, [_VP, _I, _VP, _PI64, _I]),
     ("sipb_problem_finalize", _I, [_VP]),
     ("sipb_problem_num_q_offsets", _I, [_VP, _PI]),
     ("sipb_problem_q_form", _I, [_VP, _PI]),

@@ -200,6 +200,7 @@ struct sipb_ctx {
   struct EvPair { cudaEvent_t a, b; int cls; };
   std::vector<EvPair> ev_used;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<std::pair<cudaEvent_t, int>> phase_events;      // (event, phase it closes), reused by every solve
   // algorithmic bytes of the launches of a class: every array the kernel has to read or write counted once
   // (perfect reuse of gathered vectors), the numerator of the roofline in bench.py / DESIGN.md
   void account(int cls, double nbytes) { bytes[cls] += nbytes; }
@@ -831,6 +832,7 @@ struct sipb_problem {
   virtual ~sipb_problem() {}
   virtual int add_set(const sipb_set_desc* d) = 0;
   virtual int set_ata(int idx, const void* R, int64_t rows, const int64_t* offs, int nd) = 0;
+  virtual int set_ata_classes(int idx, const void* tab, const int64_t* offs, int nd) = 0;
   virtual int finalize() = 0;
   virtual int solve(const void* m, void* x, void* const* l, void* const* y, const sipb_options* o, sipb_log* log) = 0;
   virtual int q_offsets(std::vector<int64_t>& out) = 0;
@@ -861,6 +863,7 @@ struct SetT {
   std::vector<int64_t> offs;
   std::vector<int> qcol;      // column of Q for each diagonal of AtA
   bool has_ata = false;
+  bool tab_direct = false;    // ata_tab came from the host (sipb_problem_set_ata_classes): nothing to extract / verify
   DevBuf<ProjParams<T>> pp_y, pp_f;   // dynamic projector parameters: y-update / feasibility
   DevBuf<double> warm;        // [2] warm-start thresholds (y-update, feasibility)
   bool z_halo = false;        // slabs: y, l, y_old have a halo plane in front (D_z block)
@@ -1085,6 +1088,24 @@ struct Problem : sipb_problem {
     return SIPB_OK;
   }
 
+  int set_ata_classes(int idx, const void* tab, const int64_t* offs, int nd) override {
+    SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
+    SIPB_REQUIRE(idx >= 0 && idx < (int)sets.size(), SIPB_E_INVALID, "set index out of range");
+    SIPB_REQUIRE(nd >= 1 && nd <= kMaxDiag, SIPB_E_UNSUPPORTED, "number of diagonals outside [1,32]");
+    SIPB_REQUIRE(n[0] * n[1] * n[2] < ((i64)1 << 31) && !(minkowski && sg.on), SIPB_E_UNSUPPORTED,
+                 "stencil-class tables need fewer than 2^31 grid points");
+    SetT<T>& S = *sets[idx];
+    SIPB_REQUIRE(!S.is_sparse, SIPB_E_INVALID, "custom sparse operators come as CDS arrays (sipb_problem_set_ata)");
+    SIPB_CUDA_CHECK(S.ata_tab.alloc((size_t)kMaxClasses * nd));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(S.ata_tab.p, tab, (size_t)kMaxClasses * nd * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    S.nd = nd;
+    S.offs.assign(offs, offs + nd);
+    S.has_ata = true;
+    S.tab_direct = true;
+    return SIPB_OK;
+  }
+
   int finalize() override {
     SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
     SIPB_REQUIRE(!sets.empty(), SIPB_E_INVALID, "no sets");
@@ -1153,6 +1174,16 @@ struct Problem : sipb_problem {
     if (n[0] * n[1] * n[2] >= ((i64)1 << 31)) ok = 0;
     if (minkowski && sg.on) ok = 0;
     sipb_ctx* c = ctx;
+    bool any_direct = false, all_direct = true;
+    for (auto& S : sets) { any_direct = any_direct || S->tab_direct; all_direct = all_direct && S->tab_direct; }
+    if (any_direct) {
+      // class tables handed over by the host: there is no array to fall back to
+      SIPB_REQUIRE(ok, SIPB_E_STATE, "stencil-class tables were passed although SIPB_Q_CLASSES=0 asks for CDS arrays");
+      SIPB_REQUIRE(all_direct, SIPB_E_STATE,
+                   "either every AtA comes as a stencil-class table or every AtA comes as a CDS array");
+      q_classes = true;
+      return SIPB_OK;
+    }
     if (ok) {
       int* d_bad = (int*)c->d_counter2;
       SIPB_CUDA_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream));
@@ -1628,8 +1659,30 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   log->p = p; log->pp = pp; log->iters = 0; log->feas_rows = 1; log->stopped_feasible = 0;
   log->h2d_bytes = 0; log->d2h_bytes = 0;
   for (int q = 0; q < SIPB_N_PHASES; ++q) log->phase_seconds[q] = 0.0;
-  double t_phase = now_s();
-  auto phase_end = [&](int ph) { const double t = now_s(); log->phase_seconds[ph] += t - t_phase; t_phase = t; };
+  // Phase times as TimerOutputs reports them (PARSDMM.jl:100,105,113,152,163,229): a CUDA event closes every phase
+  // on the solver's stream; the elapsed device time between consecutive events is billed to the phase that ended
+  // (host wall clock would bill the execution of asynchronously launched kernels to whichever phase synchronises).
+  std::vector<std::pair<cudaEvent_t, int>>& pev = c->phase_events;
+  size_t pev_used = 0;
+  auto phase_mark = [&](int ph) {
+    if (pev_used == pev.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      pev.push_back({e, ph});
+    }
+    pev[pev_used].second = ph;
+    cudaEventRecord(pev[pev_used].first, c->stream);
+    ++pev_used;
+  };
+  auto phase_end = [&](int ph) { phase_mark(ph); };
+  auto phase_collect = [&]() {
+    for (size_t q = 1; q < pev_used; ++q) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pev[q - 1].first, pev[q].first) == cudaSuccess)
+        log->phase_seconds[pev[q].second] += 1e-3 * (double)ms;
+    }
+  };
+  phase_mark(0);
 
   // ---------------- initialization (PARSDMM_initialize.jl) ------------------------------------
   const T feas_tol = (T)o->feas_tol, obj_tol = (T)o->obj_tol, evol_rel_tol = (T)o->evol_rel_tol;
@@ -1703,6 +1756,8 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
       log->kernel_bytes[q] = c->bytes[q];
     }
     phase_end(0);
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    phase_collect();
     log->solve_seconds = now_s() - t_begin;
     log->device_seconds = 0.0;
     return SIPB_OK;
@@ -2067,6 +2122,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   cudaEventDestroy(ev0);
   cudaEventDestroy(ev1);
   log->device_seconds = ms * 1e-3;
+  phase_collect();
   log->iters = iters_done;
   log->feas_rows = counter;       // output_check_PARSDMM keeps set_feasibility[1:counter,:]
   c->collect_profile();
@@ -2144,6 +2200,7 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   for (auto& e : c->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : c->phase_events) cudaEventDestroy(e.first);
   cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->rs_multi.partials); cudaFree(c->rs_multi.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_l1); cudaFreeHost(c->h_l1);
   cudaFree(c->d_sel); cudaFree(c->d_tie_counts);
@@ -2309,6 +2366,11 @@ int sipb_problem_add_set(sipb_problem* pb, const sipb_set_desc* d) {
 int sipb_problem_set_ata(sipb_problem* pb, int idx, const void* R, int64_t rows, const int64_t* offs, int nd) {
   SIPB_REQUIRE(pb && R && offs, SIPB_E_INVALID, "null argument");
   return pb->set_ata(idx, R, rows, offs, nd);
+}
+int sipb_problem_set_ata_classes(sipb_problem* pb, int idx, const void* tab, const int64_t* offs, int nd) {
+  SIPB_REQUIRE(pb && tab && offs, SIPB_E_INVALID, "null argument");
+  SIPB_CUDA_CHECK(cudaSetDevice(pb->ctx->device));
+  return pb->set_ata_classes(idx, tab, offs, nd);
 }
 int sipb_problem_finalize(sipb_problem* pb) {
   SIPB_REQUIRE(pb, SIPB_E_INVALID, "null argument");

@@ -182,6 +182,53 @@ class TDOperator:
             return R, offs
         return _minkowski_cds(R, offs, self.block_mode)
 
+    # -- A'A as one row per stencil class (what the device keeps; no N x nd array is formed) ----------
+    def ata_class_table(self):
+        """(tab, offsets): offsets == ata_cds()[1]; tab[cls, j] = (A'A)[r, r + offsets[j]] for any row r of stencil
+        class cls = ((half*3 + class(k))*3 + class(j))*3 + class(i), class = 0 first / 1 interior / 2 last index of
+        the axis (54 classes; `half` = second Minkowski half).  None when the grid has an axis shorter than 3.
+
+        Every A'A of get_TD_operator.jl holds one value per class and diagonal, so the table is read off the CDS form
+        of the same operator on a 3 x 3 (x 3) grid, where row index and class coincide; a diagonal of the small
+        matrix maps back through the balanced-ternary digits of its offset (strides 1, 3, 9 and the half size)."""
+        if min(self.n) < 3:
+            return None
+        small = TDOperator(self.kind, (3,) * self.ndim, self.h, self.TF, self.block_mode)
+        Rs, offs_s = small.ata_cds()
+        ns = 3 ** self.ndim                                   # rows per half of the small problem
+        strides_s = [1, 3, 9][: self.ndim] + [ns]
+        strides = [1, self.n[0], self.n[0] * self.n[1]][: self.ndim] + [self.npts]
+        offs = []
+        for o in offs_s:
+            rest, real = int(o), 0
+            for st_s, st in zip(reversed(strides_s), reversed(strides)):      # most significant digit first
+                d = int(np.rint(rest / st_s))
+                if abs(d) > 1:
+                    return None
+                rest -= d * st_s
+                real += d * st
+            if rest != 0:
+                return None
+            offs.append(real)
+        offs = np.array(offs, dtype=np.int64)
+        order = np.argsort(offs, kind="stable")
+        if np.unique(offs).size != offs.size:
+            return None
+        tab = np.zeros((54, offs.size), dtype=self.TF)
+        nhalf = 1 if self.block_mode == _lib.BLOCK_PLAIN else 2
+        for half in range(nhalf):
+            for c in range(ns):
+                digits = [(c // 3 ** a) % 3 for a in range(self.ndim)]         # (i, j[, k]) == per-axis classes
+                ci, cj = digits[0], digits[1]
+                ck = digits[2] if self.ndim == 3 else 0                        # 2-D: a single plane, class "first"
+                if self.ndim == 2:
+                    # the device decodes rows of a 2-D grid as (i, j, k) with n = (n0, n1, 1): j is the middle axis
+                    cls = ((half * 3 + 0) * 3 + cj) * 3 + ci
+                else:
+                    cls = ((half * 3 + ck) * 3 + cj) * 3 + ci
+                tab[cls, :] = Rs[half * ns + c, :][order]
+        return np.ascontiguousarray(tab), offs[order]
+
     def _ata_cds_plain(self, zrange=None):
         TF, n = self.TF, self.n
         lo, hi = 0, self.npts

@@ -18,9 +18,56 @@ from .operators import SparseOperator, TDOperator
 
 class CDSList(list):
     """Vector{Array{TF,2}} of CDS matrices; carries the cached device problem built from it.
-    `slab` = (k0, k1) when the matrices hold only this rank's rows (multi-GPU slabs)."""
+    `slab` = (k0, k1) when the matrices hold only this rank's rows (multi-GPU slabs).
+
+    Entries of stencil operators are LAZY: the device keeps one row per stencil class of every A'A
+    (`TDOperator.ata_class_table`), so the N x nd array of the reference is only formed when the caller indexes the
+    list (`AtA[i]`, iteration) — e.g. to inspect or modify it; once any entry has been formed the arrays are what
+    gets uploaded (they may have been changed)."""
     _device = None
     slab = None
+
+    def __init__(self):
+        super().__init__()
+        self._lazy = {}          # index -> (operator, zrange)
+
+    def append_lazy(self, op, zrange):
+        self._lazy[len(self)] = (op, zrange)
+        super().append(None)
+
+    def materialized(self) -> bool:
+        """True when some lazy entry has been formed (or there are none): the arrays are then authoritative."""
+        return any(super(CDSList, self).__getitem__(i) is not None for i in self._lazy)
+
+    def is_lazy(self, i) -> bool:
+        return i in self._lazy and super().__getitem__(i) is None
+
+    def class_table(self, i):
+        op, _ = self._lazy[i]
+        return op.ata_class_table()
+
+    def _form(self, i):
+        v = super().__getitem__(i)
+        if v is None and i in self._lazy:
+            op, zr = self._lazy[i]
+            v = op.ata_cds(zr)[0]
+            super().__setitem__(i, v)
+        return v
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._form(k) for k in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self._form(i)
+
+    def __iter__(self):
+        return (self._form(i) for i in range(len(self)))
+
+
+def _classes_enabled() -> bool:
+    import os
+    return os.environ.get("SIPB_Q_CLASSES", "1") != "0"
 
 
 def _require_device_operators(TD_OP):
@@ -67,6 +114,11 @@ def PARSDMM_precompute_distribute(TD_OP, set_Prop, comp_grid, options):
             if offs.size > 32:
                 raise NotImplementedError("A'A of the custom operator has %d diagonals; the device path handles 32" % offs.size)
         else:
+            ct = TD_OP[i].ata_class_table() if _classes_enabled() else None
+            if ct is not None:       # == mat2CDS(TD_OP[i]'*TD_OP[i]), formed only when somebody indexes AtA[i]
+                AtA.append_lazy(TD_OP[i], zrange)
+                set_Prop.AtA_offsets[i] = ct[1]
+                continue
             R, offs = TD_OP[i].ata_cds(zrange)    # == mat2CDS(TD_OP[i]'*TD_OP[i]) (identity when AtA_diag)
         AtA.append(R)
         set_Prop.AtA_offsets[i] = offs
@@ -113,6 +165,11 @@ def PARSDMM_precompute_distribute_Minkowski(TD_OP_c1, TD_OP_c2, TD_OP_sum, set_P
     s = len(TD_OP)
     AtA = CDSList()
     for i in range(s):
+        ct = TD_OP[i].ata_class_table() if _classes_enabled() and not isinstance(TD_OP[i], SparseOperator) else None
+        if ct is not None:
+            AtA.append_lazy(TD_OP[i], None)
+            set_Prop.AtA_offsets[i] = ct[1]
+            continue
         R, offs = TD_OP[i].ata_cds()
         AtA.append(R)
         set_Prop.AtA_offsets[i] = offs

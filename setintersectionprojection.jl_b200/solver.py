@@ -7,6 +7,7 @@ The whole iteration runs on the GPU inside `sipb_solve`; this file only marshals
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
@@ -73,6 +74,9 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
     handle = C.c_void_p()
     _lib.check(lib.sipb_problem_create(_lib.ctx(), _lib.dtype_code(TF), op0.ndim, n, h, int(bool(options.Minkowski)),
                                        int(bool(options.feasibility_only)), C.byref(handle)))
+    # one row per stencil class instead of the N x nd arrays, unless the caller formed (and maybe changed) an array
+    use_tables = (hasattr(AtA, "is_lazy") and all(AtA.is_lazy(i) for i in range(p)) and not AtA.materialized()
+                  and os.environ.get("SIPB_Q_CLASSES", "1") != "0")
     try:
         for i in range(p):
             keep = None
@@ -89,6 +93,13 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
                     raise NotImplementedError("custom operators are single-GPU (no slab decomposition)")
                 d.sparse = C.pointer(TD_OP[i].sparse_struct())
             _lib.check(lib.sipb_problem_add_set(handle, C.byref(d)))
+            if use_tables:
+                tab, offs = AtA.class_table(i)
+                offs = np.ascontiguousarray(offs, dtype=np.int64)
+                tab = np.ascontiguousarray(tab, dtype=TF)
+                _lib.check(lib.sipb_problem_set_ata_classes(handle, i, tab.ctypes.data,
+                                                            offs.ctypes.data_as(C.POINTER(C.c_int64)), offs.size))
+                continue
             R = AtA[i]
             if slab is not None and getattr(AtA, "slab", None) is None:       # global CDS given: keep this rank's rows
                 plane = op0.n[0] * op0.n[1]

@@ -288,3 +288,46 @@ def test_custom_sparse_operator_host_side(sip, TF):
         sip.PARSDMM_precompute_distribute(TD_OP, sP, sip.compgrid(d, n), sip.PARSDMM_options())
     with pytest.raises(ValueError):
         sip.SparseOperator(W[:, :-1], n, d, TF)
+
+
+def test_ata_class_table_equals_cds_rows():
+    """TDOperator.ata_class_table (what the device keeps instead of the N x nd array of mat2CDS(A'A),
+    PARSDMM_precompute_distribute.jl:44-55): same offsets, and every row of the CDS array equals — bit for bit — the
+    table row of its stencil class, for every operator kind, 2-D / 3-D, and the three Minkowski block placements."""
+    import sip_b200  # noqa: F401
+    from sip_b200 import _lib as lib, operators as ops
+
+    def row_class(r, n, npts):
+        half = 1 if r >= npts else 0
+        c = r - half * npts
+        n3 = list(n) + [1] * (3 - len(n))
+        i, q = c % n3[0], c // n3[0]
+        j, k = q % n3[1], q // n3[1]
+        ac = lambda idx, nn: 0 if idx == 0 else (2 if idx == nn - 1 else 1)      # noqa: E731
+        return ((half * 3 + ac(k, n3[2])) * 3 + ac(j, n3[1])) * 3 + ac(i, n3[0])
+
+    for TF in (np.float32, np.float64):
+        for n, h in (((7, 5), (25.0, 6.0)), ((5, 4, 6), (25.0, 12.5, 6.0)), ((3, 3, 3), (1.0, 2.0, 3.0)), ((3, 9), (2.0, 3.0))):
+            for kind in ["identity", "D_x", "D_z", "TV"] + (["D_y"] if len(n) == 3 else ["D_xz"]):
+                for bm in (lib.BLOCK_PLAIN, lib.BLOCK_LEFT, lib.BLOCK_RIGHT, lib.BLOCK_BOTH):
+                    op = ops.TDOperator(kind, n, h, TF, bm)
+                    R, offs = op.ata_cds()
+                    tab, o2 = op.ata_class_table()
+                    assert np.array_equal(offs, o2)
+                    for r in range(R.shape[0]):
+                        assert R[r, :].tobytes() == tab[row_class(r, n, op.npts), :].tobytes(), (kind, n, bm, r)
+    assert ops.TDOperator("TV", (2, 5), (1.0, 1.0), np.float32).ata_class_table() is None       # axis shorter than 3
+
+
+def test_cds_list_is_lazy_until_indexed():
+    """PARSDMM_precompute_distribute returns AtA as a list whose stencil entries are formed on first access."""
+    import sip_b200 as sip
+    spec = pr.spec_config2((6, 5, 4), np.float32)
+    b = pr.build(sip, spec, sip.PARSDMM_options())
+    A = b["AtA"]
+    assert len(A) == 5 and all(A.is_lazy(i) for i in range(5)) and not A.materialized()
+    R1 = A[1]
+    assert R1.shape == (6 * 5 * 4, 7) and not A.is_lazy(1) and A.materialized()
+    want, offs = b["TD_OP"][1].ata_cds()
+    assert np.array_equal(R1, want) and np.array_equal(b["set_Prop"].AtA_offsets[1], offs)
+    assert [M.shape[1] for M in A] == [1, 7, 3, 3, 1]
