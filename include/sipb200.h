@@ -52,7 +52,9 @@ extern "C" {
 #define SIPB_SET_CARD_FIBER    9   /* project_cardinality!.jl:23-113: k largest magnitudes of every fiber (stable ties) */
 #define SIPB_SET_CARD_SLICE   10   /* project_cardinality!.jl:115-146: k largest magnitudes of every 2-D slice of a 3-D
                                       tensor; fiber_axis = the axis the slices are orthogonal to ("x","y","z" -> 0,1,2) */
-#define SIPB_SET_KIND_MAX     10
+#define SIPB_SET_HISTOGRAM    11   /* project_histogram_relaxed.jl:9-26: sorted values clamped by sorted bound vectors
+                                      (min_vec / max_vec: TF[M], ascending); stable sort in Julia's isless order */
+#define SIPB_SET_KIND_MAX     11
 
 /* transform-domain operator kinds (get_TD_operator.jl:12-95, get_discrete_Grad.jl) */
 #define SIPB_OP_IDENTITY 0
@@ -95,7 +97,7 @@ typedef struct sipb_set_desc {
   double  min;             /* scalar lower bound / annulus sigma_min                           */
   double  max;             /* scalar upper bound / l1 tau / l2 sigma / prox_l1 rho             */
   int64_t k;               /* cardinality                                                      */
-  const void* min_vec;     /* host TF[M] for SIPB_SET_BOUNDS_VECTOR, TF[td_n[fiber_axis]] for ..._FIBER, else NULL */
+  const void* min_vec;     /* host TF[M] for SIPB_SET_BOUNDS_VECTOR / SIPB_SET_HISTOGRAM, TF[td_n[fiber_axis]] for ..._FIBER, else NULL */
   const void* max_vec;
   int32_t fiber_axis;      /* fiber modes (app_mode ("fiber","x"|"y"|"z")): 0, 1 or 2 — axis of the transform-domain grid */
   int32_t reserved;
@@ -246,6 +248,15 @@ int sipb_problem_warm_from(sipb_problem* fine, sipb_problem* coarse, const sipb_
  *      return_ly==0). ------------------------------------------------------------------------- */
 int sipb_solve(sipb_problem* pb, const void* m, void* x, void* const* l, void* const* y,
                const sipb_options* opt, sipb_log* log);
+
+/* B independent projections at once: the per-channel / per-frame PARSDMM calls of examples/Constraint_examples_2D.jl:221-226
+ * and PARSDMM used as the projector inside an outer loop (examples/Dykstra_parallel_vs_PARSDMM.jl:134,149).  pbs[b]
+ * are finalized problems, EACH CREATED IN ITS OWN CONTEXT (sipb_ctx_create: a context owns one stream and its scratch);
+ * m[b], x[b], l[b], y[b], logs[b] as in sipb_solve (l, y may be NULL).  One host thread per problem drives its solve,
+ * the GPU overlaps the streams.  Results are those of B separate sipb_solve calls, bit for bit.  rcs (optional)
+ * receives the return code of every problem; the function returns the first failure. */
+int sipb_solve_batch(sipb_problem* const* pbs, int B, const void* const* m, void* const* x, void* const* const* l,
+                     void* const* const* y, const sipb_options* opt, sipb_log* const* logs, int* rcs);
 
 /* ---- unit entry points (host pointers; used by the parity tests and micro-benchmarks) ------ */
 /* y = A*x for A in CDS form: replaces Ax_CDS_MT / CDS_MVp_MT (argmin_x.jl:72-78, CDS_MVp_MT.jl:9-25) */

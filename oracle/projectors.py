@@ -106,6 +106,31 @@ def project_annulus(x: np.ndarray, sigma_min, sigma_max) -> np.ndarray:
     return x
 
 
+def _isless_key(x: np.ndarray) -> np.ndarray:
+    """Unsigned integer key whose order is Julia's `isless` on floats: -0.0 < 0.0, every NaN after +Inf."""
+    u = x.view(np.uint32 if x.dtype == np.float32 else np.uint64).copy()
+    top = np.array(1, dtype=u.dtype) << np.array(8 * u.dtype.itemsize - 1, dtype=u.dtype)
+    neg = (u & top) != 0
+    key = np.where(neg, ~u, u | top)
+    key[np.isnan(x)] = np.iinfo(u.dtype).max
+    return key
+
+
+def project_histogram_relaxed(x: np.ndarray, LB: np.ndarray, UB: np.ndarray) -> np.ndarray:
+    """project_histogram_relaxed.jl:9-26: sort_ind = sortperm(x) (stable, `isless` order); the sorted values are clamped
+    element by element — min(., UB[j]) first, then max(LB[j], .) — by the (already sorted) bounds and moved back."""
+    TF = x.dtype.type
+    LB = np.asarray(LB, dtype=TF)
+    UB = np.asarray(UB, dtype=TF)
+    sort_ind = np.argsort(_isless_key(x), kind="stable")             # :11
+    xs = x[sort_ind]                                                 # :12
+    xs = np.where(np.isnan(xs) | (xs < UB), xs, UB)                  # :15 min(x[j], UB[j])  (Julia min propagates NaN)
+    xs = np.where(np.isnan(xs) | (xs > LB), xs, LB)                  # :16 max(LB[j], x[j])
+    xs = np.where(np.isnan(LB) | np.isnan(UB), TF(np.nan), xs)
+    x[sort_ind] = xs                                                 # :18-19 (inverse permutation)
+    return x
+
+
 def project_cardinality(x: np.ndarray, k: int) -> np.ndarray:
     """project_cardinality!.jl:3-21: sort_ind = sortperm(x, by=abs, rev=true) (stable => among equal
     magnitudes the lower index ranks first and is kept); x[sort_ind[k+1:end]] .= 0."""

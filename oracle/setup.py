@@ -46,6 +46,8 @@ def get_projector(constraint, comp_grid, A, TD_n, TF):
         return lambda x: proj.project_annulus(x, cmin, cmax)                # :49
     if st == "cardinality":
         return lambda x: proj.project_cardinality(x, int(cmax))             # :90
+    if st == "histogram":
+        return lambda x: proj.project_histogram_relaxed(x, cmin, cmax)      # :81
     raise NotImplementedError("oracle: set type %r is outside the hot path" % st)
 
 

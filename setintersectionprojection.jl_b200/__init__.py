@@ -19,12 +19,12 @@ from .operators import (CDS_MVp, CDS_MVp_MT, CDS_scaled_add, SparseOperator, TDO
                         mat2CDS)
 from .constraints import Projector, get_projector, setup_constraints
 from .precompute import PARSDMM_precompute_distribute, PARSDMM_precompute_distribute_Minkowski
-from .solver import PARSDMM
+from .solver import PARSDMM, PARSDMM_batch
 from .multilevel import (PARSDMM_multi_level, constraint2coarse, interpolate_y_l, resample_nn,
                          setup_multi_level_PARSDMM)
 
 __all__ = [
-    "PARSDMM", "PARSDMM_multi_level", "PARSDMM_options", "constraint2coarse", "interpolate_y_l", "resample_nn",
+    "PARSDMM", "PARSDMM_batch", "PARSDMM_multi_level", "PARSDMM_options", "constraint2coarse", "interpolate_y_l", "resample_nn",
     "setup_multi_level_PARSDMM", "PARSDMM_precompute_distribute", "PARSDMM_precompute_distribute_Minkowski",
     "Projector", "TDOperator", "SparseOperator", "CDS_MVp", "CDS_MVp_MT", "CDS_scaled_add", "cg", "compgrid", "convert_options",
     "default_PARSDMM_options", "get_TD_operator", "get_discrete_Grad", "get_projector", "log_type_PARSDMM",

@@ -16,7 +16,7 @@ SIPB_OK = 0
 SIPB_E_INVALID, SIPB_E_UNSUPPORTED, SIPB_E_CUDA, SIPB_E_NCCL, SIPB_E_STATE, SIPB_E_MISSING_DIAG = -1, -2, -3, -4, -5, -6
 SIPB_F32, SIPB_F64 = 0, 1
 (SET_BOUNDS_SCALAR, SET_BOUNDS_VECTOR, SET_L1, SET_L2, SET_ANNULUS, SET_CARDINALITY, SET_PROX_L1,
- SET_DISTANCE, SET_BOUNDS_FIBER, SET_CARD_FIBER, SET_CARD_SLICE) = range(11)
+ SET_DISTANCE, SET_BOUNDS_FIBER, SET_CARD_FIBER, SET_CARD_SLICE, SET_HISTOGRAM) = range(12)
 OP_IDENTITY, OP_DX, OP_DY, OP_DZ, OP_TV, OP_DXZ, OP_SPARSE = range(7)
 BLOCK_PLAIN, BLOCK_LEFT, BLOCK_RIGHT, BLOCK_BOTH = range(4)
 N_PHASES = 7
@@ -103,6 +103,8 @@ SYMBOLS = [
     ("sipb_problem_destroy", _I, [_VP]),
     ("sipb_problem_warm_from", _I, [_VP, _VP, C.POINTER(ResampleSeg), _I]),
     ("sipb_solve", _I, [_VP, _VP, _VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(Options), C.POINTER(Log)]),
+    ("sipb_solve_batch", _I, [C.POINTER(_VP), _I, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(C.POINTER(_VP)),
+                              C.POINTER(C.POINTER(_VP)), C.POINTER(Options), C.POINTER(C.POINTER(Log)), _PI]),
     ("sipb_cds_spmv", _I, [_VP, _I, _I64, _I, _VP, _PI64, _VP, _VP]),
     ("sipb_cds_cg", _I, [_VP, _I, _I64, _I, _VP, _PI64, _VP, _VP, _D, _I, _PI, _PD, _PI]),
     ("sipb_project", _I, [_VP, _I, C.POINTER(SetDesc), _I64, _VP, _VP]),
@@ -154,6 +156,19 @@ def ctx(device: int | None = None):
         check(load().sipb_ctx_create(device, C.byref(h)))
         _ctx[device] = h
     return _ctx[device]
+
+
+_batch_ctx = {}
+
+
+def batch_ctx(device: int, index: int):
+    """Extra contexts for batched projections: problem `index` of a batch gets its own stream / scratch."""
+    key = (device, index)
+    if key not in _batch_ctx:
+        h = C.c_void_p()
+        check(load().sipb_ctx_create(device, C.byref(h)))
+        _batch_ctx[key] = h
+    return _batch_ctx[key]
 
 
 def dtype_code(dt) -> int:

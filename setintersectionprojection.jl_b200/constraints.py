@@ -19,7 +19,6 @@ _REJECTED = {
     "rank": "SVD-based rank constraints are out of scope on the GPU path",
     "nuclear": "SVD-based nuclear-norm constraints are out of scope on the GPU path",
     "subspace": "subspace constraints are outside the device hot path",
-    "histogram": "histogram constraints are outside the device hot path",
 }
 
 
@@ -125,6 +124,10 @@ def get_projector(constraint, comp_grid, special_operator_list, A, TD_n, TF) -> 
         return Projector(_lib.SET_ANNULUS, TF, lo, hi, name="annulus")                   # :49
     if st == "cardinality":
         return Projector(_lib.SET_CARDINALITY, TF, k=int(hi), name="cardinality")        # :90 convert(Integer, max)
+    if st == "histogram":                                                                # :77-82, vector-valued min / max
+        if np.ndim(lo) == 0 or np.ndim(hi) == 0 or np.size(lo) != np.size(hi):
+            raise ValueError("histogram constraints need vector-valued min and max of equal length (sorted bounds)")
+        return Projector(_lib.SET_HISTOGRAM, TF, lo_vec=lo, hi_vec=hi, name="histogram")
     raise ValueError("unknown set type %r" % st)
 
 

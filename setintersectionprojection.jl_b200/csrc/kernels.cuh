@@ -780,6 +780,7 @@ __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
     }
     case SIPB_SET_CARD_SLICE:
     case SIPB_SET_CARD_FIBER:      // already projected in place by k_card_fiber_* (pass-through)
+    case SIPB_SET_HISTOGRAM:       // already projected in place by k_hist_apply (pass-through)
       return v;
     case SIPB_SET_DISTANCE: {      // (x*rho + m) / (rho + 1.0) in Float64   prox_l2s!.jl:4
       const T num = v * P.rho + P.m[r];
@@ -1542,6 +1543,47 @@ __global__ void __launch_bounds__(kThreads) k_card_fiber_strided(T* __restrict__
         ++seen;
       }
     }
+  }
+}
+
+// =============================================================================================
+// relaxed histogram projection (project_histogram_relaxed.jl:9-26): sort_ind = sortperm(x) — a stable sort in
+// Julia's isless order (-0.0 < 0.0, NaN last) — then x[sort_ind[j]] = max(LB[j], min(x[sort_ind[j]], UB[j])).
+// The permutation comes from a stable LSD radix sort of order-preserving integer keys (cub::DeviceRadixSort, library
+// code) with the row index as payload; the two kernels here build the keys and apply the bounds through it.
+// =============================================================================================
+template <typename T> struct SortKey;
+template <> struct SortKey<float> { typedef unsigned int type; };
+template <> struct SortKey<double> { typedef unsigned long long type; };
+template <typename T> __device__ __forceinline__ typename SortKey<T>::type isless_key(T v);
+template <> __device__ __forceinline__ unsigned int isless_key<float>(float v) {
+  if (v != v) return 0xffffffffu;
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+template <> __device__ __forceinline__ unsigned long long isless_key<double>(double v) {
+  if (v != v) return ~0ull;
+  const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_hist_keys(i64 M, const T* __restrict__ v,
+                                                        typename SortKey<T>::type* __restrict__ keys,
+                                                        unsigned int* __restrict__ idx) {
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
+    keys[r] = isless_key<T>(v[r]);
+    idx[r] = (unsigned int)r;
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_hist_apply(i64 M, T* __restrict__ v, const unsigned int* __restrict__ sorted_idx,
+                                                         const T* __restrict__ lb, const T* __restrict__ ub) {
+  for (i64 j = (i64)blockIdx.x * blockDim.x + threadIdx.x; j < M; j += (i64)gridDim.x * blockDim.x) {
+    const unsigned int r = sorted_idx[j];
+    T t = v[r];
+    t = t_min<T>(t, ub[j]);          // x[j] = min(x[j], UB[j])     :15
+    t = t_max<T>(lb[j], t);          // x[j] = max(LB[j], x[j])     :16
+    v[r] = t;
   }
 }
 

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -20,6 +21,7 @@
 #include <nccl.h>   // types only: the library is resolved at run time (see NcclApi)
 
 #include "kernels.cuh"
+#include <cub/device/device_radix_sort.cuh>   // stable radix sort (library code) for the histogram set only
 
 namespace sipb {
 
@@ -855,6 +857,21 @@ struct SetT {
   DevBuf<T> y, l, y_old, s, s0, y0, l0, lhat0;   // s only for reduction-type projectors
   DevBuf<T> lo_vec, hi_vec;
   DevBuf<T> perm;             // SIPB_SET_CARD_SLICE, x / y slices: slice-major scratch copy
+  // SIPB_SET_HISTOGRAM: keys / row indices (double buffered) and the scratch space of the radix sort
+  DevBuf<typename SortKey<T>::type> hkeys[2];
+  DevBuf<unsigned int> hidx[2];
+  DevBuf<unsigned char> hsort;
+  size_t hsort_bytes = 0;
+  int alloc_hist(i64 M_) {
+    for (int q = 0; q < 2; ++q) {
+      SIPB_CUDA_CHECK(hkeys[q].alloc((size_t)M_));
+      SIPB_CUDA_CHECK(hidx[q].alloc((size_t)M_));
+    }
+    hsort_bytes = 0;
+    SIPB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, hsort_bytes, hkeys[0].p, hkeys[1].p, hidx[0].p, hidx[1].p, M_));
+    SIPB_CUDA_CHECK(hsort.alloc(hsort_bytes + 256));
+    return SIPB_OK;
+  }
   SparseDev<T> sparse;        // SIPB_OP_SPARSE: the explicit operator (op is then the identity over the s buffer)
   bool is_sparse = false;
   DevBuf<T> ata;              // [nd][ld]   (released once the stencil-class table has been verified)
@@ -1004,8 +1021,7 @@ struct Problem : sipb_problem {
     SIPB_REQUIRE(!finalized, SIPB_E_STATE, "problem already finalized");
     SIPB_REQUIRE((int)sets.size() < kMaxSets, SIPB_E_UNSUPPORTED, "too many sets");
     SIPB_REQUIRE(d->set_kind >= SIPB_SET_BOUNDS_SCALAR && d->set_kind <= SIPB_SET_KIND_MAX, SIPB_E_UNSUPPORTED,
-                 "set type is outside the device hot path (rank, nuclear, subspace, histogram and slice modes are "
-                 "rejected)");
+                 "set type is outside the device hot path (rank, nuclear and subspace sets are rejected)");
     const bool fiber = d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_CARD_FIBER ||
                        d->set_kind == SIPB_SET_CARD_SLICE;
     if (fiber) {
@@ -1017,6 +1033,8 @@ struct Problem : sipb_problem {
     SIPB_REQUIRE(minkowski ? d->block_mode != SIPB_BLOCK_PLAIN : d->block_mode == SIPB_BLOCK_PLAIN, SIPB_E_INVALID,
                  "block_mode inconsistent with the Minkowski flag of the problem");
     if (d->set_kind == SIPB_SET_L1) SIPB_REQUIRE(d->max > 0.0, SIPB_E_INVALID, "Radius of L1 ball is negative");
+    if (d->set_kind == SIPB_SET_HISTOGRAM)
+      SIPB_REQUIRE(!sg.on, SIPB_E_UNSUPPORTED, "the histogram set (a global sort) is single-GPU");
     auto S = std::make_unique<SetT<T>>();
     S->desc = *d;
     S->desc.sparse = nullptr;        // the host arrays are not kept
@@ -1056,9 +1074,10 @@ struct Problem : sipb_problem {
     if (fiber)
       SIPB_REQUIRE(d->td_n[0] * d->td_n[1] * d->td_n[2] == S->M && d->td_n[0] >= 1 && d->td_n[1] >= 1 && d->td_n[2] >= 1,
                    SIPB_E_INVALID, "td_n does not match the rows of the operator");
-    if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER) {
+    if (d->set_kind == SIPB_SET_HISTOGRAM) { rc = S->alloc_hist(S->M); if (rc) return rc; }
+    if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_HISTOGRAM) {
       SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
-      const size_t nb = d->set_kind == SIPB_SET_BOUNDS_VECTOR ? (size_t)S->M : (size_t)d->td_n[d->fiber_axis];
+      const size_t nb = d->set_kind == SIPB_SET_BOUNDS_FIBER ? (size_t)d->td_n[d->fiber_axis] : (size_t)S->M;
       SIPB_CUDA_CHECK(S->lo_vec.alloc(nb));
       SIPB_CUDA_CHECK(S->hi_vec.alloc(nb));
       SIPB_CUDA_CHECK(cudaMemcpyAsync(S->lo_vec.p, d->min_vec, nb * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
@@ -1415,6 +1434,14 @@ struct Problem : sipb_problem {
         }
         LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
       }
+    } else if (kind == SIPB_SET_HISTOGRAM) {
+      // sortperm + clamp by the sorted bounds + inverse permutation, in place; the apply pass is a pass-through
+      LAUNCH(c, KC_TIES, k_hist_keys<T>, c->grid_for(M), M, (const T*)v, S.hkeys[0].p, S.hidx[0].p);
+      size_t tb = S.hsort_bytes;
+      SIPB_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(S.hsort.p, tb, S.hkeys[0].p, S.hkeys[1].p, S.hidx[0].p, S.hidx[1].p, M, 0,
+                                                      (int)(8 * sizeof(typename SortKey<T>::type)), c->stream));
+      LAUNCH(c, KC_TIES, k_hist_apply<T>, c->grid_for(M), M, v, (const unsigned int*)S.hidx[1].p, (const T*)S.lo_vec.p,
+             (const T*)S.hi_vec.p);
     } else if (kind == SIPB_SET_CARD_FIBER || kind == SIPB_SET_CARD_SLICE) {
       card_fiber(S, v);            // projects every fiber in place; the apply pass is then a pass-through
     } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {
@@ -1485,7 +1512,7 @@ struct Problem : sipb_problem {
     T* vec = sv;
     const T* ref = nullptr;
     if (S.desc.set_kind == SIPB_SET_CARDINALITY || S.desc.set_kind == SIPB_SET_CARD_FIBER ||
-        S.desc.set_kind == SIPB_SET_CARD_SLICE) {   // in-place work on a scratch copy
+        S.desc.set_kind == SIPB_SET_CARD_SLICE || S.desc.set_kind == SIPB_SET_HISTOGRAM) {   // in-place work on a scratch copy
       SIPB_CUDA_CHECK(cudaMemcpyAsync(tmp.p, sv, M * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
       vec = tmp.p;
       ref = sv;
@@ -2420,6 +2447,47 @@ int sipb_solve(sipb_problem* pb, const void* m, void* x, void* const* l, void* c
   return pb->solve(m, x, l, y, opt, log);
 }
 
+// B independent projections side by side (RGB channels of examples/Constraint_examples_2D.jl:221-226, PARSDMM as the
+// inner projector of an outer loop, examples/Dykstra_parallel_vs_PARSDMM.jl:134,149): every problem lives in its own
+// context (own stream, scratch and scalar mirrors), one host thread per problem drives it, and the GPU overlaps the
+// small kernels of the different streams — a single small projection is latency bound and leaves most SMs idle.
+int sipb_solve_batch(sipb_problem* const* pbs, int B, const void* const* m, void* const* x, void* const* const* l,
+                     void* const* const* y, const sipb_options* opt, sipb_log* const* logs, int* rcs) {
+  SIPB_REQUIRE(pbs && m && x && opt && logs && B >= 1, SIPB_E_INVALID, "null argument");
+  for (int b = 0; b < B; ++b) {
+    SIPB_REQUIRE(pbs[b] && m[b] && x[b] && logs[b], SIPB_E_INVALID, "null entry in the batch");
+    SIPB_REQUIRE(pbs[b]->ctx->world == 1, SIPB_E_UNSUPPORTED, "batched projections run as replicas: one GPU per process");
+    for (int q = 0; q < b; ++q)
+      SIPB_REQUIRE(pbs[q]->ctx != pbs[b]->ctx, SIPB_E_INVALID,
+                   "every problem of a batch needs its own context (sipb_ctx_create): a context owns one stream");
+  }
+  std::vector<int> rc(B, SIPB_OK);
+  std::vector<std::string> errs(B);
+  std::vector<std::thread> th;
+  th.reserve(B);
+  for (int b = 0; b < B; ++b) {
+    th.emplace_back([&, b]() {
+      if (cudaSetDevice(pbs[b]->ctx->device) != cudaSuccess) {
+        rc[b] = SIPB_E_CUDA;
+        errs[b] = "cudaSetDevice failed";
+        return;
+      }
+      rc[b] = pbs[b]->solve(m[b], x[b], l ? l[b] : nullptr, y ? y[b] : nullptr, opt, logs[b]);
+      if (rc[b]) errs[b] = g_err;          // thread-local message of this worker
+    });
+  }
+  for (auto& t : th) t.join();
+  int first = SIPB_OK;
+  for (int b = 0; b < B; ++b) {
+    if (rcs) rcs[b] = rc[b];
+    if (rc[b] && !first) {
+      first = rc[b];
+      set_error("problem " + std::to_string(b) + " of the batch: " + errs[b]);
+    }
+  }
+  return first;
+}
+
 int sipb_op_rows(int ndim, const int64_t* n, int op_kind, int64_t* rows) {
   SIPB_REQUIRE(n && rows, SIPB_E_INVALID, "null argument");
   const int64_t r = op_rows_host(ndim, n, op_kind);
@@ -2508,9 +2576,10 @@ static int project_impl(sipb_ctx* c, const sipb_set_desc* d, int64_t M, void* v,
   SIPB_CUDA_CHECK(cudaMemsetAsync(S.warm.p, 0, 2 * sizeof(double), c->stream));
   SIPB_CUDA_CHECK(cudaMemsetAsync(S.pp_f.p, 0, sizeof(ProjParams<T>), c->stream));
   SIPB_CUDA_CHECK(cudaMemcpyAsync(S.s.p, v, M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
-  if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER) {
+  if (d->set_kind == SIPB_SET_HISTOGRAM) { int rc = S.alloc_hist(M); if (rc) return rc; }
+  if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_HISTOGRAM) {
     SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
-    const size_t nb = d->set_kind == SIPB_SET_BOUNDS_VECTOR ? (size_t)M : (size_t)d->td_n[d->fiber_axis];
+    const size_t nb = d->set_kind == SIPB_SET_BOUNDS_FIBER ? (size_t)d->td_n[d->fiber_axis] : (size_t)M;
     SIPB_CUDA_CHECK(S.lo_vec.alloc(nb));
     SIPB_CUDA_CHECK(S.hi_vec.alloc(nb));
     SIPB_CUDA_CHECK(cudaMemcpyAsync(S.lo_vec.p, d->min_vec, nb * sizeof(T), cudaMemcpyHostToDevice, c->stream));

@@ -45,7 +45,7 @@ def _problem_key(TF, TD_OP, P_sub, set_Prop, options):
     return tuple(items)
 
 
-def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) -> _DeviceProblem:
+def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, ctx=None) -> _DeviceProblem:
     """Upload operators descriptors + AtA (CDS) once; replaces the data movement of
     PARSDMM_precompute_distribute.jl and the allocation part of PARSDMM_initialize.jl."""
     lib = _lib.load()
@@ -72,7 +72,8 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options) ->
     n = (C.c_int64 * 3)(*(list(op0.n) + [1] * (3 - op0.ndim)))
     h = (C.c_double * 3)(*([float(v) for v in op0.h] + [1.0] * (3 - op0.ndim)))
     handle = C.c_void_p()
-    _lib.check(lib.sipb_problem_create(_lib.ctx(), _lib.dtype_code(TF), op0.ndim, n, h, int(bool(options.Minkowski)),
+    _lib.check(lib.sipb_problem_create(ctx if ctx is not None else _lib.ctx(), _lib.dtype_code(TF), op0.ndim, n, h,
+                                       int(bool(options.Minkowski)),
                                        int(bool(options.feasibility_only)), C.byref(handle)))
     # one row per stencil class instead of the N x nd arrays, unless the caller formed (and maybe changed) an array
     use_tables = (hasattr(AtA, "is_lazy") and all(AtA.is_lazy(i) for i in range(p)) and not AtA.materialized()
@@ -148,27 +149,12 @@ def device_problem(m_dtype, AtA, TD_OP, set_Prop, P_sub, comp_grid, options):
     return dev
 
 
-def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
-            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False, gather_result=True,
-            warm_resident=False):
-    """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
-    Returns (x, log_PARSDMM, l, y).
+class _Call:
+    """Marshalled arguments of one sipb_solve call (kept alive until the call returns)."""
 
-    Multi-GPU slabs (after `distributed.init`, 3-D problems): every rank passes the same global `m`
-    (or its own slab of it) and receives the global `x` (host-side gather) unless `gather_result=False`;
-    `l`, `y` are this rank's slabs (see `distributed.gather_td`).
 
-    `warm_resident=True` (with options.zero_ini_guess == False): the start vectors were already placed in the
-    device buffers by `sipb_problem_warm_from` (multilevel driver); x, l, y are not uploaded."""
-    if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
-        raise TypeError("m must be a Float32/Float64 vector")
+def _marshal(dev, m, TD_OP, options, x, l, y, profile_kernels, fixed_iterations, return_ly, resident_io, warm_resident) -> _Call:
     TF = m.dtype.type
-    if np.iscomplexobj(m) or (x is not None and np.iscomplexobj(x)):
-        raise ValueError("input for PARSDMM is not real")                                  # PARSDMM.jl:50-52
-    if getattr(options, "parallel", False):
-        raise NotImplementedError("options.parallel=true is rejected on the device path (use slab decomposition)")
-    convert_options(options, TF)                                                           # PARSDMM.jl:43
-    dev = device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options)
     p, pp, N = dev.p, dev.pp, dev.N
     m = np.ascontiguousarray(m)
     slab = getattr(dev, "slab", None)
@@ -178,7 +164,8 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
             m = dd.scatter_model(m, op0.n, *slab)
         if x is not None and np.size(x) == dev.N_global:
             x = dd.scatter_model(np.ascontiguousarray(x, dtype=TF), op0.n, *slab)
-        if l is not None and len(l) and all(np.size(l[i]) == dev.rows_global[i] for i in range(p)):
+        if (l is not None and y is not None and len(l) == p and len(y) == p
+                and all(np.size(l[i]) == dev.rows_global[i] for i in range(p))):
             l = [dd.scatter_td(np.ascontiguousarray(l[i], dtype=TF), TD_OP[i], *slab) for i in range(p)]
             y = [dd.scatter_td(np.ascontiguousarray(y[i], dtype=TF), TD_OP[i], *slab) for i in range(p)]
     if options.Minkowski:
@@ -208,45 +195,51 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
         l = [np.zeros(r, dtype=TF) for r in dev.rows]
         y = [np.zeros(r, dtype=TF) for r in dev.rows]
         have_ly = True
-    lp = yp = None
+    c = _Call()
+    c.lp = c.yp = None
     if have_ly:
         l = [np.ascontiguousarray(v, dtype=TF) for v in l]
         y = [np.ascontiguousarray(v, dtype=TF) for v in y]
         for i in range(p):
             if l[i].size != dev.rows[i] or y[i].size != dev.rows[i]:
                 raise ValueError("l[%d] / y[%d] have the wrong length" % (i, i))
-        lp = (C.c_void_p * p)(*[v.ctypes.data for v in l])
-        yp = (C.c_void_p * p)(*[v.ctypes.data for v in y])
+        c.lp = (C.c_void_p * p)(*[v.ctypes.data for v in l])
+        c.yp = (C.c_void_p * p)(*[v.ctypes.data for v in y])
 
     maxit = int(options.maxit)
-    rho_ini = np.ascontiguousarray([float(v) for v in options.rho_ini], dtype=np.float64)
+    c.rho_ini = np.ascontiguousarray([float(v) for v in options.rho_ini], dtype=np.float64)
     o = _lib.Options()
     o.maxit, o.rho_update_frequency = maxit, int(options.rho_update_frequency)
     o.adjust_rho, o.adjust_gamma = int(bool(options.adjust_rho)), int(bool(options.adjust_gamma))
     o.adjust_feasibility_rho, o.zero_ini_guess = int(bool(options.adjust_feasibility_rho)), int(zero_guess)
-    o.n_rho_ini, o.profile_kernels = rho_ini.size, int(bool(profile_kernels))
+    o.n_rho_ini, o.profile_kernels = c.rho_ini.size, int(bool(profile_kernels))
     o.evol_rel_tol, o.feas_tol, o.obj_tol = float(options.evol_rel_tol), float(options.feas_tol), float(options.obj_tol)
     o.gamma_ini = float(options.gamma_ini)
-    o.rho_ini = rho_ini.ctypes.data_as(C.POINTER(C.c_double))
+    o.rho_ini = c.rho_ini.ctypes.data_as(C.POINTER(C.c_double))
     o.fixed_iterations, o.return_ly = int(fixed_iterations), int(bool(return_ly and have_ly))
     o.resident_io = int(bool(resident_io))      # benchmark mode: no H2D/D2H (see include/sipb200.h)
     o.warm_resident = int(bool(warm_resident and not zero_guess))
 
-    arr = {
+    c.arr = {
         "set_feasibility": np.zeros((maxit + 2, max(pp, 1))), "r_dual": np.zeros((maxit, p)),
         "r_pri": np.zeros((maxit, p)), "r_dual_total": np.zeros(maxit), "r_pri_total": np.zeros(maxit),
         "obj": np.zeros(maxit), "evol_x": np.zeros(maxit), "rho": np.zeros((maxit, p)), "gamma": np.zeros((maxit, p)),
         "cg_relres": np.zeros(maxit),
     }
-    cg_it = np.zeros(maxit, dtype=np.int32)
+    c.cg_it = np.zeros(maxit, dtype=np.int32)
     lg = _lib.Log()
-    for name, a in arr.items():
+    for name, a in c.arr.items():
         setattr(lg, name, a.ctypes.data_as(C.POINTER(C.c_double)))
-    lg.cg_it = cg_it.ctypes.data_as(C.POINTER(C.c_int32))
+    lg.cg_it = c.cg_it.ctypes.data_as(C.POINTER(C.c_int32))
+    c.m, c.x_in, c.x_out, c.l, c.y, c.o, c.lg, c.dev = m, x, x_out, l, y, o, lg, dev
+    c.zero_guess, c.slab = zero_guess, slab
+    return c
 
+
+def _collect(c: _Call, options, gather_result, resident_io):
     lib = _lib.load()
-    _lib.check(lib.sipb_solve(dev.handle, m.ctypes.data, x_out.ctypes.data, lp, yp, C.byref(o), C.byref(lg)))
-
+    lg, arr, dev = c.lg, c.arr, c.dev
+    pp = dev.pp
     it = max(int(lg.iters), 1)       # feasible input: logs trimmed to row 1 (PARSDMM.jl:70-80)
     rows_f = int(lg.feas_rows)
     timing = {name: float(lg.phase_seconds[i]) for i, name in enumerate(_lib.PHASE_NAMES)}
@@ -262,11 +255,97 @@ def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, 
     log = log_type_PARSDMM(
         set_feasibility=arr["set_feasibility"][:rows_f, :pp], r_dual=arr["r_dual"][:it], r_pri=arr["r_pri"][:it],
         r_dual_total=arr["r_dual_total"][:it], r_pri_total=arr["r_pri_total"][:it], obj=arr["obj"][:it],
-        evol_x=arr["evol_x"][:it], rho=arr["rho"][:it], gamma=arr["gamma"][:it], cg_it=cg_it[:it].astype(np.int64),
+        evol_x=arr["evol_x"][:it], rho=arr["rho"][:it], gamma=arr["gamma"][:it], cg_it=c.cg_it[:it].astype(np.int64),
         cg_relres=arr["cg_relres"][:it], timing=timing)
+    x, x_out, l, y = c.x_in, c.x_out, c.l, c.y
+    if lg.stopped_feasible and c.zero_guess and l is not None:
+        # feasible input: the reference returns the zero start vectors (PARSDMM_initialize.jl:304-313, PARSDMM.jl:81)
+        for v in list(l) + list(y):
+            v[:] = 0
     if x is not None and isinstance(x, np.ndarray) and x.size == x_out.size and x is not x_out:
         x[:] = x_out                                                                       # in-place like the reference
         x_out = x
-    if slab is not None and gather_result and not resident_io:
+    if c.slab is not None and gather_result and not resident_io:
         x_out = dd.gather_model(x_out)
     return x_out, log, l, y
+
+
+def _check_input(m, x, options):
+    if not isinstance(m, np.ndarray) or m.dtype not in (np.float32, np.float64) or m.ndim != 1:
+        raise TypeError("m must be a Float32/Float64 vector")
+    if np.iscomplexobj(m) or (x is not None and np.iscomplexobj(x)):
+        raise ValueError("input for PARSDMM is not real")                                  # PARSDMM.jl:50-52
+    if getattr(options, "parallel", False):
+        raise NotImplementedError("options.parallel=true is rejected on the device path (use slab decomposition)")
+
+
+def PARSDMM(m, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, x=None, l=None, y=None, *,
+            profile_kernels=False, fixed_iterations=0, return_ly=True, resident_io=False, gather_result=True,
+            warm_resident=False):
+    """Project m onto the intersection of the sets; see PARSDMM.jl:25-35 for the arguments.
+    Returns (x, log_PARSDMM, l, y).
+
+    Multi-GPU slabs (after `distributed.init`, 3-D problems): every rank passes the same global `m`
+    (or its own slab of it) and receives the global `x` (host-side gather) unless `gather_result=False`;
+    `l`, `y` are this rank's slabs (see `distributed.gather_td`).
+
+    `warm_resident=True` (with options.zero_ini_guess == False): the start vectors were already placed in the
+    device buffers by `sipb_problem_warm_from` (multilevel driver); x, l, y are not uploaded."""
+    _check_input(m, x, options)
+    TF = m.dtype.type
+    convert_options(options, TF)                                                           # PARSDMM.jl:43
+    dev = device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options)
+    c = _marshal(dev, m, TD_OP, options, x, l, y, profile_kernels, fixed_iterations, return_ly, resident_io, warm_resident)
+    lib = _lib.load()
+    _lib.check(lib.sipb_solve(dev.handle, c.m.ctypes.data, c.x_out.ctypes.data, c.lp, c.yp, C.byref(c.o), C.byref(c.lg)))
+    return _collect(c, options, gather_result, resident_io)
+
+
+def PARSDMM_batch(ms, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, *, return_ly=True):
+    """B independent projections of the models `ms[b]` at once (one GPU): the per-channel PARSDMM calls of
+    examples/Constraint_examples_2D.jl:221-226, or PARSDMM as the projector inside an outer loop
+    (examples/Dykstra_parallel_vs_PARSDMM.jl:134,149).  `AtA, TD_OP, set_Prop, P_sub` are either ONE problem definition
+    shared by all models or lists of B definitions (each channel its own constraints); the options are shared.
+    Returns a list of B `(x, log, l, y)` tuples — the results of B separate `PARSDMM` calls, bit for bit.
+    Every problem gets its own device context (stream); one host thread per problem drives it (sipb_solve_batch)."""
+    B = len(ms)
+    if B == 0:
+        return []
+    if dd.active():
+        raise NotImplementedError("batched projections run as replicas: one GPU per process, no slab decomposition")
+    shared = not (isinstance(AtA, (list, tuple)) and len(AtA) == B and isinstance(TD_OP[0], (list, tuple)))
+    defs = [(AtA, TD_OP, set_Prop, P_sub)] * B if shared else list(zip(AtA, TD_OP, set_Prop, P_sub))
+    TF = ms[0].dtype.type
+    for m in ms:
+        _check_input(m, None, options)
+        if m.dtype.type != TF:
+            raise TypeError("all models of a batch must share one float type")
+    convert_options(options, TF)
+    device = int(os.environ.get("LOCAL_RANK", "0")) if "LOCAL_RANK" in os.environ else 0
+    calls = []
+    for b, (A_b, T_b, S_b, P_b) in enumerate(defs):
+        key = _problem_key(TF, T_b, P_b, S_b, options)
+        cache = getattr(A_b, "_batch_devices", None)
+        if cache is None:
+            cache = {}
+            try:
+                A_b._batch_devices = cache
+            except AttributeError:
+                pass
+        dev = cache.get(b)
+        if dev is None or dev.key != key:
+            dev = build_device_problem(TF, A_b, T_b, S_b, P_b, comp_grid, options, ctx=_lib.batch_ctx(device, b))
+            cache[b] = dev
+        calls.append(_marshal(dev, ms[b], T_b, options, None, None, None, False, 0, return_ly, False, False))
+    lib = _lib.load()
+    VP = C.c_void_p
+    pbs = (VP * B)(*[c.dev.handle for c in calls])
+    mp = (VP * B)(*[c.m.ctypes.data for c in calls])
+    xp = (VP * B)(*[c.x_out.ctypes.data for c in calls])
+    PVP = C.POINTER(VP)
+    lps = (PVP * B)(*[C.cast(c.lp, PVP) if c.lp is not None else PVP() for c in calls])
+    yps = (PVP * B)(*[C.cast(c.yp, PVP) if c.yp is not None else PVP() for c in calls])
+    logs = (C.POINTER(_lib.Log) * B)(*[C.pointer(c.lg) for c in calls])
+    rcs = (C.c_int * B)()
+    _lib.check(lib.sipb_solve_batch(pbs, B, mp, xp, lps, yps, C.byref(calls[0].o), logs, rcs))
+    return [_collect(c, options, False, False) for c in calls]
