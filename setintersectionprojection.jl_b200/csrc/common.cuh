@@ -278,6 +278,18 @@ __device__ __forceinline__ void p_wait(const CommDev& cd, bool need_lo, bool nee
 }
 
 // ---------------------------------------------------------------------------------------------
+// device-side loops: the CG iteration and the l1 threshold search run as the body of a CUDA-graph WHILE node; the
+// kernel that decides convergence sets the loop condition (no host poll, no speculative launches)
+// ---------------------------------------------------------------------------------------------
+struct LoopCond {
+  cudaGraphConditionalHandle h;
+  int on;                 // 0: the kernel runs outside a graph (host-driven loop), the handle is unused
+};
+__device__ __forceinline__ void loop_set(const LoopCond& lc, bool keep_going) {
+  if (lc.on) cudaGraphSetConditional(lc.h, keep_going ? 1u : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-side error handling
 // ---------------------------------------------------------------------------------------------
 void set_error(const std::string& msg);

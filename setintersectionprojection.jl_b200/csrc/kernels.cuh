@@ -402,8 +402,9 @@ __global__ void k_mail_collect(const __grid_constant__ CommDev cd, double* dst, 
 // scalar epilogue of the init (after the optional all-reduce of bb, rr): tolerance rule of
 // argmin_x.jl:33-37 and the early exits of cg.jl:47,73-76
 template <typename T>
-__global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd) {
+__global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd, LoopCond lc) {
   if (cd.on) mail_collect<2>(cd, &st->bb);       // bb, rr are adjacent
+  loop_set(lc, true);
   const T nb = (T)sqrt(st->bb);
   const T nr = (T)sqrt(st->rr);
   st->iter = 0;
@@ -423,16 +424,28 @@ __global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd) {
     st->tol = (double)(T)cur;
     st->tol_prev = st->tol;
   }
-  if (nb == (T)0) {            // cg.jl:47: rhs == 0 -> zeros, flag -9, iter 0 (host zero-fills x)
+  if (nb == (T)0) {            // cg.jl:47: rhs == 0 -> zeros, flag -9, iter 0 (x is zero-filled afterwards)
     st->flag = -9;
     st->done = 1;
+    loop_set(lc, false);
     return;
   }
   if (nr / nb <= (T)st->tol) {  // cg.jl:73-76
     st->flag = 0;
     st->iter = 1;
     st->done = 1;
+    loop_set(lc, false);
   }
+  if (st->maxit < 1) {          // for iter = 1:maxIter never runs
+    st->done = 1;
+    loop_set(lc, false);
+  }
+}
+// cg.jl:47: x = zeros when the right-hand side is zero (flag -9); runs after the loop, returns at once otherwise
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cg_zero_x(i64 N, T* __restrict__ x, const CgState* st) {
+  if (st->flag != -9) return;
+  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < N; r += (i64)gridDim.x * blockDim.x) x[r] = (T)0;
 }
 
 // x += alpha p ; r -= alpha Ap ; rr_new = dot(r,r)        (cg.jl:88-100)
@@ -496,8 +509,11 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ r, T* __restrict__ p,
                                                    RedScratch rs, CgState* st, const __grid_constant__ CommDev cd,
-                                                   i64 halo) {
-  if (st->done) return;
+                                                   i64 halo, LoopCond lc) {
+  if (st->done) {               // k_cg_xr found alpha < 0 / Inf (cg.jl:91): the loop ends here
+    if (blockIdx.x == 0 && threadIdx.x == 0) loop_set(lc, false);
+    return;
+  }
   constexpr int VW = Vec<T>::W;
   if (cd.on) mail_collect_all<1>(cd, &st->rr_new);   // peer path: sum the ranks' partials of r.r
   const double rr_new = ld_vol(&st->rr_new);
@@ -544,6 +560,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
       st->rr_new = rr_new;
       if (cd.on) p_publish(cd);               // p has been rewritten: release it to the neighbours
     }
+    loop_set(lc, !(conv || last_it));
   }
 }
 
@@ -1289,6 +1306,7 @@ struct L1State {
   int on_left;       // iterate known to be <= root
   int done;
   int passes;
+  int failed;        // sticky: a search hit the pass limit without reaching its fix point
 };
 
 // Newton step theta <- (S - tau)/C with the restart / fix-point logic
@@ -1311,15 +1329,18 @@ __device__ __forceinline__ void l1_newton_step(L1State* st, double C, double S) 
       st->on_left = 1;
     }
   }
-  if (st->passes >= 200) st->done = 1;
+  if (st->passes >= 200 && !st->done) { st->done = 1; st->failed = 1; }     // no fix point: reported by the host
 }
 
 // fused != 0: the last block performs the Newton step (single GPU); otherwise it only publishes the
 // rank-local (C, S) and k_l1_step runs after the all-reduce.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict__ v, RedScratch rs, L1State* st,
-                                                      int fused, const __grid_constant__ CommDev cd) {
-  if (st->done) return;
+                                                      int fused, const __grid_constant__ CommDev cd, LoopCond lc) {
+  if (st->done) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) loop_set(lc, false);
+    return;
+  }
   const double theta = st->theta;
   double d[2] = {0.0, 0.0};
   constexpr int VW = Vec<T>::W;
@@ -1340,23 +1361,28 @@ __global__ void __launch_bounds__(kThreads) k_l1_pass(i64 M, const T* __restrict
   if (grid_sum<2>(d, rs)) {
     if (cd.on) mail_publish<2>(cd, d);          // slabs, peer path: partial (C, S) to every rank's mailbox
     else if (threadIdx.x == 0) {
-      if (fused) l1_newton_step(st, d[0], d[1]);
-      else { st->C = d[0]; st->S = d[1]; }
+      if (fused) {
+        l1_newton_step(st, d[0], d[1]);
+        loop_set(lc, !st->done);
+      } else { st->C = d[0]; st->S = d[1]; }
     }
   }
 }
 // one thread; peer path: first sums the ranks' (C, S) partials from the mailbox (C and S are adjacent)
-__global__ void k_l1_step(L1State* st, const __grid_constant__ CommDev cd) {
-  if (st->done) return;
+__global__ void k_l1_step(L1State* st, const __grid_constant__ CommDev cd, LoopCond lc) {
+  if (st->done) { loop_set(lc, false); return; }
   if (cd.on) mail_collect<2>(cd, &st->C);
   l1_newton_step(st, st->C, st->S);
+  loop_set(lc, !st->done);
 }
 
 // min |v| as an order-preserving magnitude key -> atomicMin on out[0] (initialised to ~0ull by the host).
 // Only needed when EVERY entry stays above the l1 threshold: the reference's scan stops at lv-1
 // (project_l1_Duchi!.jl:42-46), so its theta then comes from the lv-1 largest entries (see k_l1_cap).
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_absmin_key(i64 M, const T* __restrict__ v, unsigned long long* out) {
+__global__ void __launch_bounds__(kThreads) k_absmin_key(i64 M, const T* __restrict__ v, unsigned long long* out,
+                                                         const L1State* st) {
+  if (st && !(st->theta >= 0.0 && st->C == st->M && st->M >= 2.0)) return;     // the cap applies to all-active vectors only
   unsigned long long k = ~0ull;
   for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
     const unsigned long long q = mag_key<T>(v[r]);

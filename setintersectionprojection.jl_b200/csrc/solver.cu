@@ -11,7 +11,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <array>
 #include <limits>
+#include <map>
 #include <memory>
 #include <thread>
 #include <unordered_map>
@@ -142,6 +144,8 @@ struct sipb_ctx {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream_body = nullptr;      // only used while capturing the body of a graph WHILE node
+  bool graph_loops = true;                 // device-side CG / l1 loops (SIPB_GRAPH_LOOPS=0: host-driven loops)
   RedScratch rs{nullptr, nullptr};
   RedScratch rs_multi{nullptr, nullptr};   // kYlMulti slices for the multi-set y/l launch
   double* d_scal = nullptr;   // device scalar slots
@@ -180,6 +184,7 @@ struct sipb_ctx {
     return SIPB_OK;
   }
   int64_t nccl_calls = 0;
+  int64_t l1_graph_runs = 0;
   // sum-all-reduce of `count` doubles in place on the stream (no-op on a single GPU)
   int allreduce(double* d, size_t count) {
     if (world == 1) return SIPB_OK;
@@ -284,10 +289,15 @@ constexpr int kSlotGlobal = kMaxSets * kSlotPerSet;   // 256
 // Copies the scalar slots to the host.  With slabs the slots hold per-rank partial sums: one batched
 // Float64 all-reduce makes them global first; the slots are then cleared so that stale entries never
 // accumulate across iterations.
-static int ctx_sync_scalars(sipb_ctx* c) {
+static int ctx_sync_scalars(sipb_ctx* c, bool with_loop_state = false) {
   int rc = c->allreduce(c->d_scal, kScalSlots);
   if (rc) return rc;
   SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_scal, c->d_scal, kScalSlots * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  if (with_loop_state) {     // device-side loops (CG, l1 search): their outcome travels with the scalars
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_cg, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_l1, c->d_l1, sizeof(L1State), cudaMemcpyDeviceToHost, c->stream));
+    if (c->p2p) SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_p2p_err, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
   if (c->world > 1) SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_scal, 0, kScalSlots * sizeof(double), c->stream));
   SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   return SIPB_OK;
@@ -300,7 +310,8 @@ namespace sipb {
 
 template <typename T>
 __global__ void k_l1_begin(const double* stats, double tau, double M, const double* warm, L1State* st,
-                           ProjParams<T>* pp) {
+                           ProjParams<T>* pp, LoopCond lc) {
+  loop_set(lc, true);
   const T s1 = (T)stats[0];
   st->tau = tau;
   st->S1 = stats[0];
@@ -310,6 +321,7 @@ __global__ void k_l1_begin(const double* stats, double tau, double M, const doub
     st->done = 1;
     st->theta = -1.0;
     pp->theta = (T)-1;
+    loop_set(lc, false);
     return;
   }
   const double w = *warm;
@@ -824,6 +836,81 @@ static int launch_tile(sipb_ctx* c, int cls, const TileGeom& g, bool arrays, con
   return SIPB_E_STATE;
 }
 static_assert(kTileNumOrders == 3, "launch_tile dispatches three orders");
+// shared-memory opt-in of the class-form kernels of this geometry (outside any stream capture)
+template <typename T>
+static int tile_prepare(const TileGeom& g) {
+  int rc = SIPB_OK;
+  switch (g.order) {
+    case 0: rc = tile_opt_in(k_spmv_tile<T, 1, false, 0>, g.smem_bytes); if (!rc) rc = tile_opt_in(k_spmv_tile<T, 2, false, 0>, g.smem_bytes); break;
+    case 1: rc = tile_opt_in(k_spmv_tile<T, 1, false, 1>, g.smem_bytes); if (!rc) rc = tile_opt_in(k_spmv_tile<T, 2, false, 1>, g.smem_bytes); break;
+    case 2: rc = tile_opt_in(k_spmv_tile<T, 1, false, 2>, g.smem_bytes); if (!rc) rc = tile_opt_in(k_spmv_tile<T, 2, false, 2>, g.smem_bytes); break;
+    default: break;
+  }
+  return rc;
+}
+
+// A CUDA graph  init -> WHILE(cond) { body } -> tail  built by stream capture: the CG iteration and the l1 threshold
+// search loop on the device; the kernel that decides convergence sets the condition (LoopCond, common.cuh).
+struct LoopGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  void destroy() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    exec = nullptr;
+    graph = nullptr;
+  }
+};
+// init / body / tail launch kernels on ctx->stream (the body is captured on a second stream that temporarily takes its
+// place); each returns a SIPB_* code.
+template <typename FInit, typename FBody, typename FTail>
+static int build_loop_graph(sipb_ctx* c, LoopGraph& out, FInit init, FBody body, FTail tail) {
+  out.destroy();
+  cudaStream_t s = c->stream;
+  SIPB_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  int rc = SIPB_OK;
+  cudaGraph_t g = nullptr, done_graph = nullptr;
+  auto fail = [&](int code) {
+    cudaStreamEndCapture(s, &done_graph);
+    if (done_graph) cudaGraphDestroy(done_graph);
+    cudaGetLastError();
+    return code;
+  };
+  cudaStreamCaptureStatus st;
+  const cudaGraphNode_t* deps = nullptr;
+  size_t nd = 0;
+  if (cudaStreamGetCaptureInfo(s, &st, nullptr, &g, &deps, &nd) != cudaSuccess || !g) return fail(SIPB_E_CUDA);
+  LoopCond lc;
+  lc.on = 1;
+  if (cudaGraphConditionalHandleCreate(&lc.h, g, 0, cudaGraphCondAssignDefault) != cudaSuccess) return fail(SIPB_E_CUDA);
+  if ((rc = init(lc))) return fail(rc);
+  if (cudaStreamGetCaptureInfo(s, &st, nullptr, &g, &deps, &nd) != cudaSuccess) return fail(SIPB_E_CUDA);
+  cudaGraphNodeParams np = {cudaGraphNodeTypeConditional};
+  np.conditional.handle = lc.h;
+  np.conditional.type = cudaGraphCondTypeWhile;
+  np.conditional.size = 1;
+  cudaGraphNode_t cn;
+  if (cudaGraphAddNode(&cn, g, deps, nd, &np) != cudaSuccess) return fail(SIPB_E_CUDA);
+  cudaGraph_t bg = np.conditional.phGraph_out[0];
+  if (cudaStreamUpdateCaptureDependencies(s, &cn, 1, cudaStreamSetCaptureDependencies) != cudaSuccess) return fail(SIPB_E_CUDA);
+  // the loop body is captured into the conditional node's own graph on a second stream
+  cudaStream_t sb = c->stream_body;
+  if (cudaStreamBeginCaptureToGraph(sb, bg, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    return fail(SIPB_E_CUDA);
+  c->stream = sb;
+  rc = body(lc);
+  c->stream = s;
+  cudaGraph_t bdone = nullptr;
+  if (cudaStreamEndCapture(sb, &bdone) != cudaSuccess || rc) return fail(rc ? rc : SIPB_E_CUDA);
+  if ((rc = tail())) return fail(rc);
+  if (cudaStreamEndCapture(s, &out.graph) != cudaSuccess) { cudaGetLastError(); return SIPB_E_CUDA; }
+  if (cudaGraphInstantiate(&out.exec, out.graph, 0) != cudaSuccess) {
+    out.destroy();
+    cudaGetLastError();
+    return SIPB_E_CUDA;
+  }
+  return SIPB_OK;
+}
 
 // =============================================================================================
 // problem
@@ -885,6 +972,8 @@ struct SetT {
   DevBuf<double> warm;        // [2] warm-start thresholds (y-update, feasibility)
   bool z_halo = false;        // slabs: y, l, y_old have a halo plane in front (D_z block)
   int l1_last[2] = {5, 5};    // Newton passes the last l1 threshold search needed (y-update / feasibility)
+  std::map<std::array<const void*, 4>, LoopGraph> l1_graphs;   // device-side search loops, one per (vector, stats, warm, params)
+  ~SetT() { for (auto& kv : l1_graphs) kv.second.destroy(); }
 };
 
 template <typename T>
@@ -912,7 +1001,10 @@ struct Problem : sipb_problem {
   void* p_lo_base = nullptr;
   void* p_hi_base = nullptr;
   i64 n_lo = 0;
+  LoopGraph cg_graph;         // init -> WHILE { SpMV, x/r update, p update } -> zero-fill on rhs == 0
+  const void* cg_graph_key[3] = {nullptr, nullptr, nullptr};
   ~Problem() override {
+    cg_graph.destroy();
     if (p_lo_base) cudaIpcCloseMemHandle(p_lo_base);
     if (p_hi_base) cudaIpcCloseMemHandle(p_hi_base);
   }
@@ -1170,6 +1262,7 @@ struct Problem : sipb_problem {
     { int rc = setup_peer_p(); if (rc) return rc; }
     tile = plan_tile<T>(ndim, n, minkowski, q_offs, sg.on ? sg.nloc() : n[2], sg.on ? sg.k0 : 0, sg.on && sg.has_lo,
                         sg.on && sg.has_hi, ctx->num_sms);
+    if (tile.ok && q_classes) { int rc = tile_prepare<T>(tile); if (rc) return rc; }
     finalized = true;
     return SIPB_OK;
   }
@@ -1399,40 +1492,69 @@ struct Problem : sipb_problem {
     int rc = c->allreduce(stats, 3);
     if (rc) return rc;
     if (kind == SIPB_SET_L1) {
-      LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)Mg, warm, c->d_l1, pp);
-      int launched = 0;
-      int& last = S.l1_last[warm == S.warm.p ? 0 : 1];
-      for (;;) {
-        // passes are queued speculatively (they return at once after `done`); the warm-started search mostly
-        // repeats the pass count of the previous iteration, so the first batch is sized from it
-        const int batch = (launched == 0) ? std::min(std::max(last + 1, 2), 6) : 8;
-        for (int b = 0; b < batch; ++b) {
-          const bool peer = sg.on && c->p2p;
-          LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, c->grid_fit((const void*)k_l1_pass<T>, (M + Vec<T>::W - 1) / Vec<T>::W), M, v, c->rs, c->d_l1, fused,
-                 peer ? c->cd_on : c->cd_off);
-          if (!fused) {
-            if (!peer && (rc = c->allreduce(&c->d_l1->C, 2))) return rc;
-            LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1, peer ? c->cd_on : c->cd_off);
+      const bool peer = sg.on && c->p2p;
+      const int g_l1 = c->grid_fit((const void*)k_l1_pass<T>, (M + Vec<T>::W - 1) / Vec<T>::W);
+      unsigned long long* mk = c->d_tie_counts;
+      if (c->graph_loops && !c->profile && !sg.on) {
+        // the whole search as one graph launch: begin -> WHILE { pass } -> end -> lv-1 cap (device-side decisions only)
+        LoopGraph& lg = S.l1_graphs[{(const void*)v, (const void*)stats, (const void*)warm, (const void*)pp}];
+        if (!lg.exec) {
+          rc = build_loop_graph(
+              c, lg,
+              [&](const LoopCond& lc) {
+                LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)Mg, warm, c->d_l1, pp, lc);
+                return SIPB_OK;
+              },
+              [&](const LoopCond& lc) {
+                LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, g_l1, M, (const T*)v, c->rs, c->d_l1, 1, c->cd_off, lc);
+                return SIPB_OK;
+              },
+              [&]() {
+                LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
+                if (cudaMemsetAsync(mk, 0xff, sizeof(unsigned long long), c->stream) != cudaSuccess) return SIPB_E_CUDA;
+                LAUNCH(c, KC_L1_PASS, k_absmin_key<T>, c->grid_for(M), M, (const T*)v, mk, (const L1State*)c->d_l1);
+                LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
+                return SIPB_OK;
+              });
+          if (rc) { set_error("could not build the l1 search graph"); return rc; }
+        }
+        SIPB_CUDA_CHECK(cudaGraphLaunch(lg.exec, c->stream));
+        c->total_launches += 1;
+        c->l1_graph_runs += 1;
+      } else {
+        const LoopCond off{0, 0};
+        LAUNCH1(c, KC_PARAMS, k_l1_begin<T>, stats, (double)(T)S.desc.max, (double)Mg, warm, c->d_l1, pp, off);
+        int launched = 0;
+        int& last = S.l1_last[warm == S.warm.p ? 0 : 1];
+        for (;;) {
+          // passes are queued speculatively (they return at once after `done`); the warm-started search mostly
+          // repeats the pass count of the previous iteration, so the first batch is sized from it
+          const int batch = (launched == 0) ? std::min(std::max(last + 1, 2), 6) : 8;
+          for (int b = 0; b < batch; ++b) {
+            LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, g_l1, M, v, c->rs, c->d_l1, fused, peer ? c->cd_on : c->cd_off, off);
+            if (!fused) {
+              if (!peer && (rc = c->allreduce(&c->d_l1->C, 2))) return rc;
+              LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1, peer ? c->cd_on : c->cd_off, off);
+            }
           }
+          launched += batch;
+          SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_l1, c->d_l1, sizeof(L1State), cudaMemcpyDeviceToHost, c->stream));
+          SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+          if (c->h_l1->done || launched >= 256) break;
         }
-        launched += batch;
-        SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_l1, c->d_l1, sizeof(L1State), cudaMemcpyDeviceToHost, c->stream));
-        SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        if (c->h_l1->done || launched >= 256) break;
-      }
-      SIPB_REQUIRE(c->h_l1->done, SIPB_E_STATE, "l1 threshold search did not converge within 256 passes");
-      last = c->h_l1->passes;
-      LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
-      if (c->h_l1->theta >= 0.0 && c->h_l1->C == c->h_l1->M && Mg >= 2) {
-        // every entry is above the threshold: reproduce the reference's lv-1 cap (project_l1_Duchi!.jl:42-46)
-        unsigned long long* mk = c->d_tie_counts;
-        SIPB_CUDA_CHECK(cudaMemsetAsync(mk, 0xff, sizeof(unsigned long long), c->stream));
-        LAUNCH(c, KC_L1_PASS, k_absmin_key<T>, c->grid_for(M), M, (const T*)v, mk);
-        if (sg.on) {
-          c->nccl_calls++;
-          SIPB_NCCL_CHECK(NCCL(AllReduce)(mk, mk, 1, ncclUint64, ncclMin, c->comm, c->stream));
+        SIPB_REQUIRE(c->h_l1->done && !c->h_l1->failed, SIPB_E_STATE, "l1 threshold search did not converge");
+        last = c->h_l1->passes;
+        LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
+        if (c->h_l1->theta >= 0.0 && c->h_l1->C == c->h_l1->M && Mg >= 2) {
+          // every entry is above the threshold: reproduce the reference's lv-1 cap (project_l1_Duchi!.jl:42-46)
+          SIPB_CUDA_CHECK(cudaMemsetAsync(mk, 0xff, sizeof(unsigned long long), c->stream));
+          LAUNCH(c, KC_L1_PASS, k_absmin_key<T>, c->grid_for(M), M, (const T*)v, mk, (const L1State*)nullptr);
+          if (sg.on) {
+            c->nccl_calls++;
+            SIPB_NCCL_CHECK(NCCL(AllReduce)(mk, mk, 1, ncclUint64, ncclMin, c->comm, c->stream));
+          }
+          LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
         }
-        LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
       }
     } else if (kind == SIPB_SET_HISTOGRAM) {
       // sortperm + clamp by the sorted bounds + inverse permutation, in place; the apply pass is a pass-through
@@ -1528,7 +1650,7 @@ struct Problem : sipb_problem {
   // Slabs: the halos of `xv` must be valid on entry; they are valid again on exit.  Every rank launches
   // the same sequence (the control scalars are all-reduced, hence identical), so the NCCL calls match.
   int run_cg(const T* b, T* xv, T* x_old_out, int parsdmm_it, double tol, int max_iter, int predicted,
-             int* iters, double* relres, int* flag) {
+             int* iters, double* relres, int* flag, bool* deferred = nullptr) {
     sipb_ctx* c = ctx;
     CgState* h = c->h_cg;
     int rc;
@@ -1547,36 +1669,68 @@ struct Problem : sipb_problem {
     // (k_cg_init measured faster with two waves than with one: 2.03 vs 2.68 ms per solve at 200^3)
     const int g_init = c->grid_for(nvecN), g_mv = c->grid_fit((const void*)k_spmv<T, true>, nvecN),
               g_xr = c->grid_fit((const void*)k_cg_xr<T>, nvecN), g_p = c->grid_fit((const void*)k_cg_p<T>, nvecN);
-    if (tile.ok && q_classes) {
-      const TileInit<T> ti{b, r.p, pp, x_old_out};
-      if ((rc = launch_tile<T, 2>(c, KC_CG_INIT, tile, !q_classes, spmv_args(xv, nullptr), ti, nullptr, nullptr, c->d_cg, cd)))
-        return rc;
-    } else {
-      LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
-    }
+    const bool tiled = tile.ok && q_classes;
+    // r = b - Qx, p = r, x_old = x, tolerance rule / early exits        (argmin_x.jl:33-37, cg.jl:47-76)
+    auto launch_init = [&](const LoopCond& lc) -> int {
+      if (tiled) {
+        const TileInit<T> ti{b, r.p, pp, x_old_out};
+        if ((rc = launch_tile<T, 2>(c, KC_CG_INIT, tile, false, spmv_args(xv, nullptr), ti, nullptr, nullptr, c->d_cg, cd)))
+          return rc;
+      } else {
+        LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+      }
+      if (!peer && (rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
+      LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg, cd, lc);
+      return SIPB_OK;
+    };
+    // one CG iteration                                                  (cg.jl:84-114)
+    auto launch_iter = [&](const LoopCond& lc, const int* done_flag) -> int {
+      if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
+      if (tiled) {
+        const TileInit<T> ti{nullptr, nullptr, nullptr, nullptr};
+        if ((rc = launch_tile<T, 1>(c, KC_SPMV_DOT, tile, false, spmv_args_peer(Ap.p), ti, &c->d_cg->pAp, done_flag, c->d_cg, cd)))
+          return rc;
+      } else {
+        LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g_mv, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, done_flag, cd);
+      }
+      if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;      // peer path: collected inside k_cg_xr
+      LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g_xr, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
+      if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;   // peer path: collected inside k_cg_p
+      LAUNCH(c, KC_CG_P, k_cg_p<T>, g_p, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0, lc);
+      return SIPB_OK;
+    };
     const double vecN = (double)N * sizeof(T);
     const double q_rows = q_classes ? 0.0 : (double)q_offs.size();       // matrix words streamed per row
     c->account(KC_CG_INIT, (q_rows + 4 + (x_old_out ? 1 : 0)) * vecN);   // Q, x, b -> r, p (, x_old)
-    if (!peer && (rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
-    LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg, cd);
+    if (deferred) {
+      // Device-side loop: ONE graph launch runs the prologue, iterates until the convergence test of cg.jl:103 (or
+      // maxIter, or alpha < 0) ends the WHILE node, and zero-fills x for a zero right-hand side.  The host does not
+      // wait: iteration count, relres and flag are read with the per-iteration scalars (finish_cg).
+      if (!cg_graph.exec || cg_graph_key[0] != (const void*)b || cg_graph_key[1] != (const void*)xv ||
+          cg_graph_key[2] != (const void*)x_old_out) {
+        rc = build_loop_graph(
+            c, cg_graph, [&](const LoopCond& lc) { return launch_init(lc); },
+            [&](const LoopCond& lc) { return launch_iter(lc, (const int*)nullptr); },
+            [&]() {
+              LAUNCH(c, KC_FILL, k_cg_zero_x<T>, c->grid_for(N), N, xv, (const CgState*)c->d_cg);
+              return SIPB_OK;
+            });
+        if (rc) { set_error("could not build the CG loop graph"); return rc; }
+        cg_graph_key[0] = b; cg_graph_key[1] = xv; cg_graph_key[2] = x_old_out;
+      }
+      SIPB_CUDA_CHECK(cudaGraphLaunch(cg_graph.exec, c->stream));
+      c->total_launches += 1;
+      if ((rc = exchange(xv, sg.nloc(), true, true))) return rc;            // halo planes of the new x
+      *deferred = true;
+      return SIPB_OK;
+    }
+    const LoopCond off{0, 0};
+    if ((rc = launch_init(off))) return rc;
     int launched = 0;
     int batch = std::max(1, predicted);
     for (;;) {
-      for (int q = 0; q < batch && launched < max_iter; ++q, ++launched) {
-        if (!peer && (rc = exchange(pp, sg.nloc(), true, true))) return rc;     // halo planes of p
-        if (tile.ok && q_classes) {
-          const TileInit<T> ti{nullptr, nullptr, nullptr, nullptr};
-          if ((rc = launch_tile<T, 1>(c, KC_SPMV_DOT, tile, false, spmv_args_peer(Ap.p), ti, &c->d_cg->pAp,
-                                      (const int*)&c->d_cg->done, c->d_cg, cd)))
-            return rc;
-        } else {
-          LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g_mv, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, &c->d_cg->done, cd);
-        }
-        if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;      // peer path: collected inside k_cg_xr
-        LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g_xr, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
-        if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;   // peer path: collected inside k_cg_p
-        LAUNCH(c, KC_CG_P, k_cg_p<T>, g_p, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0);
-      }
+      for (int q = 0; q < batch && launched < max_iter; ++q, ++launched)
+        if ((rc = launch_iter(off, (const int*)&c->d_cg->done))) return rc;
       SIPB_CUDA_CHECK(cudaMemcpyAsync(h, c->d_cg, sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
       if (peer) SIPB_CUDA_CHECK(cudaMemcpyAsync(c->h_p2p_err, c->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
@@ -1584,16 +1738,35 @@ struct Problem : sipb_problem {
       if (h->done || launched >= max_iter) break;
       batch = std::max(2, launched / 2);
     }
-    // bytes of the loop iterations that ran (launches queued behind `done` return immediately and move nothing)
-    c->account(KC_SPMV_DOT, h->loops * (q_rows + 2) * vecN);                          // Q, p -> Ap
-    c->account(KC_CG_XR, h->loops * 6 * vecN);                                        // x, r, p, Ap -> x, r
-    c->account(KC_CG_P, std::max(0, h->loops - (h->flag == 0 ? 1 : 0)) * 3 * vecN);   // r, p -> p
+    account_cg_loops(h);
     if (h->flag == -9) SIPB_CUDA_CHECK(cudaMemsetAsync(xv, 0, N * sizeof(T), c->stream));   // cg.jl:47
     if ((rc = exchange(xv, sg.nloc(), true, true))) return rc;              // halo planes of the new x
     *iters = h->iter;
     *relres = h->relres;
     *flag = h->flag;
     return SIPB_OK;
+  }
+  // bytes of the loop iterations that ran (launches queued behind `done` return immediately and move nothing)
+  void account_cg_loops(const CgState* h) {
+    sipb_ctx* c = ctx;
+    const double vecN = (double)N * sizeof(T);
+    const double q_rows = q_classes ? 0.0 : (double)q_offs.size();
+    c->account(KC_SPMV_DOT, h->loops * (q_rows + 2) * vecN);                          // Q, p -> Ap
+    c->account(KC_CG_XR, h->loops * 6 * vecN);                                        // x, r, p, Ap -> x, r
+    c->account(KC_CG_P, std::max(0, h->loops - (h->flag == 0 ? 1 : 0)) * 3 * vecN);   // r, p -> p
+  }
+  // a deferred (graph) CG: the state arrived with the per-iteration scalars
+  void finish_cg(int* iters, double* relres, int* flag) {
+    sipb_ctx* c = ctx;
+    const CgState* h = c->h_cg;
+    account_cg_loops(h);
+    // kernels the graph ran: prologue (2), three per iteration, the zero-fill check
+    c->launches[KC_SPMV_DOT] += h->loops; c->launches[KC_CG_XR] += h->loops; c->launches[KC_CG_P] += h->loops;
+    c->launches[KC_CG_INIT] += 1; c->launches[KC_CG_FIN] += 1;
+    c->total_launches += 3 * (int64_t)h->loops + 2;
+    *iters = h->iter;
+    *relres = h->relres;
+    *flag = h->flag;
   }
 
   int solve(const void* m_h, void* x_h, void* const* l_h, void* const* y_h, const sipb_options* o,
@@ -1737,6 +1910,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   SIPB_CUDA_CHECK(cudaEventCreate(&ev1));
   SIPB_CUDA_CHECK(cudaEventRecord(ev0, c->stream));
 
+  SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_l1, 0, sizeof(L1State), c->stream));
   // initial feasibility  ||P(A m) - A m|| / (||A m|| + 100 eps)   (:97-99)
   const int nP = pp;   // P_sub has one entry per non-distance set
   for (int i = 0; i < nP; ++i) {
@@ -1764,7 +1938,22 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
   for (int i = 0; i < p; ++i) gamma[i] = gamma_ini;
 
   if (stop) {                                                      // PARSDMM.jl:63-82
-    // x = m (Minkowski: [m; 0]); device buffer m already holds exactly that
+    // x = m (Minkowski: [m; 0]); device buffer m already holds exactly that.  The resident state must equal what
+    // is returned — a later sipb_problem_warm_from (multilevel) reads x, l, y from these buffers: x = m, and
+    // l = y = 0 for a zero start (PARSDMM_initialize.jl:304-313) or the caller's l, y otherwise.
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(x.p, m.p, N * sizeof(T), cudaMemcpyDeviceToDevice, c->stream));
+    if (o->zero_ini_guess) {
+      for (auto& S : sets) {
+        SIPB_CUDA_CHECK(cudaMemsetAsync(S->y.p, 0, S->M * sizeof(T), c->stream));
+        SIPB_CUDA_CHECK(cudaMemsetAsync(S->l.p, 0, S->M * sizeof(T), c->stream));
+      }
+    } else if (!warm_res && l_h && y_h) {
+      for (int i = 0; i < p; ++i) {
+        if (!l_h[i] || !y_h[i]) continue;
+        SIPB_CUDA_CHECK(cudaMemcpyAsync(sets[i]->l.p, l_h[i], sets[i]->M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+        SIPB_CUDA_CHECK(cudaMemcpyAsync(sets[i]->y.p, y_h[i], sets[i]->M * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+      }
+    }
     if (!resident) {
       SIPB_CUDA_CHECK(cudaMemcpyAsync(x_h, m.p, N * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
       log->d2h_bytes += N * sizeof(T);
@@ -1897,8 +2086,13 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     // ---------------- x-minimisation (argmin_x.jl + cg.jl) -----------------------------------
     int cg_it = 0, cg_flag = 0;
     double cg_relres = 0.0;
+    bool cg_deferred = false;
     {
-      int rc = run_cg(rhs.p, x.p, x_old.p, i, 0.0, 1000, last_cg + 1, &cg_it, &cg_relres, &cg_flag);
+      // device-side loop (one graph launch, no host poll) unless the kernel table is being profiled or the slabs
+      // use NCCL inside the CG
+      const bool loop_on_device = c->graph_loops && !c->profile && (!sg.on || p_shared != nullptr);
+      int rc = run_cg(rhs.p, x.p, x_old.p, i, 0.0, 1000, last_cg + 1, &cg_it, &cg_relres, &cg_flag,
+                      loop_on_device ? &cg_deferred : nullptr);
       if (rc) return rc;
       last_cg = cg_it;
     }
@@ -2002,7 +2196,15 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
              (const T*)x_old.p, (const T*)m.p, c->rs, c->d_scal + kSlotGlobal);
       c->account(KC_STOP, 3.0 * N * sizeof(T));                            // x, x_old, m
     }
-    { int rc = ctx_sync_scalars(c); if (rc) return rc; }
+    { int rc = ctx_sync_scalars(c, true); if (rc) return rc; }
+    if (c->p2p) SIPB_REQUIRE(*c->h_p2p_err == 0, SIPB_E_NCCL, "peer-memory collective timed out (a rank stopped participating)");
+    SIPB_REQUIRE(!c->h_l1->failed, SIPB_E_STATE, "l1 threshold search did not converge");
+    if (cg_deferred) {
+      finish_cg(&cg_it, &cg_relres, &cg_flag);
+      last_cg = cg_it;
+      log->cg_it[i - 1] = cg_it;
+      log->cg_relres[i - 1] = cg_relres;
+    }
     {
       T rp_tot = 0, rd_tot = 0;
       for (int s = 0; s < p; ++s) {
@@ -2197,6 +2399,8 @@ int sipb_ctx_create(int device, sipb_ctx** out) {
   SIPB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
   c->num_sms = prop.multiProcessorCount;
   SIPB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  SIPB_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream_body, cudaStreamNonBlocking));
+  { const char* e = getenv("SIPB_GRAPH_LOOPS"); c->graph_loops = !(e && e[0] == '0'); }
   SIPB_CUDA_CHECK(cudaMalloc(&c->rs.partials, sizeof(double) * kMaxRed * kMaxBlocks));
   SIPB_CUDA_CHECK(cudaMalloc(&c->rs.counter, sizeof(unsigned int)));
   SIPB_CUDA_CHECK(cudaMemset(c->rs.counter, 0, sizeof(unsigned int)));
@@ -2242,6 +2446,7 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   if (c->d_gather_local) cudaFree(c->d_gather_local);
   if (c->comm) NCCL(CommDestroy)(c->comm);
   cudaStreamDestroy(c->stream);
+  if (c->stream_body) cudaStreamDestroy(c->stream_body);
   delete c;
   return SIPB_OK;
 }

@@ -911,9 +911,13 @@ def test_config3_128cubed_f32(sip, orc):
     sparse set-up and stable sort of 512^3 take tens of minutes; tools/parity_fullsize.py runs larger grids).
 
     The cardinality set is non-convex: an entry whose magnitude sits at the k-th largest value flips in or out of the
-    support on a one-ulp change of its input, and the l1 threshold of the device (exact root, Float64 sums) and of the
-    oracle (Float32 cumsum) differ by ulps.  Iteration and CG counts must match; x agrees to 1.2e-3 at this size
-    (measured; bit-identical at 96^3 / 25 iterations, see bench.py's parity object), the supports to a 1e-3 fraction."""
+    support on a one-ulp change of its input.  Measured at this size (scratch/div128.py): device and CPU runs are
+    BIT-IDENTICAL in every logged scalar for 15 iterations; at iteration 16 one rho differs by one ulp (an adaptation
+    sum rounds differently) and the supports drift apart.  After 30 iterations x differs by 1.20e-3 (device vs the
+    C/OpenMP port), 1.13e-3 (device vs the NumPy oracle) and 0.91e-3 (the two CPU restatements AGAINST EACH OTHER),
+    with 2.1 % / 1.9 % / 1.2 % of the k support entries different: no pair of faithful Float32 implementations meets
+    1e-3 here.  The test pins what is stable: iteration and CG counts, exactly k survivors, x to 3e-3, supports to
+    4 % (bit-identical x at 96^3 / 25 iterations: bench.py's parity object)."""
     def tw(o):
         o.maxit, o.evol_rel_tol = 30, 10 * float(np.finfo(np.float32).eps)
     spec = pr.spec_config3((128, 128, 128), np.float32)
@@ -923,7 +927,7 @@ def test_config3_128cubed_f32(sip, orc):
     assert np.allclose(ls.obj, lo.obj, rtol=5e-2)
     k = np.count_nonzero(yy[2])
     assert np.count_nonzero(y2[2]) == k                              # exactly k entries survive on both sides
-    assert np.count_nonzero((y2[2] != 0) != (yy[2] != 0)) <= 2e-3 * k
+    assert np.count_nonzero((y2[2] != 0) != (yy[2] != 0)) <= 4e-2 * k
 
 
 def test_baseline_size_config4_multilevel_100cubed(sip, orc):
@@ -1013,3 +1017,47 @@ def test_parsdmm_batch_matches_independent_solves(sip, orc, TF):
             xs, ls, _, _ = sip.PARSDMM(ms[b].copy(), shared["AtA"], shared["TD_OP"], shared["set_Prop"], shared["P_sub"], shared["cg"],
                                        shared["opt"])
             assert np.array_equal(out[b][0], xs) and len(out[b][1].obj) == len(ls.obj)
+
+
+def test_multilevel_feasible_coarse_level(sip, orc):
+    """A coarse level that is already feasible returns x = m_coarse, l = y = 0 (PARSDMM.jl:63-82); the finer level must
+    warm-start from exactly that, on the device-resident path as on the host path.  The slope bound holds on the
+    coarse grid (spacing doubled: differences of the noise halve) and fails on the fine grid."""
+    from oracle import multilevel as om
+    TF = np.float32
+    n = (32, 24, 16)
+    spec = pr.spec_config4(n, TF)
+    m = spec["m"]
+    sets = [("bounds", "identity", 0.0, 1e5), ("bounds", "D_z", -100.0, 100.0)]
+    # find a bound between the largest coarse and the largest fine vertical slope (coarse model and spacing as the
+    # multilevel set-up produces them)
+    cg0 = sip.compgrid(tuple(spec["d"]), n)
+    cons0 = [sip.set_definitions(st, op, lo, hi, ("tensor", "")) for (st, op, lo, hi) in sets]
+    lv0 = sip.setup_multi_level_PARSDMM(m, 2, 2, cg0, cons0, sip.PARSDMM_options())
+    cgc = lv0[4][1]
+    mc = sip.resample_nn(m, n, cgc.n).reshape(tuple(cgc.n), order="F").astype(np.float64)
+    fine = np.abs(np.diff(m.reshape(n, order="F").astype(np.float64), axis=2)).max() / float(cg0.d[2])
+    coarse = np.abs(np.diff(mc, axis=2)).max() / float(cgc.d[2])
+    assert coarse < fine
+    bound = 0.5 * (coarse + fine)
+    sets[1] = ("bounds", "D_z", -bound, bound)
+    res = []
+    for api in (orc, sip):
+        cg = api.compgrid(tuple(spec["d"]), n)
+        cons = [api.set_definitions(st, op, lo, hi, ("tensor", "")) for (st, op, lo, hi) in sets]
+        opt = api.PARSDMM_options()
+        opt.FL, opt.maxit = TF, 40
+        if api is orc:
+            lv = om.setup_multi_level_PARSDMM(m, 2, 2, cg, cons, opt, orc.types)
+            res.append(om.PARSDMM_multi_level(m.copy(), *lv[:5], opt))
+        else:
+            lv = sip.setup_multi_level_PARSDMM(m, 2, 2, cg, cons, opt)
+            dev = sip.PARSDMM_multi_level(m.copy(), *lv[:5], opt)
+            host = sip.PARSDMM_multi_level(m.copy(), *lv[:5], opt, device_resample=False)
+            assert dev[1].timing["levels"][0]["stopped_feasible"] and not dev[1].timing["levels"][1]["stopped_feasible"]
+            assert np.array_equal(dev[0], host[0]) and dev[1].timing["level_iterations"] == host[1].timing["level_iterations"]
+            assert all(np.array_equal(a, b) for a, b in zip(dev[3] + dev[2], host[3] + host[2]))
+            res.append(dev)
+    (xo, lo, ll, yy), (xs, ls, l2, y2) = res
+    assert [len(g.obj) for g in lo.levels] == ls.timing["level_iterations"]
+    assert relerr(xs, xo) < TOL[TF]
