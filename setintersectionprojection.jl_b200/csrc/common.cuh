@@ -278,6 +278,71 @@ __device__ __forceinline__ void p_wait(const CommDev& cd, bool need_lo, bool nee
 }
 
 // ---------------------------------------------------------------------------------------------
+// Small all-reduces (<= kBigN 64-bit words) over peer memory: the once-per-iteration collectives of a slab solve — the
+// batched log / adaptation sums, projector statistics, 256-bin radix histograms, tie counts — cost a kernel of one
+// block and an NVLink round trip (~5 us) instead of an NCCL launch (~25-40 us each, ~10 per PARSDMM iteration).
+// Every rank stores its words into every peer's slot, fences, raises a sequence flag; then it waits for all flags
+// and reduces the slots in rank order (bit-identical on all ranks).  Two buffers: a rank can be at most one
+// collective ahead of its slowest peer.
+// ---------------------------------------------------------------------------------------------
+constexpr int kBigN = 512;
+struct PeerBig {
+  unsigned long long data[2][kMaxRanks][kBigN];
+  unsigned long long flag[2][kMaxRanks];
+};
+struct BigDev {
+  int rank, world;
+  int* err;
+  unsigned long long* seq;           // device counter of collectives done by this rank
+  PeerBig* box[kMaxRanks];           // box[q]: rank q's buffer (peer mapped; box[rank] is local)
+};
+// OP 0: sum of doubles, 1: sum of uint64, 2: min of uint64.  One block of kBigN threads, every rank launches it.
+template <int OP>
+__global__ void __launch_bounds__(kBigN) k_peer_allreduce(const __grid_constant__ BigDev bd, unsigned long long* buf, int count) {
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) s_seq = *bd.seq + 1ull;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int b = (int)(seq & 1ull);
+  const int t = threadIdx.x;
+  if (t < count) {
+    const unsigned long long v = buf[t];
+    for (int q = 0; q < bd.world; ++q)
+      *reinterpret_cast<volatile unsigned long long*>(&bd.box[q]->data[b][bd.rank][t]) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (t < bd.world) {
+    *reinterpret_cast<volatile unsigned long long*>(&bd.box[t]->flag[b][bd.rank]) = seq;      // one flag store per peer
+    const PeerBig* me = bd.box[bd.rank];
+    const long long t0 = clock64();
+    while (ld_vol(&me->flag[b][t]) != seq) {
+      __nanosleep(64);
+      if (clock64() - t0 > kSpinLimit) { *bd.err = 1; break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (t < count) {
+    const PeerBig* me = bd.box[bd.rank];
+    if (OP == 0) {
+      double acc = 0.0;
+      for (int q = 0; q < bd.world; ++q) acc += __longlong_as_double((long long)ld_vol(&me->data[b][q][t]));
+      buf[t] = (unsigned long long)__double_as_longlong(acc);
+    } else if (OP == 1) {
+      unsigned long long acc = 0ull;
+      for (int q = 0; q < bd.world; ++q) acc += ld_vol(&me->data[b][q][t]);
+      buf[t] = acc;
+    } else {
+      unsigned long long acc = ~0ull;
+      for (int q = 0; q < bd.world; ++q) { const unsigned long long v = ld_vol(&me->data[b][q][t]); acc = v < acc ? v : acc; }
+      buf[t] = acc;
+    }
+  }
+  if (t == 0) *bd.seq = seq;
+}
+
+// ---------------------------------------------------------------------------------------------
 // device-side loops: the CG iteration and the l1 threshold search run as the body of a CUDA-graph WHILE node; the
 // kernel that decides convergence sets the loop condition (no host poll, no speculative launches)
 // ---------------------------------------------------------------------------------------------

@@ -170,6 +170,23 @@ struct sipb_ctx {
   int* h_p2p_err = nullptr;
   CommDev cd_on;                                   // descriptor with the peer path active
   CommDev cd_off;
+  PeerBig* d_big = nullptr;                        // this rank's buffer of the small peer all-reduces (exported)
+  void* peer_big_base[kMaxRanks] = {nullptr};
+  BigDev bd;                                       // valid when p2p
+  int64_t peer_collectives = 0;
+  // all-reduce of `count` 64-bit words in place: peer memory when the path is up and the payload is small, else NCCL
+  template <int OP>
+  int small_allreduce(void* d, size_t count, ncclDataType_t dt, ncclRedOp_t op) {
+    if (world == 1) return SIPB_OK;
+    if (p2p && d_big && count <= (size_t)kBigN) {
+      peer_collectives++;
+      k_peer_allreduce<OP><<<1, kBigN, 0, stream>>>(bd, reinterpret_cast<unsigned long long*>(d), (int)count);
+      return SIPB_OK;
+    }
+    nccl_calls++;
+    SIPB_NCCL_CHECK(NCCL(AllReduce)(d, d, count, dt, op, comm, stream));
+    return SIPB_OK;
+  }
   std::vector<void*> shared_bufs;                  // exported p vectors: freed at ctx teardown only (see DESIGN)
   // all-gather `bytes` per rank through a device bounce buffer (set-up only)
   int allgather_bytes(const void* mine, void* all, size_t bytes) {
@@ -186,18 +203,9 @@ struct sipb_ctx {
   int64_t nccl_calls = 0;
   int64_t l1_graph_runs = 0;
   // sum-all-reduce of `count` doubles in place on the stream (no-op on a single GPU)
-  int allreduce(double* d, size_t count) {
-    if (world == 1) return SIPB_OK;
-    nccl_calls++;
-    SIPB_NCCL_CHECK(NCCL(AllReduce)(d, d, count, ncclDouble, ncclSum, comm, stream));
-    return SIPB_OK;
-  }
-  int allreduce_u64(unsigned long long* d, size_t count) {
-    if (world == 1) return SIPB_OK;
-    nccl_calls++;
-    SIPB_NCCL_CHECK(NCCL(AllReduce)(d, d, count, ncclUint64, ncclSum, comm, stream));
-    return SIPB_OK;
-  }
+  int allreduce(double* d, size_t count) { return small_allreduce<0>(d, count, ncclDouble, ncclSum); }
+  int allreduce_u64(unsigned long long* d, size_t count) { return small_allreduce<1>(d, count, ncclUint64, ncclSum); }
+  int allreduce_min_u64(unsigned long long* d, size_t count) { return small_allreduce<2>(d, count, ncclUint64, ncclMin); }
   // launch accounting
   bool profile = false;
   int64_t launches[SIPB_N_KERNEL_CLASSES];
@@ -1549,10 +1557,7 @@ struct Problem : sipb_problem {
           // every entry is above the threshold: reproduce the reference's lv-1 cap (project_l1_Duchi!.jl:42-46)
           SIPB_CUDA_CHECK(cudaMemsetAsync(mk, 0xff, sizeof(unsigned long long), c->stream));
           LAUNCH(c, KC_L1_PASS, k_absmin_key<T>, c->grid_for(M), M, (const T*)v, mk, (const L1State*)nullptr);
-          if (sg.on) {
-            c->nccl_calls++;
-            SIPB_NCCL_CHECK(NCCL(AllReduce)(mk, mk, 1, ncclUint64, ncclMin, c->comm, c->stream));
-          }
+          if (sg.on && (rc = c->allreduce_min_u64(mk, 1))) return rc;
           LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
         }
       }
@@ -1596,9 +1601,11 @@ struct Problem : sipb_problem {
             const i64 chunk = ((std::max<i64>(Mb, 1) + g - 1) / g + kThreads - 1) / kThreads * kThreads;
             LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, Mb, v + S.op.row_start[b], pp, chunk, c->d_tie_counts + (size_t)b * g);
           }
-          LAUNCH1(c, KC_TIES, k_tie_totals, c->d_tie_counts, nb, g, g, c->d_gather_local);
-          c->nccl_calls++;
-          SIPB_NCCL_CHECK(NCCL(AllGather)(c->d_gather_local, c->d_gather, 4, ncclUint64, c->comm, c->stream));
+          // all-gather of the 4 per-block totals == sum-all-reduce of a [world][4] table in which a rank fills its row
+          SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_gather, 0, sizeof(unsigned long long) * 4 * c->world, c->stream));
+          LAUNCH1(c, KC_TIES, k_tie_totals, c->d_tie_counts, nb, g, g, c->d_gather + 4 * c->rank);
+          rc = c->allreduce_u64(c->d_gather, (size_t)4 * c->world);
+          if (rc) return rc;
           for (int b = 0; b < nb; ++b) {
             const i64 Mb = S.op.row_start[b + 1] - S.op.row_start[b];
             const i64 chunk = ((std::max<i64>(Mb, 1) + g - 1) / g + kThreads - 1) / kThreads * kThreads;
@@ -2438,6 +2445,9 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   for (int q = 0; q < kMaxRanks; ++q)
     if (c->peer_mail_base[q]) cudaIpcCloseMemHandle(c->peer_mail_base[q]);
   for (void* b : c->shared_bufs) cudaFree(b);
+  for (int q = 0; q < kMaxRanks; ++q)
+    if (c->peer_big_base[q]) cudaIpcCloseMemHandle(c->peer_big_base[q]);
+  if (c->d_big) { cudaFree(c->d_big); cudaFree(c->bd.seq); }
   if (c->d_mail) cudaFree(c->d_mail);
   if (c->d_seq_pv) cudaFree(c->d_seq_pv);
   if (c->d_p2p_err) cudaFree(c->d_p2p_err);
@@ -2502,6 +2512,41 @@ static int comm_setup_p2p(sipb_ctx* c) {
   SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
   c->p2p = (flag == 0.0);
   if (c->p2p) {
+    // second exported buffer: the small all-reduces of the y/l phase (failure here only keeps those on NCCL)
+    cudaIpcMemHandle_t hb;
+    memset(&hb, 0, sizeof(hb));
+    int okb = cudaMalloc(&c->d_big, sizeof(PeerBig)) == cudaSuccess && cudaMemset(c->d_big, 0, sizeof(PeerBig)) == cudaSuccess &&
+              cudaIpcGetMemHandle(&hb, c->d_big) == cudaSuccess;
+    cudaGetLastError();
+    std::vector<cudaIpcMemHandle_t> allb(c->world);
+    rc = c->allgather_bytes(&hb, allb.data(), sizeof(hb));
+    if (rc) return rc;
+    memset(&c->bd, 0, sizeof(c->bd));
+    c->bd.rank = c->rank;
+    c->bd.world = c->world;
+    c->bd.err = c->d_p2p_err;
+    for (int q = 0; q < c->world && okb; ++q) {
+      if (q == c->rank) { c->bd.box[q] = c->d_big; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, allb[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { okb = 0; cudaGetLastError(); break; }
+      c->peer_big_base[q] = ptr;
+      c->bd.box[q] = reinterpret_cast<PeerBig*>(ptr);
+    }
+    double fb = okb ? 0.0 : 1.0;       // all ranks or none (plain NCCL: d_big is not in use yet)
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(c->d_scal, &fb, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->nccl_calls++;
+    SIPB_NCCL_CHECK(NCCL(AllReduce)(c->d_scal, c->d_scal, 1, ncclDouble, ncclSum, c->comm, c->stream));
+    SIPB_CUDA_CHECK(cudaMemcpyAsync(&fb, c->d_scal, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_scal, 0, sizeof(double), c->stream));
+    SIPB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const char* envb = getenv("SIPB_PEER_ALLREDUCE");
+    if (fb != 0.0 || (envb && envb[0] == '0')) {
+      if (c->d_big) cudaFree(c->d_big);
+      c->d_big = nullptr;           // peer_big_base mappings are closed at teardown
+    } else {
+      SIPB_CUDA_CHECK(cudaMalloc(&c->bd.seq, sizeof(unsigned long long)));
+      SIPB_CUDA_CHECK(cudaMemset(c->bd.seq, 0, sizeof(unsigned long long)));
+    }
     c->cd_on.on = 1;
     c->cd_on.has_lo = c->rank > 0;
     c->cd_on.has_hi = c->rank < c->world - 1;
