@@ -854,7 +854,8 @@ struct YlArgs {
   T* y;                       // y^{k+1} (output; MODE 1 parks v = x_hat - l/rho here for pass 2)
   T* l;
   const T* y_old;             // y^{k}: the host swaps the y / y_old buffers instead of copying (update_y_l.jl:64)
-  T* s;                       // only reduction-type projectors keep s between their two passes
+  T* s;                       // reduction-type projectors: s = A x is stored by pass 1 only when somebody reads it later
+  int store_s;                //   (the feasibility check of every 10th iteration); pass 2 recomputes it from x
   T* lhat0; T* s0; T* l0; T* y0;   // snapshots of the adaptation scheme
   T rho, gamma;
   const T* x_old;    // distance term only: also reduce the stop sums ||x-m||^2, ||x_old-x||^2, ||x||^2 (PARSDMM.jl:140-145)
@@ -919,7 +920,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
     }
     store_n<T, W>(a.y + r0, yn);
     if (MODE == 0) store_n<T, W>(a.l + r0, ln);
-    else store_n<T, W>(a.s + r0, s);
+    else if (a.store_s) store_n<T, W>(a.s + r0, s);
     if (MODE == 0 && PK == SIPB_SET_DISTANCE) {
       // the distance term holds s = x and m in registers: the stop / log sums of PARSDMM.jl:140-145 ride along
       // (same expressions as k_stop); slot layout: d[1] ||x_old-x||^2, d[2] ||x||^2, last slot ||x-m||^2
@@ -940,7 +941,9 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
   } else {
     T v[W];
     load_n<T, W>(a.y + r0, v);
-    load_n<T, W>(a.s + r0, s);
+    // s = A x again (the same left fold as in pass 1, bit for bit): a gather of N words from x instead of a stored
+    // and re-read M-vector (M = 3N for the TV sets)
+    op_forward_n<T, W>(a.op, (unsigned)r0, a.x, s);
     load_n<T, W>(a.l + r0, lo);
     if (relaxed || ADAPT) load_n<T, W>(a.y_old + r0, yo);
 #pragma unroll

@@ -2166,10 +2166,14 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         if (++n_multi == kYlMulti) flush_multi();
       } else {
         ya.want_feas = 0;
+        // s = A x is stored only when the in-loop feasibility check reads it afterwards (every 10th iteration) or the
+        // operator is an explicit sparse matrix (its s buffer IS the input of the fused kernels)
+        ya.store_s = (want_feas && !S.is_sparse) ? 1 : 0;
         LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), c->grid_fit((const void*)k_yl<T, 1, false>, nvecM), ya, c->rs,
                c->d_scal + base + 10);
-        c->account(KC_YL_PASS1, colsB + (3 + (!(gamma[s] == (T)1) ? 1 : 0)) * rowsB);     // x, l (, y_old) -> v, s
-        c->account(KC_YL_PASS2, (5 + (needs_yold ? 1 : 0)) * rowsB + adaptB);             // v, s, l (, y_old) -> y, l
+        // pass 1: x, l (, y_old) -> v (, s);   pass 2: v, x, l (, y_old) -> y, l
+        c->account(KC_YL_PASS1, colsB + (2 + (!(gamma[s] == (T)1) ? 1 : 0) + ya.store_s) * rowsB);
+        c->account(KC_YL_PASS2, colsB + (4 + (needs_yold ? 1 : 0)) * rowsB + adaptB);
         int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
         if (rc) return rc;
         ya.dyn = S.pp_y.p;
