@@ -8,6 +8,7 @@
 """
 import collections
 import csv
+import os
 import sys
 
 FULL_COLS = [
@@ -22,7 +23,8 @@ FULL_COLS = [
 
 CLASS_OF = [   # kernel class of the library's table (sipb_kernel_class_name) <- kernel function prefix
     ("yl_update_fused", "k_yl_multi<"), ("yl_update_pass1", "k_yl<float, 1,"), ("yl_update_pass2", "k_yl<float, 2,"),
-    ("cds_spmv_dot", "k_spmv<float, 1>"), ("cg_init", "k_cg_init<"), ("cg_update_xr", "k_cg_xr<"),
+    ("cds_spmv_dot", "k_spmv<float, 1>"), ("cds_spmv_dot", "k_spmv_tile<float, 1,"), ("cg_init", "k_cg_init<"),
+    ("cg_init", "k_spmv_tile<float, 2,"), ("cg_update_xr", "k_cg_xr<"),
     ("cg_update_p", "k_cg_p<"), ("rhs_compose", "k_rhs<"), ("stop_reduce", "k_stop<"), ("l1_threshold_pass", "k_l1_pass<"),
 ]
 
@@ -61,10 +63,11 @@ def launches(path, traffic_json=None, grid=None):
     print("\ntotal %.1f us over %d launches" % (tot / 1e3, sum(len(v["ids"]) for v in agg.values())))
     if traffic_json and has_dram:
         import json
-        out = {"grid": grid, "source": path, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged "
+        out = {"workload": os.environ.get("SIPB_TRAFFIC_WORKLOAD", "config3"), "grid": grid, "source": path, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged "
                "over all launches of the kernel class in the launch list (cold-cache, serialised replays)", "kernels": {}}
-        for cls, prefix in CLASS_OF:
-            sel = [v for k, v in agg.items() if k.startswith(prefix)]
+        for cls in dict.fromkeys(c for c, _ in CLASS_OF):
+            prefixes = [pf for c, pf in CLASS_OF if c == cls]
+            sel = [v for k, v in agg.items() if any(k.startswith(pf) for pf in prefixes)]
             n = sum(len(v["ids"]) for v in sel)
             if n:
                 out["kernels"][cls] = {"dram_bytes_per_launch": sum(v["rd"] + v["wr"] for v in sel) / n, "launches": n,
