@@ -34,8 +34,13 @@ class Projector:
         self.min = lo
         self.max = hi
         self.k = int(k)
-        self.min_vec = None if lo_vec is None else np.ascontiguousarray(lo_vec, dtype=self.TF)
-        self.max_vec = None if hi_vec is None else np.ascontiguousarray(hi_vec, dtype=self.TF)
+        # private copies: the device problem built from this projector is cached and keyed on these arrays, so a caller
+        # who later changes the bound vectors in place must not silently keep the stale device copy
+        self.min_vec = None if lo_vec is None else np.array(lo_vec, dtype=self.TF, order="C", copy=True)
+        self.max_vec = None if hi_vec is None else np.array(hi_vec, dtype=self.TF, order="C", copy=True)
+        for v in (self.min_vec, self.max_vec):
+            if v is not None:
+                v.setflags(write=False)
         self.name = name
 
     def descriptor(self, op_kind=_lib.OP_IDENTITY, block_mode=_lib.BLOCK_PLAIN, ncvx=False) -> _lib.SetDesc:

@@ -1503,8 +1503,10 @@ struct Problem : sipb_problem {
       const bool peer = sg.on && c->p2p;
       const int g_l1 = c->grid_fit((const void*)k_l1_pass<T>, (M + Vec<T>::W - 1) / Vec<T>::W);
       unsigned long long* mk = c->d_tie_counts;
-      if (c->graph_loops && !c->profile && !sg.on) {
-        // the whole search as one graph launch: begin -> WHILE { pass } -> end -> lv-1 cap (device-side decisions only)
+      if (c->graph_loops && !c->profile && (!sg.on || (peer && c->d_big))) {
+        // the whole search as one graph launch: begin -> WHILE { pass [, step] } -> end -> lv-1 cap (device-side
+        // decisions only; on slabs the pass publishes its partial (C, S) to the peers' mailboxes, k_l1_step collects
+        // them and decides, and the cap's minimum is a small peer all-reduce every rank takes part in)
         LoopGraph& lg = S.l1_graphs[{(const void*)v, (const void*)stats, (const void*)warm, (const void*)pp}];
         if (!lg.exec) {
           rc = build_loop_graph(
@@ -1514,13 +1516,20 @@ struct Problem : sipb_problem {
                 return SIPB_OK;
               },
               [&](const LoopCond& lc) {
-                LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, g_l1, M, (const T*)v, c->rs, c->d_l1, 1, c->cd_off, lc);
+                if (fused) {
+                  LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, g_l1, M, (const T*)v, c->rs, c->d_l1, 1, c->cd_off, lc);
+                } else {
+                  const LoopCond off{0, 0};
+                  LAUNCH(c, KC_L1_PASS, k_l1_pass<T>, g_l1, M, (const T*)v, c->rs, c->d_l1, 0, c->cd_on, off);
+                  LAUNCH1(c, KC_PARAMS, k_l1_step, c->d_l1, c->cd_on, lc);
+                }
                 return SIPB_OK;
               },
               [&]() {
                 LAUNCH1(c, KC_PARAMS, k_l1_end<T>, c->d_l1, warm, pp);
                 if (cudaMemsetAsync(mk, 0xff, sizeof(unsigned long long), c->stream) != cudaSuccess) return SIPB_E_CUDA;
                 LAUNCH(c, KC_L1_PASS, k_absmin_key<T>, c->grid_for(M), M, (const T*)v, mk, (const L1State*)c->d_l1);
+                if (sg.on) { int r2 = c->allreduce_min_u64(mk, 1); if (r2) return r2; }
                 LAUNCH1(c, KC_PARAMS, k_l1_cap<T>, c->d_l1, (const unsigned long long*)mk, pp);
                 return SIPB_OK;
               });
