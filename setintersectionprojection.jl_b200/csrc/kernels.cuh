@@ -745,7 +745,8 @@ struct ProjDev {
   const T* lo_vec;   // vector bounds
   const T* hi_vec;
   const T* m;        // distance term: the vector being projected
-  unsigned td[3];    // fiber bounds: transform-domain grid
+  unsigned td[3];    // fiber bounds: transform-domain grid (rank-local on slabs)
+  unsigned td_kofs;  //   slabs: global index of local plane 0 (the bounds of a z fiber are indexed by the global plane)
   int fiber_axis;
   T rho;             // distance term / prox_l1: current rho
   // parameters produced by the reduction passes:
@@ -792,7 +793,7 @@ __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
       const unsigned q = (unsigned)r;
       unsigned c = q % P.td[0];
       if (P.fiber_axis == 1) c = (q / P.td[0]) % P.td[1];
-      else if (P.fiber_axis == 2) c = q / (P.td[0] * P.td[1]);
+      else if (P.fiber_axis == 2) c = q / (P.td[0] * P.td[1]) + P.td_kofs;
       return t_min<T>(t_max<T>(v, P.lo_vec[c]), P.hi_vec[c]);       // project_bounds!.jl:46,50,65-77
     }
     case SIPB_SET_CARD_SLICE:

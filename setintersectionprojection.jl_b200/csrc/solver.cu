@@ -969,6 +969,7 @@ struct SetT {
   }
   SparseDev<T> sparse;        // SIPB_OP_SPARSE: the explicit operator (op is then the identity over the s buffer)
   bool is_sparse = false;
+  unsigned td_kofs = 0;       // slabs, fiber modes: global index of the first local plane of the transform-domain grid
   DevBuf<T> ata;              // [nd][ld]   (released once the stencil-class table has been verified)
   DevBuf<T> ata_tab;          // [kMaxClasses][nd] stencil-class form of AtA
   int nd = 0;
@@ -1125,8 +1126,17 @@ struct Problem : sipb_problem {
     const bool fiber = d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_CARD_FIBER ||
                        d->set_kind == SIPB_SET_CARD_SLICE;
     if (fiber) {
-      SIPB_REQUIRE(!sg.on && !minkowski, SIPB_E_UNSUPPORTED, "fiber modes are single-GPU, non-Minkowski");
+      SIPB_REQUIRE(!minkowski, SIPB_E_UNSUPPORTED, "fiber modes are not available for Minkowski problems");
       SIPB_REQUIRE(d->fiber_axis >= 0 && d->fiber_axis < ndim, SIPB_E_INVALID, "fiber axis outside the grid");
+      // slabs cut the slowest axis: everything that stays inside a plane works rank-locally — per-fiber bounds along
+      // any axis (element-wise; the bound of a z fiber is indexed by the GLOBAL plane), per-fiber cardinality along x / y,
+      // per-slice cardinality of z slices (= planes).  Fibers / slices that cross slabs would need a distributed select.
+      if (sg.on) {
+        SIPB_REQUIRE(!(d->set_kind == SIPB_SET_CARD_FIBER && d->fiber_axis == 2), SIPB_E_UNSUPPORTED,
+                     "per-fiber cardinality along the slab axis is single-GPU (the fibers cross the slabs)");
+        SIPB_REQUIRE(!(d->set_kind == SIPB_SET_CARD_SLICE && d->fiber_axis != 2), SIPB_E_UNSUPPORTED,
+                     "per-slice cardinality of x / y slices is single-GPU (the slices cross the slabs)");
+      }
       SIPB_REQUIRE(d->op_kind != SIPB_OP_TV, SIPB_E_INVALID,
                    "fiber modes need a single-block operator (the TV output is not a grid)");
     }
@@ -1171,9 +1181,15 @@ struct Problem : sipb_problem {
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->warm.p, 0, 2 * sizeof(double), ctx->stream));
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->pp_y.p, 0, sizeof(ProjParams<T>), ctx->stream));
     SIPB_CUDA_CHECK(cudaMemsetAsync(S->pp_f.p, 0, sizeof(ProjParams<T>), ctx->stream));
-    if (fiber)
-      SIPB_REQUIRE(d->td_n[0] * d->td_n[1] * d->td_n[2] == S->M && d->td_n[0] >= 1 && d->td_n[1] >= 1 && d->td_n[2] >= 1,
+    if (fiber) {
+      SIPB_REQUIRE(d->td_n[0] * d->td_n[1] * d->td_n[2] == S->Mglob && d->td_n[0] >= 1 && d->td_n[1] >= 1 && d->td_n[2] >= 1,
                    SIPB_E_INVALID, "td_n does not match the rows of the operator");
+      if (sg.on) {     // the rank-local transform-domain grid: this rank's planes of the (single) row block
+        SIPB_REQUIRE(S->M % (d->td_n[0] * d->td_n[1]) == 0, SIPB_E_INVALID, "slab rows are not whole planes of td_n");
+        S->desc.td_n[2] = S->M / (d->td_n[0] * d->td_n[1]);
+        S->td_kofs = (unsigned)sg.k0;
+      }
+    }
     if (d->set_kind == SIPB_SET_HISTOGRAM) { rc = S->alloc_hist(S->M); if (rc) return rc; }
     if (d->set_kind == SIPB_SET_BOUNDS_VECTOR || d->set_kind == SIPB_SET_BOUNDS_FIBER || d->set_kind == SIPB_SET_HISTOGRAM) {
       SIPB_REQUIRE(d->min_vec && d->max_vec, SIPB_E_INVALID, "vector bounds need min_vec and max_vec");
@@ -1454,6 +1470,7 @@ struct Problem : sipb_problem {
     P.m = m.p;
     for (int a = 0; a < 3; ++a) P.td[a] = (unsigned)std::max<int64_t>(S.desc.td_n[a], 1);
     P.fiber_axis = S.desc.fiber_axis;
+    P.td_kofs = S.td_kofs;
     P.rho = (S.desc.set_kind == SIPB_SET_PROX_L1) ? (T)S.desc.max : rho_dist;
     P.theta = (T)-1; P.scale = (T)1; P.fill = (T)NAN; P.key_thr = 0ull; P.keep_all = 1; P.keep_none = 0;
     return P;

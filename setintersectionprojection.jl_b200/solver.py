@@ -83,7 +83,8 @@ def build_device_problem(TF, AtA, TD_OP, set_Prop, P_sub, comp_grid, options, ct
             keep = None
             if i < pp:
                 d = P_sub[i].descriptor(TD_OP[i].op_kind, TD_OP[i].block_mode, set_Prop.ncvx[i])
-                if slab is not None and P_sub[i].min_vec is not None:      # vector bounds: this rank's rows only
+                if slab is not None and P_sub[i].min_vec is not None and P_sub[i].set_kind == _lib.SET_BOUNDS_VECTOR:
+                    # vector bounds: this rank's rows only (fiber bounds are indexed by the fiber coordinate: whole vector)
                     keep = (dd.scatter_td(P_sub[i].min_vec, TD_OP[i], *slab), dd.scatter_td(P_sub[i].max_vec, TD_OP[i], *slab))
                     d.min_vec, d.max_vec = keep[0].ctypes.data, keep[1].ctypes.data
             else:

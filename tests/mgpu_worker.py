@@ -76,6 +76,36 @@ def main():
             print("[mgpu %d ranks] %-14s %s iters=%d/%d relerr_x=%.2e %s" % (
                 world, name, "OK " if good else "FAIL", len(ls.obj), len(lo.obj), relerr(xs, xo),
                 "" if good else str({k: v for k, v in checks.items() if not v})), flush=True)
+    # fiber / slice application modes whose fibers stay inside a plane (SURVEY §8f-1 on slabs): per-fiber bounds along z
+    # (indexed by the global plane), per-fiber cardinality along x on D_x, per-slice cardinality of the z slices
+    for TF in (np.float32, np.float64):
+        n, d = (20, 16, 13), (25.0, 25.0, 12.5)
+        m = pr.synthetic_model(n, TF)
+        lo_v, hi_v = np.linspace(1400.0, 1700.0, n[2]), np.linspace(3200.0, 4700.0, n[2])
+        res = []
+        for api in ([sip] if rank else [sip, orc]):
+            cg = api.compgrid(d, n)
+            cons = [api.set_definitions("bounds", "identity", lo_v.copy(), hi_v.copy(), ("fiber", "z")),
+                    api.set_definitions("cardinality", "D_x", 0, 5, ("fiber", "x")),
+                    api.set_definitions("cardinality", "D_y", 0, 90, ("slice", "z"))]
+            opt = api.PARSDMM_options()
+            opt.FL, opt.maxit = TF, 25
+            P_sub, TD_OP, set_Prop = api.setup_constraints(cons, cg, TF)
+            TD_OP, AtA, l0, y0 = api.PARSDMM_precompute_distribute(TD_OP, set_Prop, cg, opt)
+            out = api.PARSDMM(m.copy(), AtA, TD_OP, set_Prop, P_sub, cg, opt)
+            if api is sip:
+                out = out[:3] + ([dd.gather_td(v, A) for v, A in zip(out[3], TD_OP)],)
+            res.append(out)
+        if rank == 0:
+            (xs, ls, _, yg), (xo, lo, _, yy) = res
+            checks = {"iters": len(ls.obj) == len(lo.obj), "cg_it": bool(np.array_equal(ls.cg_it, lo.cg_it)),
+                      "x": relerr(xs, xo) < TOL[TF],
+                      "support": bool(np.array_equal(yg[1] != 0, yy[1] != 0) and np.array_equal(yg[2] != 0, yy[2] != 0))}
+            good = all(checks.values())
+            ok = ok and good
+            print("[mgpu %d ranks] %-14s %s iters=%d/%d relerr_x=%.2e %s" % (
+                world, "fiber_" + np.dtype(TF).name, "OK " if good else "FAIL", len(ls.obj), len(lo.obj), relerr(xs, xo),
+                "" if good else str({k: v for k, v in checks.items() if not v})), flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.destroy_process_group()
