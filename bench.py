@@ -222,7 +222,7 @@ def run_reference(args, rank, world):
     cores = cpu_threads()
     vals, secs = [], []
     t_start = time.perf_counter()
-    budget_s = float(os.environ.get("SIPB_REFERENCE_BUDGET_S", "240"))      # keep the whole arm within a few minutes
+    budget_s = float(os.environ.get("SIPB_REFERENCE_BUDGET_S", "200"))      # keep the whole arm within a few minutes
     warm = min(args.warmup, 1)       # one warm-up builds and caches the operators (outside PARSDMM in the reference too)
     last = None
     for s in range(warm + args.steps):

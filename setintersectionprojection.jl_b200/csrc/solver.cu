@@ -425,11 +425,15 @@ __global__ void __launch_bounds__(kThreads) k_tie_count_p(i64 M, const T* __rest
 }
 // totals[b] = number of threshold ties in row block b of this rank (slabs)
 __global__ void k_tie_totals(const unsigned long long* counts, int nblk, int g, int stride, unsigned long long* totals) {
-  for (int b = 0; b < 4; ++b) {       // launched with a single thread
+  // one warp: lanes stride over the per-block counts of each row block
+  const int lane = threadIdx.x & 31;
+  for (int b = 0; b < 4; ++b) {
     unsigned long long t = 0;
     if (b < nblk)
-      for (int i = 0; i < g; ++i) t += counts[b * stride + i];
-    totals[b] = t;
+      for (int i = lane; i < g; i += 32) t += counts[b * stride + i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) totals[b] = t;
   }
 }
 
@@ -1620,8 +1624,8 @@ struct Problem : sipb_problem {
                  0, 1, 0);
         } else {
           // index-ordered ties across slabs: per row block tie totals are all-gathered (4 x world counters)
-          const int g = c->max_grid() / 4;
           const int nb = S.op.kind == SIPB_OP_IDENTITY ? 1 : S.op.nblk;
+          const int g = std::min(c->max_grid(), kMaxBlocks / nb);       // the count table holds kMaxBlocks entries
           for (int b = 0; b < nb; ++b) {
             const i64 Mb = S.op.row_start[b + 1] - S.op.row_start[b];
             const i64 chunk = ((std::max<i64>(Mb, 1) + g - 1) / g + kThreads - 1) / kThreads * kThreads;
@@ -1629,7 +1633,9 @@ struct Problem : sipb_problem {
           }
           // all-gather of the 4 per-block totals == sum-all-reduce of a [world][4] table in which a rank fills its row
           SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_gather, 0, sizeof(unsigned long long) * 4 * c->world, c->stream));
-          LAUNCH1(c, KC_TIES, k_tie_totals, c->d_tie_counts, nb, g, g, c->d_gather + 4 * c->rank);
+          c->pre_launch(KC_TIES);
+          k_tie_totals<<<1, 32, 0, c->stream>>>(c->d_tie_counts, nb, g, g, c->d_gather + 4 * c->rank);
+          c->post_launch();
           rc = c->allreduce_u64(c->d_gather, (size_t)4 * c->world);
           if (rc) return rc;
           for (int b = 0; b < nb; ++b) {
