@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_spmv(SpmvArgs<T> a, RedScratch 
   const T* tab = spmv_stage_table<T>(a, tab_s);
   double d[1] = {0.0};
   const i64 nvec = a.N / VW;
-  if (cd.on) {
+  if (cd.on && (a.x_lo || a.x_hi)) {
     // rows within one plane (= max |offset|) of the slab ends read the neighbours' p: only the blocks that
     // own such rows wait for the neighbours' version flag
     i64 halo = 0;
@@ -383,8 +383,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(SpmvArgs<T> a, const T* __
   }
   if (grid_sum<2>(d, rs, sys)) {
     if (cd.on) {
-      mail_publish<2>(cd, d);
-      if (threadIdx.x == 0) p_publish(cd);      // p = r has been (re)written
+      mail_publish<2>(cd, d);                   // (the boundary planes of r were fenced at system scope: k_p_halo_init reads them)
     } else if (threadIdx.x == 0) {
       st->bb = d[0];
       st->rr = d[1];
@@ -441,6 +440,17 @@ __global__ void k_cg_init_fin(CgState* st, const __grid_constant__ CommDev cd, L
     loop_set(lc, false);
   }
 }
+// Slabs, peer path: p = r on the halo planes too (cg.jl:77 on the neighbours' rows): copies the neighbours' boundary
+// planes of r into the local halo planes of p.  Runs after k_cg_init_fin, i.e. after every rank's prologue has
+// published its partial sums — their r is complete and fenced.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_p_halo_init(i64 N, i64 halo, T* __restrict__ p, const T* __restrict__ r_lo,
+                                                          const T* __restrict__ r_hi, i64 n_lo) {
+  for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < halo; q += (i64)gridDim.x * blockDim.x) {
+    if (r_lo) p[q - halo] = __ldcg(r_lo + (n_lo - halo + q));
+    if (r_hi) p[N + q] = __ldcg(r_hi + q);
+  }
+}
 // cg.jl:47: x = zeros when the right-hand side is zero (flag -9); runs after the loop, returns at once otherwise
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_zero_x(i64 N, T* __restrict__ x, const CgState* st) {
@@ -452,7 +462,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_zero_x(i64 N, T* __restrict__ x
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T* __restrict__ r,
                                                     const T* __restrict__ p, const T* __restrict__ Ap,
-                                                    RedScratch rs, CgState* st, const __grid_constant__ CommDev cd) {
+                                                    RedScratch rs, CgState* st, const __grid_constant__ CommDev cd,
+                                                    i64 halo) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
   if (cd.on) mail_collect_all<1>(cd, &st->pAp);      // peer path: sum the ranks' partials of p.Ap
@@ -488,7 +499,13 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
       r[row] = rv;
     }
   }
-  if (grid_sum<1>(d, rs)) {
+  bool sys = false;
+  if (cd.on) {                 // the neighbours read the boundary planes of r (k_cg_p): those blocks fence at system scope
+    bool lo, hi;
+    block_touches_ends(N, halo, VW, lo, hi);
+    sys = lo || hi;
+  }
+  if (grid_sum<1>(d, rs, sys)) {
     if (bad) {
       if (threadIdx.x == 0) {
         st->flag = -2;          // "Matrix A in cg has to be positive definite"
@@ -509,7 +526,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ r, T* __restrict__ p,
                                                    RedScratch rs, CgState* st, const __grid_constant__ CommDev cd,
-                                                   i64 halo, LoopCond lc) {
+                                                   i64 halo, LoopCond lc, const T* __restrict__ r_lo,
+                                                   const T* __restrict__ r_hi, i64 n_lo) {
   if (st->done) {               // k_cg_xr found alpha < 0 / Inf (cg.jl:91): the loop ends here
     if (blockIdx.x == 0 && threadIdx.x == 0) loop_set(lc, false);
     return;
@@ -538,14 +556,18 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
     for (i64 row = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; row < N;
          row += (i64)gridDim.x * blockDim.x)
       p[row] = r[row] + beta * p[row];
+    // Slabs, peer path: the halo planes of p are updated HERE, redundantly, with the same expression — from the
+    // neighbour's boundary plane of r (read over NVLink; complete on every rank once the r.r partials have been
+    // collected above) and the local halo copy of the old p.  The SpMV then finds all of p in local memory: no
+    // p-halo transfer, no version flag, one rendezvous less per CG iteration (bit-identical: same beta, same operands).
+    if (r_lo)
+      for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < halo; q += (i64)gridDim.x * blockDim.x)
+        p[q - halo] = __ldcg(r_lo + (n_lo - halo + q)) + beta * p[q - halo];
+    if (r_hi)
+      for (i64 q = (i64)blockIdx.x * blockDim.x + threadIdx.x; q < halo; q += (i64)gridDim.x * blockDim.x)
+        p[N + q] = __ldcg(r_hi + q) + beta * p[N + q];
   }
-  bool sys = false;
-  if (cd.on) {
-    bool lo, hi;
-    block_touches_ends(N, halo, VW, lo, hi);
-    sys = lo || hi;              // only boundary rows of p are read by the neighbours
-  }
-  if (last_block_ticket(rs.counter, sys) && threadIdx.x == 0) {
+  if (last_block_ticket(rs.counter, false) && threadIdx.x == 0) {
     st->iter = it;
     st->loops = st->loops + 1;
     st->relres = (double)res;
@@ -558,7 +580,6 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
     } else {
       st->rr = rr_new;
       st->rr_new = rr_new;
-      if (cd.on) p_publish(cd);               // p has been rewritten: release it to the neighbours
     }
     loop_set(lc, !(conv || last_it));
   }

@@ -1008,9 +1008,11 @@ struct Problem : sipb_problem {
   bool m_resident = false;
   SlabGeom sg;                // active when the ctx has a communicator with world > 1
   // peer path: p lives in an IPC-exported allocation; the neighbours' p are mapped here
-  T* p_shared = nullptr;      // owned start of the exported p vector (null => pvec)
-  const T* p_lo = nullptr;    // lower / upper neighbour's p (owned start)
-  const T* p_hi = nullptr;
+  // peer path: the CG residual r lives in an IPC-exported allocation; the neighbours' r are mapped here (k_cg_p reads
+  // their boundary planes to update the local halo planes of p)
+  T* r_shared = nullptr;      // owned start of the exported r vector (null => r)
+  const T* r_lo = nullptr;    // lower / upper neighbour's r (owned start)
+  const T* r_hi = nullptr;
   void* p_lo_base = nullptr;
   void* p_hi_base = nullptr;
   i64 n_lo = 0;
@@ -1021,7 +1023,8 @@ struct Problem : sipb_problem {
     if (p_lo_base) cudaIpcCloseMemHandle(p_lo_base);
     if (p_hi_base) cudaIpcCloseMemHandle(p_hi_base);
   }
-  T* pv() { return p_shared ? p_shared : pvec.p; }
+  T* pv() { return pvec.p; }
+  T* rv() { return r_shared ? r_shared : r.p; }
   // Export this rank's p vector and import the neighbours' (collective over all ranks).
   int setup_peer_p() {
     sipb_ctx* c = ctx;
@@ -1038,18 +1041,18 @@ struct Problem : sipb_problem {
     std::vector<cudaIpcMemHandle_t> all(c->world);
     int rc = c->allgather_bytes(&mine, all.data(), sizeof(mine));
     if (rc) return rc;
-    SIPB_REQUIRE(ok, SIPB_E_CUDA, "could not export the p vector for the peer path");
+    SIPB_REQUIRE(ok, SIPB_E_CUDA, "could not export the r vector for the peer path");
     c->shared_bufs.push_back(base);
-    p_shared = reinterpret_cast<T*>(base) + fpad;
+    r_shared = reinterpret_cast<T*>(base) + fpad;
     if (sg.has_lo) {
       SIPB_CUDA_CHECK(cudaIpcOpenMemHandle(&p_lo_base, all[c->rank - 1], cudaIpcMemLazyEnablePeerAccess));
-      p_lo = reinterpret_cast<const T*>(p_lo_base) + fpad;
+      r_lo = reinterpret_cast<const T*>(p_lo_base) + fpad;
       const i64 k0l = n[2] * (c->rank - 1) / c->world, k1l = n[2] * c->rank / c->world;
       n_lo = sg.plane * (k1l - k0l);
     }
     if (sg.has_hi) {
       SIPB_CUDA_CHECK(cudaIpcOpenMemHandle(&p_hi_base, all[c->rank + 1], cudaIpcMemLazyEnablePeerAccess));
-      p_hi = reinterpret_cast<const T*>(p_hi_base) + fpad;
+      r_hi = reinterpret_cast<const T*>(p_hi_base) + fpad;
     }
     return SIPB_OK;
   }
@@ -1458,9 +1461,8 @@ struct Problem : sipb_problem {
   }
   // SpMV on p with the neighbours' planes read through peer pointers
   SpmvArgs<T> spmv_args_peer(T* yout) {
-    SpmvArgs<T> a = spmv_args(pv(), yout);
-    if (p_shared) { a.x_lo = p_lo; a.x_hi = p_hi; a.n_lo = n_lo; }
-    return a;
+    // the halo planes of p are local on every path: NCCL fills them, or k_cg_p computes them from the neighbours' r
+    return spmv_args(pv(), yout);
   }
 
   ProjDev<T> proj_static(const SetT<T>& S, T rho_dist) const {
@@ -1701,7 +1703,8 @@ struct Problem : sipb_problem {
     SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->parsdmm_it, &h->parsdmm_it, sizeof(int), cudaMemcpyHostToDevice, c->stream));
     if (parsdmm_it == 0)
       SIPB_CUDA_CHECK(cudaMemcpyAsync(&c->d_cg->tol, &h->tol, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    const bool peer = p_shared != nullptr;            // peer-memory collectives instead of NCCL inside the CG
+    const bool peer = r_shared != nullptr;            // peer-memory collectives instead of NCCL inside the CG
+    T* rr = rv();
     const CommDev& cd = peer ? c->cd_on : c->cd_off;
     T* pp = pv();
     const i64 nvecN = (N + Vec<T>::W - 1) / Vec<T>::W;
@@ -1712,14 +1715,16 @@ struct Problem : sipb_problem {
     // r = b - Qx, p = r, x_old = x, tolerance rule / early exits        (argmin_x.jl:33-37, cg.jl:47-76)
     auto launch_init = [&](const LoopCond& lc) -> int {
       if (tiled) {
-        const TileInit<T> ti{b, r.p, pp, x_old_out};
+        const TileInit<T> ti{b, rr, pp, x_old_out};
         if ((rc = launch_tile<T, 2>(c, KC_CG_INIT, tile, false, spmv_args(xv, nullptr), ti, nullptr, nullptr, c->d_cg, cd)))
           return rc;
       } else {
-        LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, r.p, pp, x_old_out, c->rs, c->d_cg, cd);
+        LAUNCH(c, KC_CG_INIT, k_cg_init<T>, g_init, spmv_args(xv, nullptr), b, rr, pp, x_old_out, c->rs, c->d_cg, cd);
       }
       if (!peer && (rc = c->allreduce(&c->d_cg->bb, 2))) return rc;          // bb, rr are adjacent
       LAUNCH1(c, KC_CG_FIN, k_cg_init_fin<T>, c->d_cg, cd, lc);
+      if (peer)      // p = r on the halo planes: the neighbours' boundary planes of r (complete: their partials were collected)
+        LAUNCH(c, KC_CG_INIT, k_p_halo_init<T>, c->grid_for(sg.plane), N, sg.plane, pp, r_lo, r_hi, n_lo);
       return SIPB_OK;
     };
     // one CG iteration                                                  (cg.jl:84-114)
@@ -1733,9 +1738,10 @@ struct Problem : sipb_problem {
         LAUNCH(c, KC_SPMV_DOT, (k_spmv<T, true>), g_mv, spmv_args_peer(Ap.p), c->rs, &c->d_cg->pAp, done_flag, cd);
       }
       if (!peer && (rc = c->allreduce(&c->d_cg->pAp, 1))) return rc;      // peer path: collected inside k_cg_xr
-      LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g_xr, N, xv, r.p, pp, Ap.p, c->rs, c->d_cg, cd);
+      LAUNCH(c, KC_CG_XR, k_cg_xr<T>, g_xr, N, xv, rr, pp, Ap.p, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0);
       if (!peer && (rc = c->allreduce(&c->d_cg->rr_new, 1))) return rc;   // peer path: collected inside k_cg_p
-      LAUNCH(c, KC_CG_P, k_cg_p<T>, g_p, N, r.p, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0, lc);
+      LAUNCH(c, KC_CG_P, k_cg_p<T>, g_p, N, (const T*)rr, pp, c->rs, c->d_cg, cd, sg.on ? sg.plane : (i64)0, lc,
+             peer ? r_lo : (const T*)nullptr, peer ? r_hi : (const T*)nullptr, n_lo);
       return SIPB_OK;
     };
     const double vecN = (double)N * sizeof(T);
@@ -2129,7 +2135,7 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
     {
       // device-side loop (one graph launch, no host poll) unless the kernel table is being profiled or the slabs
       // use NCCL inside the CG
-      const bool loop_on_device = c->graph_loops && !c->profile && (!sg.on || p_shared != nullptr);
+      const bool loop_on_device = c->graph_loops && !c->profile && (!sg.on || r_shared != nullptr);
       int rc = run_cg(rhs.p, x.p, x_old.p, i, 0.0, 1000, last_cg + 1, &cg_it, &cg_relres, &cg_flag,
                       loop_on_device ? &cg_deferred : nullptr);
       if (rc) return rc;

@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, kTileMinCtas)
       else if (threadIdx.x == 0 && out_dot) out_dot[0] = d1[0];
     }
   } else if (MODE == 2) {
-    // only CTAs that wrote boundary planes of p need the system-scope fence (the neighbours read those planes)
+    // only CTAs that wrote boundary planes of r need the system-scope fence (the neighbours read those planes)
     bool sys = false;
     if (cd.on) {
       for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -466,7 +466,6 @@ __global__ void __launch_bounds__(kThreads, kTileMinCtas)
     if (grid_sum<2>(dsum, rs, sys)) {
       if (cd.on) {
         mail_publish<2>(cd, dsum);
-        if (threadIdx.x == 0) p_publish(cd);
       } else if (threadIdx.x == 0) {
         st->bb = dsum[0];
         st->rr = dsum[1];
