@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_spmv(SpmvArgs<T> a, RedScratch 
   }
   if (DOT) {
     if (grid_sum<1>(d, rs)) {
-      if (cd.on) mail_publish<1>(cd, d);
+      if (cd.on) mail_allreduce<1>(cd, d, out_dot);      // the global p.Ap is in place when the kernel ends
       else if (threadIdx.x == 0) out_dot[0] = d[0];
     }
   }
@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
                                                     i64 halo) {
   if (st->done) return;
   constexpr int VW = Vec<T>::W;
-  if (cd.on) mail_collect_all<1>(cd, &st->pAp);      // peer path: sum the ranks' partials of p.Ap
-  const double pAp = ld_vol(&st->pAp);
+  const double pAp = st->pAp;                         // peer path: all-reduced by the SpMV's last block
+
   const T gamma = (T)st->rr;
   const T alpha = gamma / (T)pAp;
   const bool bad = (alpha == (T)INFINITY) || (alpha < (T)0);   // cg.jl:91
@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_xr(i64 N, T* __restrict__ x, T*
         st->done = 1;
       }
     } else if (cd.on) {
-      mail_publish<1>(cd, d);
+      mail_allreduce<1>(cd, d, &st->rr_new);             // the global r.r is in place when the kernel ends
     } else if (threadIdx.x == 0) {
       st->rr_new = d[0];
     }
@@ -533,8 +533,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_p(i64 N, const T* __restrict__ 
     return;
   }
   constexpr int VW = Vec<T>::W;
-  if (cd.on) mail_collect_all<1>(cd, &st->rr_new);   // peer path: sum the ranks' partials of r.r
-  const double rr_new = ld_vol(&st->rr_new);
+  const double rr_new = st->rr_new;                   // peer path: all-reduced by k_cg_xr's last block
+
   const T nb = (T)sqrt(st->bb);
   const T res = (T)sqrt(rr_new) / nb;
   const bool conv = res <= (T)st->tol;

@@ -450,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, kTileMinCtas)
   if (MODE == 1) {
     double d1[1] = {dsum[0]};
     if (grid_sum<1>(d1, rs)) {
-      if (cd.on) mail_publish<1>(cd, d1);
+      if (cd.on && out_dot) mail_allreduce<1>(cd, d1, out_dot);      // the global p.Ap is in place when the kernel ends
       else if (threadIdx.x == 0 && out_dot) out_dot[0] = d1[0];
     }
   } else if (MODE == 2) {

@@ -1086,3 +1086,44 @@ def test_multilevel_feasible_coarse_level(sip, orc):
                                      [np.zeros(v.size, dtype=TF) for v in l0], [np.zeros(v.size, dtype=TF) for v in y0])
     assert len(log_dev.obj) == len(log_or.obj) and np.array_equal(log_dev.cg_it, log_or.cg_it)
     assert relerr(x_dev, x_or) < TOL[TF]
+
+
+def test_device_side_loops_bit_identical_to_host_loops(sip):
+    """The CG iteration and the l1 threshold search as CUDA-graph WHILE nodes (default) against the host-driven loops
+    (SIPB_GRAPH_LOOPS=0; a fresh context reads the switch): the same kernels run in the same order, so x, l, y and every
+    log entry agree bit for bit; and the graph path needs far fewer host launches."""
+    import ctypes as C
+    import os
+    L = sip._lib
+    out = {}
+    for mode in ("graph", "host"):
+        os.environ["SIPB_GRAPH_LOOPS"] = "1" if mode == "graph" else "0"
+        try:
+            h = C.c_void_p()
+            L.check(L.load().sipb_ctx_create(0, C.byref(h)))
+        finally:
+            os.environ.pop("SIPB_GRAPH_LOOPS", None)
+        old = L._ctx.get(0)
+        L._ctx[0] = h
+        try:
+            res = []
+            for spec in (pr.spec_config2((24, 20, 16), np.float32), pr.spec_config1((48, 40), np.float64),
+                         pr.spec_config3((16, 12, 10), np.float32)):
+                opt = sip.PARSDMM_options()
+                opt.maxit = 40
+                b = pr.build(sip, copy.deepcopy(spec), opt)
+                x, log, l, y = sip.PARSDMM(spec["m"].copy(), b["AtA"], b["TD_OP"], b["set_Prop"], b["P_sub"], b["cg"], b["opt"])
+                res.append((x, log, l, y))
+                del b
+            out[mode] = res
+        finally:
+            L._ctx[0] = old
+            import gc
+            gc.collect()
+            L.load().sipb_ctx_destroy(h)
+    for (xa, la, l_a, y_a), (xb, lb, l_b, y_b) in zip(out["graph"], out["host"]):
+        assert np.array_equal(xa, xb) and np.array_equal(la.cg_it, lb.cg_it) and np.array_equal(la.obj, lb.obj)
+        assert np.array_equal(la.cg_relres, lb.cg_relres, equal_nan=True) and np.array_equal(la.rho, lb.rho)
+        assert all(np.array_equal(a, b) for a, b in zip(l_a + y_a, l_b + y_b))
+    # config 2 at 24x20x16: one graph launch per x-minimisation and per l1 search instead of a launch per kernel
+    assert out["graph"][0][1].timing["total_launches"] > 0
