@@ -1613,7 +1613,9 @@ struct Problem : sipb_problem {
         if (!fused) {
           rc = c->allreduce_u64(c->d_sel->hist, 256);
           if (rc) return rc;
-          LAUNCH1(c, KC_PARAMS, k_radix_pick, c->d_sel);
+          c->pre_launch(KC_PARAMS);
+          k_radix_pick<<<1, 256, 0, c->stream>>>(c->d_sel);
+          c->post_launch();
         }
       }
       LAUNCH1(c, KC_PARAMS, k_sel_end<T>, c->d_sel, pp);
