@@ -777,6 +777,13 @@ struct ProjDev {
   unsigned long long key_thr;   // cardinality: smallest kept magnitude key
   int keep_all;      // cardinality: k >= M
   int keep_none;     // cardinality: k <= 0
+  // cardinality, deferred tie handling (y/l pass 2 on a single GPU): entries equal to the threshold are zeroed here when
+  // all ties of their row chunk lie beyond the quota (tie_base[chunk] >= quota); the one chunk the quota boundary
+  // falls into was handled in place by k_tie_cross.  tie_base == null: ties were already zeroed in place.
+  const unsigned long long* tie_base;
+  long long tie_chunk;
+  unsigned long long quota;
+  int need_ties;
 };
 
 template <typename T> __device__ __forceinline__ unsigned long long mag_key(T v);
@@ -839,7 +846,12 @@ __device__ __forceinline__ T proj_apply(const ProjDev<T>& P, T v, i64 r) {
     case SIPB_SET_CARDINALITY:     // zero everything below the k-th largest magnitude
       if (P.keep_all) return v;
       if (P.keep_none) return (T)0;
-      return (mag_key<T>(v) >= P.key_thr) ? v : (T)0;
+      {
+        const unsigned long long key = mag_key<T>(v);
+        if (key != P.key_thr) return (key > P.key_thr) ? v : (T)0;
+        if (P.need_ties && P.tie_base && P.tie_base[r / P.tie_chunk] >= P.quota) return (T)0;
+        return v;
+      }
     default:
       return v;
   }
@@ -850,6 +862,20 @@ __host__ __device__ __forceinline__ bool proj_is_elementwise(int kind) {
          kind == SIPB_SET_DISTANCE ||
          kind == SIPB_SET_PROX_L1;
 }
+
+// cardinality search (defined with the radix select below): digit histograms that pass 1 of the y/l update
+// accumulates on the side while it produces v
+constexpr int kSelBins = 2048;          // bins of one level (2^11)
+constexpr int kSpecBits = 11;           // digit width of the speculative histograms built by pass 1 of the y/l update
+constexpr int kSpecLevels = 3;          // levels covered speculatively (all of a Float32 key, the top 33 bits of a Float64 key)
+struct SpecCtx {
+  unsigned int* sh;               // shared-memory histograms of levels 1 .. kSpecLevels-1
+  unsigned long long guess;       // threshold key of the previous PARSDMM iteration
+  unsigned int g0;                // its top digit
+  unsigned int above;             // this thread's count of keys whose top digit exceeds the guess's
+};
+template <typename T>
+__device__ __forceinline__ void spec_hist_add(SpecCtx& sc, T v);
 
 // =============================================================================================
 // y / l update                               (update_y_l.jl:39-94)
@@ -909,7 +935,8 @@ template <typename T, int W> __device__ __forceinline__ void store_n(T* p, const
 // d[]: MODE 0/2: [0] ||y-s||^2, [1] ||P(s)-s||^2, [2] ||s||^2 ; MODE 1: [0] sum|v|, [1] sum v^2, [2] nnz(v)
 //      ADAPT   : [3] dot(dH,dlh) [4] ||dH||^2 [5] ||dlh||^2 [6] ||dl||^2 [7] ||dG||^2 [8] dot(dG,dl)
 template <typename T, int MODE, bool ADAPT, int W, int PK>
-__device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P, i64 r0, double* d) {
+__device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P, i64 r0, double* d,
+                                        SpecCtx* spec = nullptr) {
   const T rho = a.rho, gamma = a.gamma;
   const T rho1 = (T)1.0 / rho;                      // update_y_l.jl:34
   const bool relaxed = !(gamma == (T)1);
@@ -938,6 +965,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
         d[0] += (double)t_abs<T>(v);
         d[1] += (double)v * (double)v;
         d[2] += (v != (T)0) ? 1.0 : 0.0;
+        if (spec) spec_hist_add<T>(*spec, v);                      // k_yl_spec only
       }
     }
     store_n<T, W>(a.y + r0, yn);
@@ -1019,13 +1047,14 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
 // out: [0..2] as d[0..2] (MODE 2 writes only [0]); ADAPT sums go to out[4..9]
 // PK: compile-time set kind of the specialised instances (-1: read the kind from the descriptor)
 template <typename T, int MODE, bool ADAPT, int PK>
-__device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs, double* out) {
+__device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs, double* out, SpecCtx* spec = nullptr) {
   constexpr int VW = Vec<T>::W;
   constexpr int NR = (ADAPT ? 9 : 3) + (MODE == 0 ? 1 : 0);      // MODE 0: one more slot for the fused stop sums
   ProjDev<T> P = a.P;
   if (a.dyn) {
     P.theta = a.dyn->theta; P.scale = a.dyn->scale; P.fill = a.dyn->fill;
     P.key_thr = a.dyn->key_thr; P.keep_all = a.dyn->keep_all; P.keep_none = a.dyn->keep_none;
+    P.quota = a.dyn->quota; P.need_ties = a.dyn->need_ties;
   }
   double d[NR];
 #pragma unroll
@@ -1033,9 +1062,9 @@ __device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs
   const i64 M = a.op.rows;
   const i64 nvec = M / VW;
   for (i64 iv = (i64)blockIdx.x * blockDim.x + threadIdx.x; iv < nvec; iv += (i64)gridDim.x * blockDim.x)
-    yl_rows<T, MODE, ADAPT, VW, PK>(a, P, iv * VW, d);
+    yl_rows<T, MODE, ADAPT, VW, PK>(a, P, iv * VW, d, spec);
   for (i64 r = nvec * VW + (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x)
-    yl_rows<T, MODE, ADAPT, 1, PK>(a, P, r, d);
+    yl_rows<T, MODE, ADAPT, 1, PK>(a, P, r, d, spec);
   if (grid_sum<NR>(d, rs) && threadIdx.x == 0) {
     out[0] = d[0];
     if (MODE != 2) {
@@ -1059,6 +1088,37 @@ __global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlAr
   // one dispatch on the set kind per block: the common kinds run fully specialised bodies
   if (MODE == 2 && a.P.kind == SIPB_SET_L1) yl_body<T, MODE, ADAPT, SIPB_SET_L1>(a, rs, out);
   else yl_body<T, MODE, ADAPT, -1>(a, rs, out);
+}
+
+// Pass 1 of a vector-mode cardinality set on a single GPU: as k_yl<T, 1, false>, and the first levels of the radix
+// select ride along (spec_hist_add): a per-thread count and shared-memory histograms per block, flushed into
+// SelState::spec_above / spec at the end.  `guess_pp` holds the threshold key of the previous iteration (any value is a
+// valid guess).
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4) k_yl_spec(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out,
+                                                         unsigned long long* __restrict__ spec_above,
+                                                         unsigned long long* __restrict__ spec,
+                                                         const ProjParams<T>* __restrict__ guess_pp) {
+  constexpr int NB = (kSpecLevels - 1) * kSelBins;
+  __shared__ unsigned int sh[NB];
+  __shared__ unsigned int s_above[kThreads / 32];
+  for (int t = threadIdx.x; t < NB; t += blockDim.x) sh[t] = 0u;
+  __syncthreads();
+  const unsigned long long guess = guess_pp->key_thr;
+  SpecCtx sc{sh, guess, (unsigned)(guess >> ((int)sizeof(T) * 8 - kSpecBits)), 0u};
+  yl_body<T, 1, false, -1>(a, rs, out, &sc);
+  unsigned int ab = sc.above;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ab += __shfl_xor_sync(0xffffffffu, ab, o);
+  if ((threadIdx.x & 31) == 0) s_above[threadIdx.x >> 5] = ab;
+  __syncthreads();
+  for (int t = threadIdx.x; t < NB; t += blockDim.x)
+    if (sh[t]) atomicAdd(&spec[t], (unsigned long long)sh[t]);
+  if (threadIdx.x == 0) {
+    unsigned long long tot = 0ull;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) tot += s_above[i];
+    if (tot) atomicAdd(spec_above, tot);
+  }
 }
 
 // All element-wise sets of one PARSDMM iteration in a single launch: blockIdx.y selects the set, every set
@@ -1422,104 +1482,167 @@ __global__ void __launch_bounds__(kThreads) k_absmin_key(i64 M, const T* __restr
 }
 
 // =============================================================================================
-// cardinality: radix select of the k-th largest magnitude key (8-bit digits, MSB first)
+// cardinality: radix select of the k-th largest magnitude key (MSB-first digits of `dbits` bits:
+// 11 on a single GPU — 3 levels for Float32 keys —, 8 on slabs where every level's histogram is all-reduced)
 // =============================================================================================
 struct SelState {
   unsigned long long prefix;      // digits decided so far (high bits)
   unsigned long long k_rem;       // rank still to locate inside the current prefix bucket (1-based)
   unsigned long long count_eq;    // elements whose key == final threshold
-  unsigned long long hist[256];
-  int shift;                      // bit position of the digit to examine next (>= 0), -8 when finished
+  unsigned long long hist[kSelBins];
+  unsigned long long spec_above;                     // speculation (k_yl_spec): keys whose top digit exceeds the guess's,
+  unsigned long long spec[(kSpecLevels - 1) * kSelBins];   //   histograms of levels 1.. ; consumed and cleared by k_sel_begin
+  int bits_left;                  // undecided low bits of the key; <= 0 when finished
   int key_bits;
+  int dbits;                      // digit width of this search
+  int table_valid;                // the last level's per-block histograms are in the tie table (single GPU)
 };
 
-// choose the digit bucket that contains the k_rem-th largest key among the current prefix bucket
-__device__ __forceinline__ void radix_pick(SelState* st) {
-  const int shift = st->shift;
-  if (shift < 0) return;
-  unsigned long long k = st->k_rem, cum = 0;
-  int bin = 0;
-  for (int b = 255; b >= 0; --b) {
-    const unsigned long long c = st->hist[b];
-    if (cum + c >= k) {
-      bin = b;
-      break;
-    }
-    cum += c;
-  }
-  st->k_rem = k - cum;
-  st->count_eq = st->hist[bin];
-  st->prefix = (st->prefix << 8) | (unsigned long long)bin;
-  st->shift = shift - 8;
-  for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
-}
-
-// The same with the 256 threads of a block (every thread calls it): bins are loaded and cleared in parallel, the
-// "k-th largest" bucket is found with a block-wide scan from the top bin down.  (One thread walking 256 global counters
-// and clearing them took ~10 us; with slabs that kernel runs four times per projection on the critical path.)
-__device__ __forceinline__ void radix_pick_block(SelState* st) {
+// Choose the digit bucket that contains the k_rem-th largest key among the current prefix bucket, from the level
+// histogram `h` (cleared on the way).  Called by all 256 threads of a block: every thread takes 2^w / 256 consecutive
+// bins from the top down, a block-wide scan finds the thread whose bins hold the k-th largest key.
+__device__ __forceinline__ void radix_pick_block(SelState* st, unsigned long long* h) {
   __shared__ unsigned long long s_wsum[8];
-  __shared__ int s_shift;
+  __shared__ int s_bl;
   const int t = threadIdx.x;                       // blockDim.x == 256
-  if (t == 0) s_shift = st->shift;
+  if (t == 0) s_bl = st->bits_left;
   __syncthreads();
-  const int shift = s_shift;
-  if (shift < 0) return;
+  const int bl = s_bl;
+  if (bl <= 0) return;                             // block-uniform
+  const int w = min(st->dbits, bl);                // 8 <= w <= 11
+  const int per = (1 << w) >> 8;                   // bins per thread: 1, 2, 4 or 8
   const unsigned long long k = st->k_rem;
-  const int bin = 255 - t;                         // thread t looks at bins from the top down
-  const unsigned long long h = st->hist[bin];
-  st->hist[bin] = 0ull;
-  // inclusive scan of h over t (bins 255, 254, ...)
-  unsigned long long incl = h;
-  const int lane = t & 31, w = t >> 5;
+  const int top = (1 << w) - 1 - t * per;
+  unsigned long long c[8];
+  unsigned long long sum = 0ull;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    c[j] = 0ull;
+    if (j < per) {
+      c[j] = h[top - j];
+      h[top - j] = 0ull;
+      sum += c[j];
+    }
+  }
+  unsigned long long incl = sum;                   // inclusive scan over t (bins from the top down)
+  const int lane = t & 31, wp = t >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += up;
   }
-  if (lane == 31) s_wsum[w] = incl;
-  __syncthreads();
+  if (lane == 31) s_wsum[wp] = incl;
+  __syncthreads();                                 // (also orders every thread's read of k_rem before the winner's write)
   unsigned long long base = 0ull;
-  for (int q = 0; q < w; ++q) base += s_wsum[q];
+  for (int q = 0; q < wp; ++q) base += s_wsum[q];
   incl += base;
-  const unsigned long long excl = incl - h;        // keys in strictly higher bins
-  if (incl >= k && excl < k) {                     // exactly one thread: the bucket that holds the k-th largest key
-    st->k_rem = k - excl;
-    st->count_eq = h;
-    st->prefix = (st->prefix << 8) | (unsigned long long)bin;
-    st->shift = shift - 8;
+  const unsigned long long excl = incl - sum;      // keys in strictly higher bins than this thread's
+  if (incl >= k && excl < k) {                     // exactly one thread
+    unsigned long long cum = excl;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (j < per) {
+        if (cum + c[j] >= k) {
+          st->k_rem = k - cum;
+          st->count_eq = c[j];
+          st->prefix = (st->prefix << w) | (unsigned long long)(top - j);
+          st->bits_left = bl - w;
+          break;
+        }
+        cum += c[j];
+      }
+    }
   }
+  __syncthreads();                                 // the state and the scratch may be reused by a following call
 }
 
+// One level of the search: histogram of the next digit over the keys that match the decided prefix.
+// chunk > 0 (single GPU): block b owns rows [b*chunk, (b+1)*chunk) — the partition of the tie kernels —, and the last
+//   level leaves its per-block histogram in `table[b][*]`: the per-block tie counts are then a look-up (k_tie_count_p).
+// chunk == 0 (slabs): grid-stride.
 // fused != 0: the last block also picks the digit (single GPU); with slabs the histogram is all-reduced
 // first and k_radix_pick runs afterwards.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_radix_hist(i64 M, const T* __restrict__ v, SelState* st,
-                                                         unsigned int* counter, int fused) {
-  __shared__ unsigned int sh[256];
-  const int shift = st->shift;
-  if (shift < 0) return;
+                                                         unsigned int* counter, int fused, i64 chunk,
+                                                         unsigned int* __restrict__ table) {
+  __shared__ unsigned int sh[kSelBins];
+  const int bl = st->bits_left;
+  if (bl <= 0) return;
+  const int w = min(st->dbits, bl), shift = bl - w, nb = 1 << w;
+  const unsigned long long mask = (unsigned long long)(nb - 1);
   const unsigned long long prefix = st->prefix;
-  const int hi_shift = shift + 8;
-  const bool all_match = hi_shift >= st->key_bits;
-  for (int t = threadIdx.x; t < 256; t += blockDim.x) sh[t] = 0u;
+  const bool all_match = bl >= st->key_bits;
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) sh[t] = 0u;
   __syncthreads();
-  for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (i64)gridDim.x * blockDim.x) {
-    const unsigned long long key = mag_key<T>(v[r]);
-    const bool match = all_match ? true : ((key >> hi_shift) == prefix);
-    if (match) atomicAdd(&sh[(unsigned)((key >> shift) & 0xffull)], 1u);
+  i64 lo = (i64)blockIdx.x * blockDim.x, hi = M, step = (i64)gridDim.x * blockDim.x;
+  if (chunk > 0) {
+    lo = (i64)blockIdx.x * chunk;
+    hi = min(M, lo + chunk);
+    step = blockDim.x;
+  }
+  auto add = [&](T val) {
+    const unsigned long long key = mag_key<T>(val);
+    const bool match = all_match ? true : ((key >> bl) == prefix);
+    if (match) atomicAdd(&sh[(unsigned)((key >> shift) & mask)], 1u);
+  };
+  if (chunk > 0 && (reinterpret_cast<unsigned long long>(v) & 15ull) == 0ull) {
+    // a chunk starts on a multiple of 256 rows: 16-byte loads, every block streams 4 KB per step
+    constexpr int VW = Vec<T>::W;
+    const i64 nv = (hi - lo) / VW;
+    for (i64 iv = threadIdx.x; iv < nv; iv += blockDim.x) {
+      T x4[VW];
+      vload<T>(v + lo + iv * VW, x4);
+#pragma unroll
+      for (int e = 0; e < VW; ++e) add(x4[e]);
+    }
+    for (i64 r = lo + nv * VW + threadIdx.x; r < hi; r += blockDim.x) add(v[r]);
+  } else {
+    for (i64 r = lo + threadIdx.x; r < hi; r += step) add(v[r]);
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < 256; t += blockDim.x)
+  for (int t = threadIdx.x; t < nb; t += blockDim.x)
     if (sh[t]) atomicAdd(&st->hist[t], (unsigned long long)sh[t]);
+  const bool keep = table != nullptr && chunk > 0 && shift == 0;
+  if (keep)
+    for (int t = threadIdx.x; t < nb; t += blockDim.x) table[(size_t)blockIdx.x * kSelBins + t] = sh[t];
   if (fused) {
     if (last_block_ticket(counter)) {
       __threadfence();
-      radix_pick_block(st);
+      if (keep && threadIdx.x == 0) st->table_valid = 1;
+      radix_pick_block(st, st->hist);
     }
   }
 }
-__global__ void __launch_bounds__(256) k_radix_pick(SelState* st) { radix_pick_block(st); }
+__global__ void __launch_bounds__(256) k_radix_pick(SelState* st) { radix_pick_block(st, st->hist); }
+
+// Speculative levels of the cardinality search, accumulated by pass 1 of the y/l update while it produces v (k_yl_spec),
+// around `guess` = the previous PARSDMM iteration's threshold.  Level 0 is not histogrammed at all (one shared-memory
+// atomic per row, mostly on a handful of bins, cost 0.2 ms per 512^3 pass): the rows whose top digit EXCEEDS the guess's
+// are counted in a register, and level j > 0 histograms digit j of the keys whose higher digits equal the guess's — a
+// few per cent of the rows.  The threshold lies in the guess's top-digit bucket iff  above < k <= above + |bucket|
+// (|bucket| = the total of the level-1 histogram); k_sel_begin then walks the levels for as long as the digits it
+// decides agree with the guess, and the remaining levels run as ordinary k_radix_hist passes.  Exactness does not depend
+// on the guess: a wrong guess only costs the passes it was meant to save.
+template <typename T> struct NativeKey { typedef unsigned long long type; };
+template <> struct NativeKey<float> { typedef unsigned int type; };       // Float32 keys: 32-bit integer arithmetic
+template <typename T>
+__device__ __forceinline__ void spec_hist_add(SpecCtx& sc, T v) {
+  typedef typename NativeKey<T>::type K;
+  constexpr int KB = (int)sizeof(T) * 8;
+  const K key = (K)mag_key<T>(v), guess = (K)sc.guess;
+  const unsigned d0 = (unsigned)(key >> (KB - kSpecBits));
+  sc.above += (d0 > sc.g0) ? 1u : 0u;
+  if (d0 == sc.g0) {
+#pragma unroll
+    for (int lv = 1; lv < kSpecLevels; ++lv) {
+      const int bl = KB - kSpecBits * lv;                       // bits left at this level (> 0 for both key widths)
+      const int w = bl < kSpecBits ? bl : kSpecBits;
+      if (lv == 1 || (key >> bl) == (guess >> bl))
+        atomicAdd(&sc.sh[(lv - 1) * kSelBins + (unsigned)((key >> (bl - w)) & (K)((1 << w) - 1))], 1u);
+    }
+  }
+}
 
 // nearest-neighbour resampling of a column-major box (multilevel warm starts): sample k of an axis reads source
 // index floor(pos + 1/2) - 1 with pos = 1 + k (ns-1)/(nd-1), evaluated in exact integer arithmetic

@@ -156,6 +156,9 @@ struct sipb_ctx {
   L1State* h_l1 = nullptr;
   SelState* d_sel = nullptr;
   unsigned long long* d_tie_counts = nullptr;
+  unsigned long long* d_tie_base = nullptr;   // [kMaxBlocks] exclusive prefix of d_tie_counts (deferred tie handling)
+  unsigned int* d_sel_table = nullptr;   // [max_grid()][kSelBins] per-block histograms of the last select level (tie counts)
+  bool sel_spec = true;                  // speculative select levels inside pass 1 of the y/l update (SIPB_SEL_SPEC=0: off)
   unsigned int* d_counter2 = nullptr;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -378,20 +381,74 @@ __global__ void k_l2_params(const double* stats, int kind, double smin, double s
   }
 }
 
+// 256 threads.  spec != 0: pass 1 of the y/l update (k_yl_spec) left speculative histograms of the first levels in
+// st->spec, built around the guess pp->key_thr (the previous iteration's threshold, still in place): levels are
+// consumed for as long as the digits decided so far agree with the guess.
 template <typename T>
-__global__ void k_sel_begin(long long k, long long M, SelState* st, ProjParams<T>* pp) {
-  pp->keep_all = (k >= M) ? 1 : 0;
-  pp->keep_none = (k <= 0) ? 1 : 0;
-  pp->need_ties = 0;
-  pp->key_thr = 0ull;
-  pp->quota = 0ull;
-  pp->count_eq = 0ull;
-  st->key_bits = (int)(sizeof(T) * 8);
-  st->prefix = 0ull;
-  st->k_rem = (unsigned long long)(k > 0 ? k : 0);
-  st->count_eq = 0ull;
-  for (int b = 0; b < 256; ++b) st->hist[b] = 0ull;
-  st->shift = (pp->keep_all || pp->keep_none) ? -8 : st->key_bits - 8;
+__global__ void __launch_bounds__(256) k_sel_begin(long long k, long long M, SelState* st, ProjParams<T>* pp, int dbits,
+                                                   int spec) {
+  __shared__ unsigned long long s_guess;
+  if (threadIdx.x == 0) {
+    s_guess = pp->key_thr;
+    pp->keep_all = (k >= M) ? 1 : 0;
+    pp->keep_none = (k <= 0) ? 1 : 0;
+    pp->need_ties = 0;
+    pp->key_thr = 0ull;
+    pp->quota = 0ull;
+    pp->count_eq = 0ull;
+    st->key_bits = (int)(sizeof(T) * 8);
+    st->dbits = dbits;
+    st->prefix = 0ull;
+    st->k_rem = (unsigned long long)(k > 0 ? k : 0);
+    st->count_eq = 0ull;
+    st->table_valid = 0;
+    st->bits_left = (pp->keep_all || pp->keep_none) ? 0 : st->key_bits;
+  }
+  for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) st->hist[b] = 0ull;
+  __syncthreads();
+  if (!spec) return;
+  const unsigned long long guess = s_guess;
+  constexpr int KB = (int)sizeof(T) * 8;
+  // level 0: the threshold lies in the guess's top-digit bucket iff  above < k <= above + |bucket|
+  {
+    __shared__ unsigned long long s_part[8];
+    __shared__ int s_hit;
+    unsigned long long mine = 0ull;
+    for (int b = threadIdx.x; b < kSelBins; b += blockDim.x) mine += st->spec[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long bucket = 0ull;
+      for (int i = 0; i < 8; ++i) bucket += s_part[i];
+      const unsigned long long above = st->spec_above, kk = st->k_rem;
+      s_hit = 0;
+      if (st->bits_left == KB && above < kk && kk <= above + bucket) {
+        st->prefix = guess >> (KB - kSpecBits);
+        st->k_rem = kk - above;
+        st->count_eq = bucket;
+        st->bits_left = KB - kSpecBits;
+        s_hit = 1;
+      }
+      st->spec_above = 0ull;
+    }
+    __syncthreads();
+    if (s_hit) {
+      for (int lv = 1; lv < kSpecLevels; ++lv) {
+        __shared__ int s_go;
+        if (threadIdx.x == 0) {
+          const int bl = st->bits_left;             // level lv was histogrammed for bl == KB - lv * kSpecBits
+          s_go = (bl == KB - lv * kSpecBits) && st->prefix == (guess >> bl);
+        }
+        __syncthreads();
+        if (!s_go) break;                           // block-uniform
+        radix_pick_block(st, st->spec + (size_t)(lv - 1) * kSelBins);
+      }
+    }
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < (kSpecLevels - 1) * kSelBins; b += blockDim.x) st->spec[b] = 0ull;
 }
 template <typename T>
 __global__ void k_sel_end(SelState* st, ProjParams<T>* pp) {
@@ -405,9 +462,19 @@ __global__ void k_sel_end(SelState* st, ProjParams<T>* pp) {
 // wrappers that read the tie parameters from device memory (no host round trip)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_tie_count_p(i64 M, const T* __restrict__ v, const ProjParams<T>* pp,
-                                                          i64 chunk, unsigned long long* counts) {
+                                                          i64 chunk, unsigned long long* counts, const SelState* st,
+                                                          const unsigned int* __restrict__ table) {
   if (!pp->need_ties) return;
   const unsigned long long key = pp->key_thr;
+  if (st && table && st->table_valid) {
+    // the last level of the search ran over the same row partition and kept its per-block histograms: the number of
+    // keys equal to the threshold in this block's rows is the entry of the threshold's last digit
+    int wl = st->key_bits % st->dbits;
+    if (wl == 0) wl = st->dbits;
+    if (threadIdx.x == 0)
+      counts[blockIdx.x] = (unsigned long long)table[(size_t)blockIdx.x * kSelBins + (unsigned)(key & (unsigned long long)((1 << wl) - 1))];
+    return;
+  }
   const i64 lo = (i64)blockIdx.x * chunk, hi = min(M, lo + chunk);
   unsigned int c = 0;
   for (i64 r = lo + threadIdx.x; r < hi; r += blockDim.x) c += (mag_key<T>(v[r]) == key) ? 1u : 0u;
@@ -437,6 +504,77 @@ __global__ void k_tie_totals(const unsigned long long* counts, int nblk, int g, 
   }
 }
 
+// Deferred tie handling (single GPU, y/l update): one block of 1024 threads turns the per-chunk tie counts into their
+// exclusive prefix `base` (read by pass 2 through ProjDev::tie_base) and settles the one chunk the quota boundary falls
+// into in place — every thread walks a contiguous piece of that chunk, the pieces are ranked by a block scan, ties of
+// rank >= quota become zero (stable order = index order, project_cardinality!.jl:18-19 with a stable sortperm).
+template <typename T>
+__global__ void __launch_bounds__(1024) k_tie_cross(i64 M, T* __restrict__ v, const ProjParams<T>* pp, i64 chunk, int g,
+                                                    const unsigned long long* __restrict__ counts,
+                                                    unsigned long long* __restrict__ base) {
+  if (!pp->need_ties) return;
+  __shared__ unsigned long long s_warp[32];
+  __shared__ unsigned long long s_cross_base;
+  __shared__ int s_cross;
+  const unsigned long long key = pp->key_thr, quota = pp->quota;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  if (t == 0) s_cross = -1;
+  // exclusive prefix of counts[0..g): thread t owns `per` consecutive chunks
+  const int per = (g + 1023) / 1024;
+  unsigned long long mine = 0ull;
+  for (int j = 0; j < per; ++j) {
+    const int b = t * per + j;
+    if (b < g) mine += counts[b];
+  }
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  unsigned long long off = 0ull;
+  for (int q = 0; q < w; ++q) off += s_warp[q];
+  unsigned long long run = off + incl - mine;
+  for (int j = 0; j < per; ++j) {
+    const int b = t * per + j;
+    if (b < g) {
+      const unsigned long long nb = counts[b];
+      base[b] = run;
+      if (run < quota && run + nb > quota) { s_cross = b; s_cross_base = run; }     // at most one chunk
+      run += nb;
+    }
+  }
+  __syncthreads();
+  const int cb = s_cross;
+  if (cb < 0) return;                                  // the boundary falls between two chunks: nothing to do in place
+  const i64 lo = (i64)cb * chunk, hi = min(M, lo + chunk);
+  const i64 len = (hi - lo + 1023) / 1024;
+  const i64 a0 = min(hi, lo + (i64)t * len), a1 = min(hi, a0 + len);
+  unsigned long long c = 0ull;
+  for (i64 r = a0; r < a1; ++r) c += (mag_key<T>(v[r]) == key) ? 1ull : 0ull;
+  incl = c;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  __syncthreads();                                     // s_warp is reused
+  if (lane == 31) s_warp[w] = incl;
+  __syncthreads();
+  off = 0ull;
+  for (int q = 0; q < w; ++q) off += s_warp[q];
+  unsigned long long rank = s_cross_base + off + incl - c;
+  if (rank + c <= quota) return;                       // all ties of this piece are kept
+  for (i64 r = a0; r < a1; ++r) {
+    if (mag_key<T>(v[r]) == key) {
+      if (rank >= quota) v[r] = (T)0;
+      ++rank;
+    }
+  }
+}
+
 // `gather` (slabs): all-gathered totals [world][4]; the global index order of the reference's vector is
 // row-block major, planes (= ranks) ascending inside a block, so the ties that precede this rank's
 // block `blk` are all ties of earlier blocks plus those of lower ranks in the same block.
@@ -447,23 +585,31 @@ __global__ void __launch_bounds__(kThreads) k_tie_zero_p(i64 M, T* __restrict__ 
                                                          int world, int blk) {
   if (!pp->need_ties) return;
   const unsigned long long key = pp->key_thr, quota = pp->quota;
-  __shared__ unsigned long long s_base;
+  __shared__ unsigned long long s_part[32];
   __shared__ unsigned int s_warp[32];
-  if (threadIdx.x == 0) {
-    unsigned long long b = 0;
-    if (gather) {
-      for (int bb = 0; bb < blk; ++bb)
-        for (int r = 0; r < world; ++r) b += gather[r * 4 + bb];
-      for (int r = 0; r < rank; ++r) b += gather[r * 4 + blk];
-    }
-    for (unsigned i = 0; i < blockIdx.x; ++i) b += counts[i];
-    s_base = b;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // ties that precede this block's rows: the block sums the counts of the lower blocks in parallel (one thread walking
+  // ~1000 counters took 0.5 ms on the last blocks)
+  unsigned long long b = 0;
+  if (threadIdx.x == 0 && gather) {
+    for (int bb = 0; bb < blk; ++bb)
+      for (int r = 0; r < world; ++r) b += gather[r * 4 + bb];
+    for (int r = 0; r < rank; ++r) b += gather[r * 4 + blk];
   }
+  for (unsigned i = threadIdx.x; i < blockIdx.x; i += blockDim.x) b += counts[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+  if (lane == 0) s_part[w] = b;
   __syncthreads();
-  unsigned long long base = s_base;
+  unsigned long long base = 0ull;
+  for (int i = 0; i < nw; ++i) base += s_part[i];
   if (base + counts[blockIdx.x] <= quota) return;
   const i64 lo = (i64)blockIdx.x * chunk, hi = min(M, lo + chunk);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (base >= quota) {            // every tie of this block's rows lies beyond the quota: no ranking needed
+    for (i64 r = lo + threadIdx.x; r < hi; r += blockDim.x)
+      if (mag_key<T>(v[r]) == key) v[r] = (T)0;
+    return;
+  }
   for (i64 t0 = lo; t0 < hi; t0 += blockDim.x) {
     const i64 r = t0 + threadIdx.x;
     const bool tie = (r < hi) && (mag_key<T>(v[r]) == key);
@@ -1513,7 +1659,10 @@ struct Problem : sipb_problem {
   // Computes the dynamic parameters of a reduction-type projector for the vector `v` whose stats
   // (sum|v|, sum v^2, nnz) sit in d_scal[stat_slot..].  No host synchronisation except the polling
   // of the l1 Newton iteration.
-  int projector_params(SetT<T>& S, T* v, int stat_slot, ProjParams<T>* pp, double* warm, bool allow_tie_zero) {
+  // tie_defer (single GPU, cardinality): instead of zeroing the surplus ties in place, leave the per-chunk prefix in
+  // d_tie_base for the consumer (pass 2 of the y/l update) and return the chunk length through *tie_defer
+  int projector_params(SetT<T>& S, T* v, int stat_slot, ProjParams<T>* pp, double* warm, bool allow_tie_zero,
+                       bool spec = false, i64* tie_defer = nullptr) {
     sipb_ctx* c = ctx;
     const int kind = S.desc.set_kind;
     const i64 M = S.M;               // rank-local rows
@@ -1606,11 +1755,22 @@ struct Problem : sipb_problem {
     } else if (kind == SIPB_SET_L2 || kind == SIPB_SET_ANNULUS) {
       LAUNCH1(c, KC_PARAMS, k_l2_params<T>, stats, kind, S.desc.min, S.desc.max, (double)Mg, pp);
     } else if (kind == SIPB_SET_CARDINALITY) {
-      LAUNCH1(c, KC_PARAMS, k_sel_begin<T>, (long long)S.desc.k, (long long)Mg, c->d_sel, pp);
-      const int npass = (int)sizeof(T);
-      for (int q = 0; q < npass; ++q) {
-        LAUNCH(c, KC_RADIX_HIST, k_radix_hist<T>, c->grid_for(M), M, v, c->d_sel, c->d_counter2, fused);
-        if (!fused) {
+      // single GPU: 11-bit digits (3 levels for Float32), every level over the row partition of the tie kernels, the last
+      // one keeping its per-block histograms; `spec`: pass 1 of the y/l update already histogrammed the first levels
+      // around the previous threshold (k_yl_spec).  Slabs: 8-bit digits, one small all-reduce per level.
+      const int dbits = sg.on ? 8 : kSpecBits;
+      const int nlev = ((int)sizeof(T) * 8 + dbits - 1) / dbits;
+      const int g_sel = c->max_grid();
+      const i64 chunk_sel = ((M + g_sel - 1) / g_sel + kThreads - 1) / kThreads * kThreads;
+      c->pre_launch(KC_PARAMS);
+      k_sel_begin<T><<<1, 256, 0, c->stream>>>((long long)S.desc.k, (long long)Mg, c->d_sel, pp, dbits, spec ? 1 : 0);
+      c->post_launch();
+      for (int q = 0; q < nlev; ++q) {                // (a level decided by the speculation returns at once)
+        if (fused) {
+          LAUNCH(c, KC_RADIX_HIST, k_radix_hist<T>, g_sel, M, v, c->d_sel, c->d_counter2, 1, chunk_sel, c->d_sel_table);
+        } else {
+          LAUNCH(c, KC_RADIX_HIST, k_radix_hist<T>, c->grid_for(M), M, v, c->d_sel, c->d_counter2, 0, (i64)0,
+                 (unsigned int*)nullptr);
           rc = c->allreduce_u64(c->d_sel->hist, 256);
           if (rc) return rc;
           c->pre_launch(KC_PARAMS);
@@ -1623,9 +1783,19 @@ struct Problem : sipb_problem {
         if (!sg.on) {
           const int g = c->max_grid();
           const i64 chunk = ((M + g - 1) / g + kThreads - 1) / kThreads * kThreads;
-          LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, M, v, pp, chunk, c->d_tie_counts);
-          LAUNCH(c, KC_TIES, k_tie_zero_p<T>, g, M, v, pp, chunk, c->d_tie_counts, (const unsigned long long*)nullptr,
-                 0, 1, 0);
+          LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, M, v, pp, chunk, c->d_tie_counts, (const SelState*)c->d_sel,
+                 (const unsigned int*)c->d_sel_table);
+          if (tie_defer) {
+            // pass 2 of the y/l update zeroes the ties of the chunks beyond the quota boundary (ProjDev::tie_base);
+            // only the chunk the boundary falls into is settled here
+            c->pre_launch(KC_TIES);
+            k_tie_cross<T><<<1, 1024, 0, c->stream>>>(M, v, pp, chunk, g, c->d_tie_counts, c->d_tie_base);
+            c->post_launch();
+            *tie_defer = chunk;
+          } else {
+            LAUNCH(c, KC_TIES, k_tie_zero_p<T>, g, M, v, pp, chunk, c->d_tie_counts, (const unsigned long long*)nullptr,
+                   0, 1, 0);
+          }
         } else {
           // index-ordered ties across slabs: per row block tie totals are all-gathered (4 x world counters)
           const int nb = S.op.kind == SIPB_OP_IDENTITY ? 1 : S.op.nblk;
@@ -1633,7 +1803,8 @@ struct Problem : sipb_problem {
           for (int b = 0; b < nb; ++b) {
             const i64 Mb = S.op.row_start[b + 1] - S.op.row_start[b];
             const i64 chunk = ((std::max<i64>(Mb, 1) + g - 1) / g + kThreads - 1) / kThreads * kThreads;
-            LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, Mb, v + S.op.row_start[b], pp, chunk, c->d_tie_counts + (size_t)b * g);
+            LAUNCH(c, KC_TIES, k_tie_count_p<T>, g, Mb, v + S.op.row_start[b], pp, chunk, c->d_tie_counts + (size_t)b * g,
+                   (const SelState*)nullptr, (const unsigned int*)nullptr);
           }
           // all-gather of the 4 per-block totals == sum-all-reduce of a [world][4] table in which a rank fills its row
           SIPB_CUDA_CHECK(cudaMemsetAsync(c->d_gather, 0, sizeof(unsigned long long) * 4 * c->world, c->stream));
@@ -2209,14 +2380,23 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         // s = A x is stored only when the in-loop feasibility check reads it afterwards (every 10th iteration) or the
         // operator is an explicit sparse matrix (its s buffer IS the input of the fused kernels)
         ya.store_s = (want_feas && !S.is_sparse) ? 1 : 0;
-        LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), c->grid_fit((const void*)k_yl<T, 1, false>, nvecM), ya, c->rs,
-               c->d_scal + base + 10);
+        // vector-mode cardinality on one GPU: the first levels of the radix select ride on pass 1 (k_yl_spec)
+        const bool spec = S.desc.set_kind == SIPB_SET_CARDINALITY && !sg.on && c->sel_spec;
+        if (spec)
+          LAUNCH(c, KC_YL_PASS1, (k_yl_spec<T>), c->grid_fit((const void*)k_yl_spec<T>, nvecM), ya, c->rs,
+                 c->d_scal + base + 10, &c->d_sel->spec_above, c->d_sel->spec, (const ProjParams<T>*)S.pp_y.p);
+        else
+          LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), c->grid_fit((const void*)k_yl<T, 1, false>, nvecM), ya, c->rs,
+                 c->d_scal + base + 10);
         // pass 1: x, l (, y_old) -> v (, s);   pass 2: v, x, l (, y_old) -> y, l
         c->account(KC_YL_PASS1, colsB + (2 + (!(gamma[s] == (T)1) ? 1 : 0) + ya.store_s) * rowsB);
         c->account(KC_YL_PASS2, colsB + (4 + (needs_yold ? 1 : 0)) * rowsB + adaptB);
-        int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true);
+        i64 tie_chunk = 0;
+        const bool defer = S.desc.set_kind == SIPB_SET_CARDINALITY && !sg.on && c->sel_spec;
+        int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true, spec, defer ? &tie_chunk : nullptr);
         if (rc) return rc;
         ya.dyn = S.pp_y.p;
+        if (tie_chunk > 0) { ya.P.tie_base = c->d_tie_base; ya.P.tie_chunk = tie_chunk; }
         if (fuse_adapt)
           LAUNCH(c, KC_YL_PASS2, (k_yl<T, 2, true>), c->grid_fit((const void*)k_yl<T, 2, true>, nvecM), ya, c->rs,
                  c->d_scal + base);
@@ -2473,6 +2653,9 @@ int sipb_ctx_create(int device, sipb_ctx** out) {
   SIPB_CUDA_CHECK(cudaMalloc(&c->d_sel, sizeof(SelState)));
   SIPB_CUDA_CHECK(cudaMemset(c->d_sel, 0, sizeof(SelState)));
   SIPB_CUDA_CHECK(cudaMalloc(&c->d_tie_counts, sizeof(unsigned long long) * kMaxBlocks));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_tie_base, sizeof(unsigned long long) * kMaxBlocks));
+  SIPB_CUDA_CHECK(cudaMalloc(&c->d_sel_table, sizeof(unsigned int) * (size_t)kMaxBlocks * kSelBins));
+  if (const char* e = getenv("SIPB_SEL_SPEC")) c->sel_spec = atoi(e) != 0;
   *out = c;
   return SIPB_OK;
 }
@@ -2485,7 +2668,7 @@ int sipb_ctx_destroy(sipb_ctx* c) {
   for (auto& e : c->phase_events) cudaEventDestroy(e.first);
   cudaFree(c->rs.partials); cudaFree(c->rs.counter); cudaFree(c->rs_multi.partials); cudaFree(c->rs_multi.counter); cudaFree(c->d_counter2); cudaFree(c->d_scal);
   cudaFreeHost(c->h_scal); cudaFree(c->d_cg); cudaFreeHost(c->h_cg); cudaFree(c->d_l1); cudaFreeHost(c->h_l1);
-  cudaFree(c->d_sel); cudaFree(c->d_tie_counts);
+  cudaFree(c->d_sel); cudaFree(c->d_tie_counts); cudaFree(c->d_sel_table); cudaFree(c->d_tie_base);
   for (int q = 0; q < kMaxRanks; ++q)
     if (c->peer_mail_base[q]) cudaIpcCloseMemHandle(c->peer_mail_base[q]);
   for (void* b : c->shared_bufs) cudaFree(b);

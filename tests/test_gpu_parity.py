@@ -906,6 +906,33 @@ def test_baseline_size_config2_200cubed_f32(sip, orc):
     _same_run(_dev_parsdmm(sip, spec, tw), _cpu_parsdmm(orc, spec, tw), np.float32)
 
 
+@pytest.mark.parametrize("TF", [np.float32, np.float64])
+@pytest.mark.parametrize("n,frac,seed", [((72, 60), 0.4, 5), ((96, 64), 0.3, 6), ((333, 257), 0.55, 7), ((640, 512), 0.4, 8),
+                                         ((640, 512), 0.12, 9)])
+def test_parsdmm_cardinality_ties_in_the_loop(sip, orc, TF, n, frac, seed):
+    """Threshold ties inside the y/l update: with an integer-valued model and Q a multiple of the identity the CG scales
+    every entry alike, so in iteration 2 the k-th largest magnitude is shared by hundreds to tens of thousands of rows
+    (708 ties for a quota of 679 at 72 x 60; 52936 for 51431 at 640 x 512) and the stable order of sortperm
+    (project_cardinality!.jl:18-19) decides the support — across many row chunks of the select kernels (speculative
+    levels in pass 1, per-chunk tie prefix applied by pass 2, the chunk on the quota boundary settled in place).
+    Two iterations only: from iteration 3 on, classes that are EQUAL in exact arithmetic are ordered by rounding, and the
+    CPU restatements themselves (NumPy f64acc / native reductions, C port) end in different supports
+    (scratch/tie_sens2.py) — nothing to compare against."""
+    rng = np.random.default_rng(seed)
+    N = int(np.prod(n))
+    m = np.round(rng.standard_normal(N) * 3).astype(TF)
+    k = int(frac * N)
+    spec = dict(n=n, d=(1.0, 1.0), TF=TF, m=m, sets=[("cardinality", "identity", 0, k)], mode="matrix")
+    def tw(o):
+        o.maxit = 2
+    o, s = run_both(sip, orc, spec, tw)
+    assert np.count_nonzero(o[3][0]) == k                          # the ties were cut at the quota, not kept wholesale
+    assert np.array_equal(o[0] != 0, s[0] != 0)                   # support of x
+    for a, b in zip(s[3], o[3]):
+        assert np.array_equal(a != 0, b != 0)                     # support of every y
+    check_parity(o, s, TF)
+
+
 def test_config3_128cubed_f32(sip, orc):
     """BASELINE configs[2] (bounds ∩ TV l1 ∩ cardinality of the gradient) at 128^3, 30 iterations (the CPU oracle's
     sparse set-up and stable sort of 512^3 take tens of minutes; tools/parity_fullsize.py runs larger grids).

@@ -22,7 +22,7 @@ FULL_COLS = [
 
 
 CLASS_OF = [   # kernel class of the library's table (sipb_kernel_class_name) <- kernel function prefix
-    ("yl_update_fused", "k_yl_multi<"), ("yl_update_pass1", "k_yl<float, 1,"), ("yl_update_pass2", "k_yl<float, 2,"),
+    ("yl_update_fused", "k_yl_multi<"), ("yl_update_pass1", "k_yl<float, 1,"), ("yl_update_pass1", "k_yl_spec<"), ("yl_update_pass2", "k_yl<float, 2,"),
     ("cds_spmv_dot", "k_spmv<float, 1>"), ("cds_spmv_dot", "k_spmv_tile<float, 1,"), ("cg_init", "k_cg_init<"),
     ("cg_init", "k_spmv_tile<float, 2,"), ("cg_update_xr", "k_cg_xr<"),
     ("cg_update_p", "k_cg_p<"), ("rhs_compose", "k_rhs<"), ("stop_reduce", "k_stop<"), ("l1_threshold_pass", "k_l1_pass<"),
