@@ -172,7 +172,11 @@ typedef struct sipb_log {
  *   SIPB_SPMV_TILE=0      the CG uses the generic grid-stride SpMV instead of the tiled TMA-staged kernel
  *   SIPB_P2P=0            sipb_comm_init uses NCCL for the CG reductions and halos instead of peer memory
  *   SIPB_FUSE_STOP_OFF=1  sipb_solve reduces the obj / evol_x sums in a separate pass instead of inside the
- *                         distance term's y/l update */
+ *                         distance term's y/l update
+ *   SIPB_GRAPH_LOOPS=0    host-driven CG / l1-search loops instead of CUDA-graph WHILE nodes (same kernels)
+ *   SIPB_SEL_SPEC=0       cardinality sets on one GPU: no speculative select levels inside pass 1 of the y/l
+ *                         update and in-place tie zeroing (the search then runs all its histogram passes)
+ *   SIPB_PEER_ALLREDUCE=0 slabs: NCCL instead of the small peer-memory all-reduces */
 
 /* ---- library / context ------------------------------------------------------------------- */
 int         sipb_abi_version(void);

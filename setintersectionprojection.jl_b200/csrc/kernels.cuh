@@ -1575,10 +1575,14 @@ __global__ void __launch_bounds__(kThreads) k_radix_hist(i64 M, const T* __restr
   const bool all_match = bl >= st->key_bits;
   for (int t = threadIdx.x; t < nb; t += blockDim.x) sh[t] = 0u;
   __syncthreads();
-  i64 lo = (i64)blockIdx.x * blockDim.x, hi = M, step = (i64)gridDim.x * blockDim.x;
+  // rows [lo, hi) of this block, visited with stride `step` after the block's / grid's first pass (chunk > 0: the block's
+  // own contiguous chunk; else grid-stride over all rows); 16-byte loads when the vector is aligned (a chunk starts on a
+  // multiple of 256 rows)
+  i64 lo = 0, hi = M, first = (i64)blockIdx.x * blockDim.x + threadIdx.x, step = (i64)gridDim.x * blockDim.x;
   if (chunk > 0) {
     lo = (i64)blockIdx.x * chunk;
     hi = min(M, lo + chunk);
+    first = threadIdx.x;
     step = blockDim.x;
   }
   auto add = [&](T val) {
@@ -1586,19 +1590,20 @@ __global__ void __launch_bounds__(kThreads) k_radix_hist(i64 M, const T* __restr
     const bool match = all_match ? true : ((key >> bl) == prefix);
     if (match) atomicAdd(&sh[(unsigned)((key >> shift) & mask)], 1u);
   };
-  if (chunk > 0 && (reinterpret_cast<unsigned long long>(v) & 15ull) == 0ull) {
-    // a chunk starts on a multiple of 256 rows: 16-byte loads, every block streams 4 KB per step
-    constexpr int VW = Vec<T>::W;
-    const i64 nv = (hi - lo) / VW;
-    for (i64 iv = threadIdx.x; iv < nv; iv += blockDim.x) {
-      T x4[VW];
-      vload<T>(v + lo + iv * VW, x4);
+  if (hi > lo) {
+    if ((reinterpret_cast<unsigned long long>(v) & 15ull) == 0ull) {
+      constexpr int VW = Vec<T>::W;
+      const i64 nv = (hi - lo) / VW;
+      for (i64 iv = first; iv < nv; iv += step) {
+        T x4[VW];
+        vload<T>(v + lo + iv * VW, x4);
 #pragma unroll
-      for (int e = 0; e < VW; ++e) add(x4[e]);
+        for (int e = 0; e < VW; ++e) add(x4[e]);
+      }
+      for (i64 r = lo + nv * VW + first; r < hi; r += step) add(v[r]);
+    } else {
+      for (i64 r = lo + first; r < hi; r += step) add(v[r]);
     }
-    for (i64 r = lo + nv * VW + threadIdx.x; r < hi; r += blockDim.x) add(v[r]);
-  } else {
-    for (i64 r = lo + threadIdx.x; r < hi; r += step) add(v[r]);
   }
   __syncthreads();
   for (int t = threadIdx.x; t < nb; t += blockDim.x)
