@@ -176,6 +176,9 @@ typedef struct sipb_log {
  *   SIPB_GRAPH_LOOPS=0    host-driven CG / l1-search loops instead of CUDA-graph WHILE nodes (same kernels)
  *   SIPB_SEL_SPEC=0       cardinality sets on one GPU: no speculative select levels inside pass 1 of the y/l
  *                         update and in-place tie zeroing (the search then runs all its histogram passes)
+ *   SIPB_L1_SKIPV=0|2     l1 sets on one GPU: pass 1 of the y/l update always stores v (0) / never stores it and
+ *                         leaves that to the device-gated second launch (2); default 1: skip while the ball was
+ *                         inactive in the previous iteration
  *   SIPB_PEER_ALLREDUCE=0 slabs: NCCL instead of the small peer-memory all-reduces */
 
 /* ---- library / context ------------------------------------------------------------------- */

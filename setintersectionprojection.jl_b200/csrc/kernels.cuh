@@ -904,6 +904,10 @@ struct YlArgs {
   const T* y_old;             // y^{k}: the host swaps the y / y_old buffers instead of copying (update_y_l.jl:64)
   T* s;                       // reduction-type projectors: s = A x is stored by pass 1 only when somebody reads it later
   int store_s;                //   (the feasibility check of every 10th iteration); pass 2 recomputes it from x
+  int skip_v;                 // pass 1 of an l1 set: do not store v (pass 2 recomputes it; the threshold search only reads
+                              //   v when the ball is active — a gated second launch of pass 1 then writes it)
+  const double* gate;         // gated launch of pass 1: return at once when (T)gate[0] <= (T)gate_tau (sum|v| <= tau: the
+  double gate_tau;            //   vector lies inside the l1 ball, project_l1_Duchi!.jl:23, nobody will read v)
   T* lhat0; T* s0; T* l0; T* y0;   // snapshots of the adaptation scheme
   T rho, gamma;
   const T* x_old;    // distance term only: also reduce the stop sums ||x-m||^2, ||x_old-x||^2, ||x||^2 (PARSDMM.jl:140-145)
@@ -968,7 +972,7 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
         if (spec) spec_hist_add<T>(*spec, v);                      // k_yl_spec only
       }
     }
-    store_n<T, W>(a.y + r0, yn);
+    if (MODE == 0 || !a.skip_v) store_n<T, W>(a.y + r0, yn);
     if (MODE == 0) store_n<T, W>(a.l + r0, ln);
     else if (a.store_s) store_n<T, W>(a.s + r0, s);
     if (MODE == 0 && PK == SIPB_SET_DISTANCE) {
@@ -990,7 +994,9 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
     }
   } else {
     T v[W];
-    load_n<T, W>(a.y + r0, v);
+    // the l1 ball never changes v in place: pass 2 recomputes it like s (same expressions as pass 1, bit for bit)
+    constexpr bool kRecomputeV = (PK == SIPB_SET_L1);
+    if (!kRecomputeV) load_n<T, W>(a.y + r0, v);
     // s = A x again (the same left fold as in pass 1, bit for bit): a gather of N words from x instead of a stored
     // and re-read M-vector (M = 3N for the TV sets)
     op_forward_n<T, W>(a.op, (unsigned)r0, a.x, s);
@@ -998,6 +1004,11 @@ __device__ __forceinline__ void yl_rows(const YlArgs<T>& a, const ProjDev<T>& P,
     if (relaxed || ADAPT) load_n<T, W>(a.y_old + r0, yo);
 #pragma unroll
     for (int e = 0; e < W; ++e) {
+      if (kRecomputeV) {
+        T xh = s[e];
+        if (relaxed) xh = gamma * s[e] + ((T)1.0 - gamma) * yo[e];     // update_y_l.jl:72
+        v[e] = xh - lo[e] * rho1;                                         // :67 / :74
+      }
       yn[e] = proj_apply<T, PK>(P, v[e], r0 + e);
       const T rp = -s[e] + yn[e];
       if (relaxed) {
@@ -1085,6 +1096,7 @@ __device__ __forceinline__ void yl_body(const YlArgs<T>& a, const RedScratch& rs
 
 template <typename T, int MODE, bool ADAPT>
 __global__ void __launch_bounds__(kThreads, 4) k_yl(const __grid_constant__ YlArgs<T> a, RedScratch rs, double* out) {
+  if (MODE == 1 && a.gate && (T)a.gate[0] <= (T)a.gate_tau) return;      // gated pass 1: v is not needed
   // one dispatch on the set kind per block: the common kinds run fully specialised bodies
   if (MODE == 2 && a.P.kind == SIPB_SET_L1) yl_body<T, MODE, ADAPT, SIPB_SET_L1>(a, rs, out);
   else yl_body<T, MODE, ADAPT, -1>(a, rs, out);

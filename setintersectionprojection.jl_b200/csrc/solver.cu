@@ -159,6 +159,8 @@ struct sipb_ctx {
   unsigned long long* d_tie_base = nullptr;   // [kMaxBlocks] exclusive prefix of d_tie_counts (deferred tie handling)
   unsigned int* d_sel_table = nullptr;   // [max_grid()][kSelBins] per-block histograms of the last select level (tie counts)
   bool sel_spec = true;                  // speculative select levels inside pass 1 of the y/l update (SIPB_SEL_SPEC=0: off)
+  int l1_skipv = 1;                      // l1 sets: pass 1 skips the store of v while the ball is inactive (SIPB_L1_SKIPV=0: never,
+                                         //   2: always — the gated launch then materialises v whenever the ball is active)
   unsigned int* d_counter2 = nullptr;
   int rank = 0, world = 1;
   ncclComm_t comm = nullptr;
@@ -1131,6 +1133,7 @@ struct SetT {
   DevBuf<double> warm;        // [2] warm-start thresholds (y-update, feasibility)
   bool z_halo = false;        // slabs: y, l, y_old have a halo plane in front (D_z block)
   int l1_last[2] = {5, 5};    // Newton passes the last l1 threshold search needed (y-update / feasibility)
+  bool l1_inactive_prev = false;   // l1 set: the last y-update found sum|v| <= tau (guess for the next pass 1, see skip_v)
   std::map<std::array<const void*, 4>, LoopGraph> l1_graphs;   // device-side search loops, one per (vector, stats, warm, params)
   ~SetT() { for (auto& kv : l1_graphs) kv.second.destroy(); }
 };
@@ -2382,15 +2385,32 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         ya.store_s = (want_feas && !S.is_sparse) ? 1 : 0;
         // vector-mode cardinality on one GPU: the first levels of the radix select ride on pass 1 (k_yl_spec)
         const bool spec = S.desc.set_kind == SIPB_SET_CARDINALITY && !sg.on && c->sel_spec;
+        // l1 ball on one GPU: pass 2 recomputes v, so pass 1 need not store it while the ball is inactive (the previous
+        // iteration's sum|v| <= tau is the guess; a wrong guess costs the gated launch below, never the result)
+        if (S.desc.set_kind == SIPB_SET_L1 && !sg.on && (c->l1_skipv == 2 || (c->l1_skipv == 1 && S.l1_inactive_prev)))
+          ya.skip_v = 1;
         if (spec)
           LAUNCH(c, KC_YL_PASS1, (k_yl_spec<T>), c->grid_fit((const void*)k_yl_spec<T>, nvecM), ya, c->rs,
                  c->d_scal + base + 10, &c->d_sel->spec_above, c->d_sel->spec, (const ProjParams<T>*)S.pp_y.p);
         else
           LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), c->grid_fit((const void*)k_yl<T, 1, false>, nvecM), ya, c->rs,
                  c->d_scal + base + 10);
+        if (ya.skip_v) {
+          // v was not stored: the threshold search reads it only when sum|v| > tau.  A second launch of pass 1, gated on the
+          // device by that test (the statistics are in place), writes it then; it returns at once otherwise.
+          YlArgs<T> yb = ya;
+          yb.skip_v = 0;
+          yb.store_s = 0;
+          yb.gate = c->d_scal + base + 10;
+          yb.gate_tau = (double)(T)S.desc.max;
+          LAUNCH(c, KC_YL_PASS1, (k_yl<T, 1, false>), c->grid_fit((const void*)k_yl<T, 1, false>, nvecM), yb, c->rs,
+                 c->d_scal + base + 13);
+        }
         // pass 1: x, l (, y_old) -> v (, s);   pass 2: v, x, l (, y_old) -> y, l
-        c->account(KC_YL_PASS1, colsB + (2 + (!(gamma[s] == (T)1) ? 1 : 0) + ya.store_s) * rowsB);
-        c->account(KC_YL_PASS2, colsB + (4 + (needs_yold ? 1 : 0)) * rowsB + adaptB);
+        // (an l1 set's pass 2 recomputes v instead of reading it; pass 1 skips the store while the ball is inactive)
+        const int l1set = S.desc.set_kind == SIPB_SET_L1 ? 1 : 0;
+        c->account(KC_YL_PASS1, colsB + (2 - ya.skip_v + (!(gamma[s] == (T)1) ? 1 : 0) + ya.store_s) * rowsB);
+        c->account(KC_YL_PASS2, colsB + (4 - l1set + (needs_yold ? 1 : 0)) * rowsB + adaptB);
         i64 tie_chunk = 0;
         const bool defer = S.desc.set_kind == SIPB_SET_CARDINALITY && !sg.on && c->sel_spec;
         int rc = projector_params(S, S.y.p, base + 10, S.pp_y.p, S.warm.p, true, spec, defer ? &tie_chunk : nullptr);
@@ -2442,6 +2462,8 @@ int Problem<T>::solve(const void* m_h, void* x_h, void* const* l_h, void* const*
         const int base = s * kSlotPerSet;
         const T rp = (T)std::sqrt(c->h_scal[base + 0]);            // update_y_l.jl:81
         LG(log->r_pri, i - 1, s, p_log) = (double)rp;
+        if (sets[s]->desc.set_kind == SIPB_SET_L1 && !sg.on)       // k_l1_begin's test on this iteration's sum|v|
+          sets[s]->l1_inactive_prev = (T)c->h_scal[base + 10] <= (T)sets[s]->desc.max;
         rp_tot = rp_tot + rp;
         if (!fuse_rdual) {
           const T rd = rho[s] * (T)std::sqrt(c->h_scal[base + 3]);   // :84
@@ -2656,6 +2678,7 @@ int sipb_ctx_create(int device, sipb_ctx** out) {
   SIPB_CUDA_CHECK(cudaMalloc(&c->d_tie_base, sizeof(unsigned long long) * kMaxBlocks));
   SIPB_CUDA_CHECK(cudaMalloc(&c->d_sel_table, sizeof(unsigned int) * (size_t)kMaxBlocks * kSelBins));
   if (const char* e = getenv("SIPB_SEL_SPEC")) c->sel_spec = atoi(e) != 0;
+  if (const char* e = getenv("SIPB_L1_SKIPV")) c->l1_skipv = atoi(e);
   *out = c;
   return SIPB_OK;
 }
