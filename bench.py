@@ -20,7 +20,7 @@ Device arm (default):
   config2    BASELINE configs[1] (200^3 Float32, bounds ∩ anisotropic TV ∩ lateral slope bounds) on the same N GPUs:
              value, e2e and FULL-SIZE parity against the CPU oracle (x, iteration count, CG iteration counts)
   parity     configs[2] against the CPU oracle on a reduced grid (the oracle's sparse set-up of 512^3 alone takes
-             minutes; tools/parity_fullsize.py runs larger grids, logs under profiles/)
+             minutes; tests/checks/parity_fullsize.py runs larger grids, logs under profiles/)
   cpu_baseline  N=1: the threaded C/OpenMP restatement of the reference algorithm on the box's host cores, bounded
              sample: the first iterations of a sub-volume of the same workload (see `sample`)
 Reference arm (--impl reference): the CPU restatement alone (Julia is not installable here), same metric / config,
@@ -438,7 +438,7 @@ def run_device(args, rank, world, local_rank):
                     "grid": list(pg), "maxit": pmaxit, "rel_l2": relerr(xg, xo), "iters_equal": len(ls.obj) == len(lo.obj),
                     "cg_it_equal": bool(np.array_equal(ls.cg_it, lo.cg_it)), "iterations": len(ls.obj),
                     "note": "same workload and options on a reduced grid against the CPU oracle (the oracle's sparse set-up "
-                            "of the full grid takes minutes; profiles/ holds full-size runs of tools/parity_fullsize.py)"}
+                            "of the full grid takes minutes; profiles/ holds full-size runs of tests/checks/parity_fullsize.py)"}
             del pp_
         except Exception as e:       # noqa: BLE001
             parity[args.workload + "_reduced"] = {"error": str(e)[:300]}

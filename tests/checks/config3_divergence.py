@@ -3,13 +3,13 @@
 NumPy oracle, iteration by iteration (obj, r_pri, rho) and the supports of the cardinality set's y at the end — the
 measurement quoted in tests/test_gpu_parity.py::test_config3_128cubed_f32 and DESIGN.md §7.  Needs a GPU.
 
-  python tools/config3_divergence.py [n=128]
+  python tests/checks/config3_divergence.py [n=128]
 """
 import copy
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

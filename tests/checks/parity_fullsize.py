@@ -2,7 +2,7 @@
 """Parity of the device path against the CPU oracle (threaded C/OpenMP port) at grid sizes beyond what the test-suite
 runs: BASELINE configs[2] (bounds ∩ TV l1 ∩ cardinality of the gradient) at --size^3 for --iters PARSDMM iterations.
 The oracle's sparse set-up and stable sorts dominate the run time (minutes at 256^3).  One JSON line per run; keep the
-output under profiles/.   python tools/parity_fullsize.py --size 256 --iters 12"""
+output under profiles/.   python tests/checks/parity_fullsize.py --size 256 --iters 12"""
 import argparse
 import copy
 import json
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

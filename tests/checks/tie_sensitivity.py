@@ -8,13 +8,13 @@ hence the support — depends on the last ulp of the reductions: the three CPU r
 with Float64-accumulated reductions, with NumPy's native reductions, and the C/OpenMP port) disagree with EACH OTHER.
 This script prints, per iteration count, whether they end in the same support.  CPU only (oracle/ is test infrastructure).
 
-  python tools/tie_sensitivity.py [maxit ...]          default: 2 3 4 8
+  python tests/checks/tie_sensitivity.py [maxit ...]          default: 2 3 4 8
 """
 import copy
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402

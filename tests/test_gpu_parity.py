@@ -917,7 +917,7 @@ def test_parsdmm_cardinality_ties_in_the_loop(sip, orc, TF, n, frac, seed):
     levels in pass 1, per-chunk tie prefix applied by pass 2, the chunk on the quota boundary settled in place).
     Two iterations only: from iteration 3 on, classes that are EQUAL in exact arithmetic are ordered by rounding, and the
     CPU restatements themselves (NumPy f64acc / native reductions, C port) end in different supports
-    (tools/tie_sensitivity.py) — nothing to compare against."""
+    (tests/checks/tie_sensitivity.py) — nothing to compare against."""
     rng = np.random.default_rng(seed)
     N = int(np.prod(n))
     m = np.round(rng.standard_normal(N) * 3).astype(TF)
@@ -935,10 +935,10 @@ def test_parsdmm_cardinality_ties_in_the_loop(sip, orc, TF, n, frac, seed):
 
 def test_config3_128cubed_f32(sip, orc):
     """BASELINE configs[2] (bounds ∩ TV l1 ∩ cardinality of the gradient) at 128^3, 30 iterations (the CPU oracle's
-    sparse set-up and stable sort of 512^3 take tens of minutes; tools/parity_fullsize.py runs larger grids).
+    sparse set-up and stable sort of 512^3 take tens of minutes; tests/checks/parity_fullsize.py runs larger grids).
 
     The cardinality set is non-convex: an entry whose magnitude sits at the k-th largest value flips in or out of the
-    support on a one-ulp change of its input.  Measured at this size (tools/config3_divergence.py): device and CPU runs are
+    support on a one-ulp change of its input.  Measured at this size (tests/checks/config3_divergence.py): device and CPU runs are
     BIT-IDENTICAL in every logged scalar for 15 iterations; at iteration 16 one rho differs by one ulp (an adaptation
     sum rounds differently) and the supports drift apart.  After 30 iterations x differs by 1.20e-3 (device vs the
     C/OpenMP port), 1.13e-3 (device vs the NumPy oracle) and 0.91e-3 (the two CPU restatements AGAINST EACH OTHER),
