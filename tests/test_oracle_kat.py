@@ -210,6 +210,65 @@ def test_cg():
     assert flag == -9 and it0 == 0 and not x.any()               # cg.jl:47
 
 
+# ---- test/test_rhs_compose.jl:5-36 (serial branches; the formula rhs_compose.jl:24-36 is the spec) -------------
+def test_rhs_compose():
+    rng = np.random.default_rng(16)
+    TF = np.float64
+    y = [rng.standard_normal(5100), rng.standard_normal(10000)]
+    l = [rng.standard_normal(5100), rng.standard_normal(10000)]
+    rho = np.array([1.234, 10.23432])
+    TD = [sp.eye(5100, 10000, format="csc", dtype=TF) * 2.0, sp.eye(10000, format="csc", dtype=TF)]
+    rhs = rng.standard_normal(10000)                              # overwritten, as in the reference test
+    par.rhs_compose(rhs, l, y, rho, TD, 2)
+    want = np.zeros(10000)
+    want[:5100] += 2.0 * (rho[0] * y[0] + l[0])
+    want += rho[1] * y[1] + l[1]
+    assert np.allclose(rhs, want, rtol=10 * np.finfo(TF).eps, atol=0)       # test_rhs_compose.jl:36 (rtol 10 eps)
+
+
+# ---- test/test_argmin_x.jl:39-63 (CDS branch) -------------------------------------------------------
+def _spd_system(rng, n=100):
+    A = sp.random(n, n, density=0.01, random_state=np.random.RandomState(int(rng.integers(1 << 30))), data_rvs=rng.standard_normal) \
+        + sp.eye(n)
+    A = sp.csc_matrix(A.T @ A)
+    while np.linalg.matrix_rank(A.toarray()) < n:
+        A = sp.csc_matrix(A + sp.eye(n))
+    xt = rng.standard_normal(n)
+    return A, xt, A @ xt
+
+
+@pytest.mark.parametrize("tol", [1e-5, 1e-10])
+def test_argmin_x_cds(tol):
+    rng = np.random.default_rng(17)
+    A, xt, b = _spd_system(rng)
+    R, off = ops.mat2CDS(A)
+    x, it, relres, tol_used = par.argmin_x(R, b, np.zeros(100), tol, 5, off)     # i = 5 >= 3: min(rule, given tolerance)
+    assert tol_used <= tol
+    res = np.linalg.norm(A @ x - b) / np.linalg.norm(b)
+    assert res <= tol and res <= 2.0 * relres                                  # test_argmin_x.jl:52-53,60-61
+
+
+def test_argmin_x_tolerance_rule():
+    """argmin_x.jl:33-36: tol = max(0.1 ||Qx - rhs|| / ||rhs||, 10 eps); the first two iterations take it as is, later
+    ones never loosen it; a good starting guess needs fewer CG iterations (test_argmin_x.jl:26-30)."""
+    rng = np.random.default_rng(18)
+    A, xt, b = _spd_system(rng)
+    R, off = ops.mat2CDS(A)
+    x0 = xt + rng.standard_normal(100) * 1e-4
+    want = 0.1 * np.linalg.norm(A @ x0 - b) / np.linalg.norm(b)
+    _, it_good, _, tol1 = par.argmin_x(R, b, x0.copy(), 1e-12, 1, off)
+    assert np.isclose(tol1, want, rtol=1e-12)                                  # i < 3: the reference tolerance is ignored
+    _, _, _, tol5 = par.argmin_x(R, b, x0.copy(), 1e-12, 5, off)
+    assert tol5 == 1e-12
+    _, it_zero, _, tolz = par.argmin_x(R, b, np.zeros(100), 1.0, 5, off)
+    assert np.isclose(tolz, 0.1, rtol=1e-12)                                   # x = 0: ratio is exactly 0.1
+    _, it_tight, _, _ = par.argmin_x(R, b, np.zeros(100), 1e-5, 5, off)
+    _, it_tight_good, _, _ = par.argmin_x(R, b, x0.copy(), 1e-5, 5, off)
+    assert it_tight_good < it_tight
+    _, _, _, tole = par.argmin_x(R, b, xt.copy(), 1.0, 5, off)
+    assert tole >= 10 * np.finfo(np.float64).eps                               # floor of the rule
+
+
 # ---- test/test_update_y_l.jl:56-87 (formulas are the spec) -----------------------------------------
 def test_update_y_l_formulas():
     TF = np.float64
