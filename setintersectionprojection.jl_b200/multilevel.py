@@ -34,10 +34,15 @@ def _nearest_table(n_src: int, n_dst: int) -> np.ndarray:
 
 def resample_nn(v: np.ndarray, shape_src, shape_dst) -> np.ndarray:
     """Nearest-neighbour resampling of vec(A) (column-major) from shape_src to shape_dst."""
-    A = np.reshape(v, tuple(int(s) for s in shape_src), order="F")
-    for axis, (ns, nd) in enumerate(zip(shape_src, shape_dst)):
-        A = np.take(A, _nearest_table(int(ns), int(nd)), axis=axis)
-    return np.ascontiguousarray(A.ravel(order="F"))
+    src = tuple(int(s) for s in shape_src)
+    dst = tuple(int(s) for s in shape_dst)
+    # the column-major box seen as a C-ordered array with the axes reversed: every `take` then copies contiguous runs
+    # (slowest axis first, the gather along the fastest axis last, on the already reduced array) — 5-10x faster at 400^3
+    # than taking along the axes of the Fortran-ordered view, same elements
+    A = np.reshape(np.ascontiguousarray(v), src[::-1])
+    for axis, (ns, nd) in enumerate(zip(src[::-1], dst[::-1])):
+        A = np.take(A, _nearest_table(ns, nd), axis=axis)
+    return np.ascontiguousarray(A.ravel())
 
 
 def constraint2coarse(constraint, comp_grid, coarsening_factor):

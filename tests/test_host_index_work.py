@@ -202,6 +202,11 @@ def test_nearest_neighbour_tables_and_resampling(sip):
     for dst in ((12, 10, 8), (3, 3, 2), (6, 5, 4)):
         assert np.array_equal(sip.resample_nn(v, (6, 5, 4), dst), om.resample(v, (6, 5, 4), dst))
     assert np.array_equal(sip.resample_nn(v, (6, 5, 4), (6, 5, 4)), v)
+    for src, dst in (((7, 9), (14, 17)), ((14, 17), (7, 9)), ((5, 6, 7), (11, 3, 7)), ((9,), (4,)), ((4, 1, 5), (8, 1, 3))):
+        w = rng.standard_normal(int(np.prod(src)))
+        assert np.array_equal(sip.resample_nn(w, src, dst), om.resample(w, src, dst))
+        w2 = rng.standard_normal(2 * int(np.prod(src)))[::2]                    # strided input
+        assert np.array_equal(sip.resample_nn(w2, src, dst), om.resample(np.ascontiguousarray(w2), src, dst))
 
 
 def test_multilevel_setup_matches_oracle(sip):
